@@ -1,0 +1,316 @@
+#!/usr/bin/env python
+"""bench.py -- LM iterations/s of the joint-optimisation hot path (BASELINE.json metric).
+
+  python bench.py --gpus N --steps K --warmup W            this repo's CUDA path
+  python bench.py --impl reference --gpus N --steps K ...  the reference's CPU algorithm
+                                                           (oracle port; the reference itself
+                                                           cannot be built here)
+
+One "step" = one LM iteration = one call of OptimizeJointly(max_iteration_count=1): one H/b
+build over all observations, >= 1 Schur solve, >= 1 trial-cost pass.
+Workload: BASELINE config 2 -- central-generic B-spline camera 2050x1450 (84x60 grid, 10 080
+intrinsics), 500 imagesets, 2 000 pattern points, ~0.95 M observations, seed 2, synthetic.
+Under torchrun the imagesets are sharded over the ranks (strong scaling: the problem is fixed).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+BYTES_PER_OBS = {0: 720, 1: 1488, 3: 400}  # algorithmic bytes of the Jacobian kernel (C = 1)
+
+
+def _peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, index: int):
+        self.index = index
+        self.samples = []
+        self.reasons = set()
+        self._stop = threading.Event()
+        self._t = None
+
+    def _run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i",
+                                      str(self.index)], capture_output=True, text=True, timeout=5).stdout.strip()
+                f = [v.strip() for v in out.split(",")]
+                self.samples.append((float(f[0]), float(f[1])))
+                for n, v in zip(names, f[2:]):
+                    if v.lower().startswith("active"):
+                        self.reasons.add(n)
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def start(self):
+        self._t = threading.Thread(target=self._run, daemon=True)
+        self._t.start()
+
+    def stop(self):
+        self._stop.set()
+        if self._t:
+            self._t.join(timeout=6)
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        sm = sorted(s[0] for s in self.samples)
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(s[1] for s in self.samples),
+                "reasons": sorted(self.reasons), "samples": len(sm)}
+
+
+def make_workload(args):
+    from camera_calibration_b200 import synthetic
+    kw = {}
+    if args.imagesets:
+        kw["n_imagesets"] = args.imagesets
+    sp = synthetic.make_problem(args.config, **kw)
+    return sp
+
+
+def cpu_baseline(sp, opt_numeric, budget_s=20.0, verbose=False):
+    """Single-threaded CPU port of the reference (numeric Jacobian) on a bounded sample, scaled
+    to one full LM iteration = 1 Compute<true> + 1 Schur solve + 1 Compute<false>."""
+    from oracle import oracle
+    p = sp.problem
+    n_upd = sum(c.update_parameter_count() for c in p.cameras)
+    nd = 6 * p.n_imagesets + (6 * p.n_cameras if p.n_cameras > 1 else 0) + n_upd
+    nbd = 3 * p.n_points
+    # 1) Jacobian + accumulation on a few imagesets
+    k = max(1, min(p.n_imagesets, 2))
+    t_j = oracle.time_jacobian(p, sp.init_state, opt_numeric, 0, k, True)
+    per = t_j / k
+    k2 = int(max(k, min(p.n_imagesets, (0.45 * budget_s) / max(per, 1e-9))))
+    if k2 > k:
+        t_j = oracle.time_jacobian(p, sp.init_state, opt_numeric, 0, k2, True)
+        k = k2
+    obs_frac = float(np.sum(p.obs_imageset < k)) / max(1, p.n_obs)
+    t_jac_full = t_j / max(obs_frac, 1e-12)
+    t_r = oracle.time_jacobian(p, sp.init_state, opt_numeric, 0, k, False)
+    t_res_full = t_r / max(obs_frac, 1e-12)
+    # 2) B^T D^-1 B on a column slice (cost ~ n_cols^2 / 2 * nbd)
+    nc = int(min(nd, 1200))
+    t_c = oracle.time_contraction(nbd, nc)
+    t_con_full = t_c * (nd / nc) ** 2
+    # 3) pivoted LDLT (cost ~ n^3 / 3)
+    nl = int(min(nd, 1800))
+    t_l = oracle.time_ldlt(nl)
+    t_ldlt_full = t_l * (nd / nl) ** 3
+    total = t_jac_full + t_res_full + t_con_full + t_ldlt_full
+    sample = (f"Compute<true> on {k} of {p.n_imagesets} imagesets ({t_j:.1f}s), Compute<false> on the same ({t_r:.1f}s), "
+              f"B^T D^-1 B on {nc} of {nd} dense columns ({t_c:.1f}s, x(nd/nc)^2), pivoted LDLT at n={nl} of {nd} "
+              f"({t_l:.1f}s, x(nd/n)^3); single thread like the reference")
+    return {"value": 1.0 / total, "unit": "LM iterations/s", "cores": 1, "kind": "port", "sample": sample,
+            "seconds_per_iteration_est": total,
+            "breakdown_s": {"jacobian": t_jac_full, "residual": t_res_full, "contraction": t_con_full, "ldlt": t_ldlt_full}}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    from camera_calibration_b200 import cabi
+    from oracle import oracle
+    oracle.build()
+    sp = make_workload(args)
+    opt = cabi.default_options(jacobian_mode=cabi.JACOBIAN_NUMERIC)
+    steps = max(1, args.steps)
+    vals = []
+    base = None
+    for i in range(args.warmup + steps):
+        base = cpu_baseline(sp, opt, budget_s=args.cpu_budget / max(1, (min(args.warmup, 1) + steps)))
+        if i >= args.warmup:
+            vals.append(base["seconds_per_iteration_est"])
+        if i == 0 and args.warmup > 1:
+            args.warmup = 1  # one untimed pass is enough for a CPU code path
+    sec = float(np.mean(vals))
+    val = 1.0 / sec
+    line = {
+        "impl": "reference", "metric": "LM iterations/sec", "value": val, "unit": "LM iterations/s",
+        "n_gpus": args.gpus, "steps": steps, "warmup": args.warmup, "ms_per_step": 1e3 * sec,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(sp, args, 1),
+        "cpu_baseline": {k: base[k] for k in ("unit", "cores", "kind", "sample")} | {"value": val},
+        "e2e": {"value": val, "unit": "LM iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+def workload_config(sp, args, world):
+    c = sp.problem.cameras[0]
+    return {"workload": f"BASELINE config {args.config}: " + {1: "CentralOpenCV 12-param", 2: "central-generic B-spline",
+                                                              3: "noncentral-generic B-spline", 4: "2x central-generic rig",
+                                                              5: "4x central-generic rig"}[args.config],
+            "n_obs": sp.n_obs, "n_imagesets": sp.problem.n_imagesets, "n_points": sp.problem.n_points,
+            "n_cameras": sp.problem.n_cameras, "grid": [c.grid_width, c.grid_height],
+            "intrinsic_unknowns": sum(cc.update_parameter_count() for cc in sp.problem.cameras), "seed": sp.seed,
+            "options": "eliminate_points=1 localize_only=0 huber=1 max_lm_attempts=50 init_lambda=-1",
+            "parallelism": f"imageset-sharded x{world}" if world > 1 else "single GPU",
+            "l2": "inputs larger than L2 (J 0.6 GB, B 0.6 GB, C 1.4 GB per step >> 126 MB)"}
+
+
+def run_b200(args):
+    import torch
+    from camera_calibration_b200 import api, cabi, distributed
+    rank, world, local = distributed.env_rank_world()
+    dist = None
+    if world > 1:
+        dist = distributed.init_process_group("nccl")
+    torch.cuda.set_device(local)
+    sp = make_workload(args)
+    opt = cabi.default_options(max_iteration_count=1)
+    if world > 1:
+        adj, idx = distributed.make_sharded_adjuster(sp.problem)
+        state0 = distributed.shard_state(sp.init_state, idx)
+    else:
+        adj = api.BundleAdjuster(sp.problem, local)
+        state0 = sp.init_state.copy()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    W, K = max(3, args.warmup), max(1, args.steps)
+    sampler = ClockSampler(local)
+
+    # ---- device-resident: the state stays in HBM between steps ---------------------------------
+    adj.set_state(state0)
+    lam = -1.0
+    for _ in range(W):
+        opt.init_lambda = lam
+        rep = adj.optimize(opt)
+        lam = rep.final_lambda
+    barrier()
+    sampler.start()
+    t0 = time.perf_counter()
+    dev_ms = 0.0
+    jac_ms, jac_n, launches = 0.0, 0, 0
+    phases = {"jacobian": 0.0, "accumulate": 0.0, "schur": 0.0, "factor": 0.0, "trial": 0.0, "update": 0.0, "allreduce": 0.0}
+    costs = []
+    for _ in range(K):
+        opt.init_lambda = lam
+        rep = adj.optimize(opt)
+        lam = rep.final_lambda
+        t = adj.timings()
+        dev_ms += t.total_ms
+        jac_ms += t.jacobian_kernel_ms
+        jac_n += t.jacobian_kernel_launches
+        launches += t.kernel_launches
+        for k, v in (("jacobian", t.jacobian_kernel_ms), ("accumulate", t.accumulate_ms), ("schur", t.schur_ms),
+                     ("factor", t.factor_ms), ("trial", t.trial_cost_ms), ("update", t.update_ms), ("allreduce", t.allreduce_ms)):
+            phases[k] += v / K
+        costs.append(rep.final_cost)
+    barrier()
+    wall_ms = 1e3 * (time.perf_counter() - t0)
+    clocks = sampler.stop()
+    rmse = rep.rmse
+
+    # ---- end to end: host buffers in, host buffers out, every step (b200ba_optimize_host) --------
+    st = state0.copy()
+    lam2 = -1.0
+    for _ in range(W):
+        opt.init_lambda = lam2
+        rep2 = adj.optimize_host(st, opt)
+        lam2 = rep2.final_lambda
+    barrier()
+    t1 = time.perf_counter()
+    for _ in range(K):
+        opt.init_lambda = lam2
+        rep2 = adj.optimize_host(st, opt)
+        lam2 = rep2.final_lambda
+    barrier()
+    e2e_ms = 1e3 * (time.perf_counter() - t1)
+    state_bytes = 8 * (st.points.size + st.rig_tr_global.size + st.camera_tr_rig.size + sum(a.size for a in st.intrinsics)
+                       + st.last_projection.size)
+
+    # max over ranks
+    if dist is not None:
+        tt = torch.tensor([dev_ms, wall_ms, e2e_ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dev_ms, wall_ms, e2e_ms = [float(v) for v in tt.tolist()]
+    ms_per_step = max(dev_ms, 0.0) / K
+    value = 1e3 / ms_per_step
+    peak, peak_src = _peaks()
+    n_local = adj.problem.n_obs
+    model = sp.problem.cameras[0].model_type
+    bpo = BYTES_PER_OBS.get(model, 720) + (96 if sp.problem.n_cameras > 1 else 0)
+    jac_avg_ms = jac_ms / max(1, jac_n)
+    achieved = n_local * bpo / (jac_avg_ms * 1e-3) / 1e9 if jac_avg_ms > 0 else 0.0
+    traffic = None
+    prof = os.path.join(ROOT, "profiles", "jacobian_kernel_latest.json")
+    if os.path.exists(prof):
+        try:
+            traffic = json.load(open(prof)).get("dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+
+    if rank == 0:
+        line = {
+            "metric": "LM iterations/sec", "value": value, "unit": "LM iterations/s", "n_gpus": world, "steps": K,
+            "warmup": W, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(sp, args, world),
+            "wall_ms_per_step": wall_ms / K, "final_cost": costs[-1], "rmse_px": rmse,
+            "phases_ms_per_step": phases,
+            "roofline": {"kernel": "residual_jacobian_kernel", "bound": "hbm", "achieved": achieved, "peak": peak,
+                         "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                         "algorithmic_bytes_per_obs": bpo, "obs_per_launch": n_local, "avg_launch_ms": jac_avg_ms},
+            "e2e": {"value": 1e3 / (e2e_ms / K), "unit": "LM iterations/s", "h2d_bytes_per_step": int(state_bytes),
+                    "d2h_bytes_per_step": int(state_bytes), "ms_per_step": e2e_ms / K},
+            "gpu_launches": int(launches), "clocks": clocks,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            from oracle import oracle
+            oracle.build()
+            optn = cabi.default_options(jacobian_mode=cabi.JACOBIAN_NUMERIC)
+            line["cpu_baseline"] = cpu_baseline(sp, optn, budget_s=args.cpu_budget)
+        print(json.dumps(line))
+    adj.close()
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--config", type=int, default=2)
+    ap.add_argument("--imagesets", type=int, default=0, help="shrink the workload (debugging only)")
+    ap.add_argument("--cpu-budget", type=float, default=20.0, help="seconds of CPU work for the bounded baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_b200(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

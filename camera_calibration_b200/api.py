@@ -1,0 +1,630 @@
+"""Host-side mirror of the reference interface of the bundle-adjustment path.
+
+Same names, argument meaning and error behaviour as the reference
+(applications/camera_calibration/src/camera_calibration/, "APP" below):
+
+  CameraModel, CentralGenericModel, NoncentralGenericModel, CentralOpenCVModel
+      APP/models/camera_model.h:42-204, central_generic.h, noncentral_generic.h, central_opencv.h
+  PointFeature, Imageset, Dataset      APP/dataset.h:57-212
+  BAState                              APP/bundle_adjustment/ba_state.h:46-97
+  SchurMode, OptimizeJointly           APP/bundle_adjustment/joint_optimization.h:38-70
+  OptimizationReport, CudaOptimizeJointly   libvis lm_optimizer.h:55-77, cuda_joint_optimization.h:45-59
+
+Everything numerical happens in ``libb200ba.so`` (hand-written sm_100a kernels) through the C
+ABI of ``include/b200ba.h``; this module only flattens the containers into the POD structs of
+that ABI and back. There is no CPU fallback: without the built library / a CUDA device the
+calls raise.
+
+Poses are numpy rows ``(qw, qx, qy, qz, tx, ty, tz)`` (the reference's SE3d; Eigen stores
+quaternion coefficients as x, y, z, w -- the conversion belongs to the C++ shim).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import enum
+from dataclasses import dataclass
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import cabi
+from .cabi import Camera, FlatProblem, FlatState, Options, Report
+
+
+class B200BAError(RuntimeError):
+    pass
+
+
+def _check(rc: int, handle=None):
+    if rc != 0:
+        lib = cabi.load_library()
+        msg = lib.b200ba_last_error(handle)
+        raise B200BAError(f"libb200ba error {rc}: {msg.decode() if msg else ''}")
+
+
+# ---------------------------------------------------------------------------------------
+# thin, explicit wrapper of the handle (used by tests, bench and OptimizeJointly below)
+# ---------------------------------------------------------------------------------------
+class BundleAdjuster:
+    """Owns a ``b200ba_handle``: the problem and the state stay resident on the device."""
+
+    def __init__(self, problem: FlatProblem, device: int = -1):
+        self.lib = cabi.load_library()
+        self.problem = problem
+        self._h = C.c_void_p()
+        rc = self.lib.b200ba_create(C.byref(problem.c_struct()), device, C.byref(self._h))
+        if rc != 0:
+            raise B200BAError(f"b200ba_create failed ({rc}): {self.lib.b200ba_last_error(None).decode()}")
+
+    def close(self):
+        if self._h:
+            self.lib.b200ba_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def set_state(self, state: FlatState):
+        state.check(self.problem)
+        cs = state.c_struct()
+        _check(self.lib.b200ba_set_state(self._h, C.byref(cs)), self._h)
+
+    def get_state(self, like: Optional[FlatState] = None) -> FlatState:
+        p = self.problem
+        st = FlatState(np.zeros((p.n_points, 3)), np.zeros((p.n_imagesets, 7)), np.zeros((p.n_cameras, 7)),
+                       [np.zeros(c.intrinsics_size()) for c in p.cameras], np.zeros((p.n_obs, 2)))
+        cs = st.c_struct()
+        _check(self.lib.b200ba_get_state(self._h, C.byref(cs)), self._h)
+        return st
+
+    def optimize(self, opt: Options) -> Report:
+        rep = Report()
+        _check(self.lib.b200ba_optimize(self._h, C.byref(opt), C.byref(rep)), self._h)
+        return rep
+
+    def optimize_host(self, state: FlatState, opt: Options) -> Report:
+        """set_state + optimize + get_state with host buffers (one OptimizeJointly call)."""
+        state.check(self.problem)
+        if state.last_projection is None:
+            state.last_projection = np.zeros((self.problem.n_obs, 2))
+        rep = Report()
+        cs = state.c_struct()
+        _check(self.lib.b200ba_optimize_host(self._h, C.byref(cs), C.byref(opt), C.byref(rep)), self._h)
+        return rep
+
+    def evaluate(self, opt: Options, compute_jacobians: bool = False) -> Dict:
+        n = self.problem.n_obs
+        res = np.zeros((n, 2))
+        costs = np.zeros(n)
+        total = C.c_double(0)
+        _check(self.lib.b200ba_evaluate(self._h, C.byref(opt), int(compute_jacobians), _dp(res), _dp(costs),
+                                        C.byref(total)), self._h)
+        out = {"residuals": res, "costs": costs, "total_cost": total.value}
+        if compute_jacobians:
+            K = max(c.intrinsics_jacobian_size() for c in self.problem.cameras)
+            jp = np.zeros((n, 2, 3))
+            jo = np.zeros((n, 2, 6))
+            jr = np.zeros((n, 2, 6))
+            ji = np.zeros((n, 2, K))
+            ii = np.full((n, K), -1, dtype=np.int32)
+            _check(self.lib.b200ba_get_jacobians(self._h, _dp(jp), _dp(jo), _dp(jr), _dp(ji),
+                                                 ii.ctypes.data_as(C.POINTER(C.c_int32)), K), self._h)
+            out.update(j_point=jp, j_pose=jo, j_rig=jr, j_intr=ji, intr_index=ii)
+        return out
+
+    def degrees_of_freedom(self, opt: Options) -> int:
+        return int(self.lib.b200ba_degrees_of_freedom(self._h, C.byref(opt)))
+
+    def build_system(self, opt: Options):
+        n = self.degrees_of_freedom(opt)
+        H = np.zeros((n, n))
+        b = np.zeros(n)
+        cost = C.c_double(0)
+        _check(self.lib.b200ba_build_system(self._h, C.byref(opt), n, _dp(H), _dp(b), C.byref(cost)), self._h)
+        return H, b, cost.value
+
+    def timings(self) -> cabi.Timings:
+        t = cabi.Timings()
+        _check(self.lib.b200ba_get_timings(self._h, C.byref(t)), self._h)
+        return t
+
+    def comm_init(self, unique_id: bytes, rank: int, n_ranks: int):
+        buf = (C.c_uint8 * cabi.NCCL_UNIQUE_ID_BYTES).from_buffer_copy(unique_id)
+        _check(self.lib.b200ba_comm_init(self._h, buf, rank, n_ranks), self._h)
+
+
+def _dp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def nccl_unique_id() -> bytes:
+    lib = cabi.load_library()
+    buf = (C.c_uint8 * cabi.NCCL_UNIQUE_ID_BYTES)()
+    _check(lib.b200ba_nccl_unique_id(buf))
+    return bytes(buf)
+
+
+def schur_solve(block_size: int, D, B, Cm, b1, b2, device: int = -1) -> np.ndarray:
+    """SolveWithSchurComplementDenseOffDiag (libvis lm_optimizer.h:1246-1369) on the device."""
+    lib = cabi.load_library()
+    D = np.ascontiguousarray(D, dtype=np.float64)
+    B = np.ascontiguousarray(B, dtype=np.float64)
+    Cm = np.ascontiguousarray(Cm, dtype=np.float64)
+    b1 = np.ascontiguousarray(b1, dtype=np.float64)
+    b2 = np.ascontiguousarray(b2, dtype=np.float64)
+    nb, nd = D.shape[0], Cm.shape[0]
+    x = np.zeros(nb * block_size + nd)
+    _check(lib.b200ba_schur_solve(device, block_size, nb, nd, _dp(D), _dp(B), _dp(Cm), _dp(b1), _dp(b2), _dp(x)))
+    return x
+
+
+# ---------------------------------------------------------------------------------------
+# CameraModel plugin mirror
+# ---------------------------------------------------------------------------------------
+class CameraModel:
+    """APP/models/camera_model.h:42-204."""
+
+    class Type(enum.IntEnum):
+        CentralGeneric = 0
+        NoncentralGeneric = 1
+        CentralRadial = 4
+        CentralThinPrismFisheye = 2
+        CentralOpenCV = 3
+        InvalidType = 5
+
+    def __init__(self, width, height, calibration_min_x, calibration_min_y, calibration_max_x, calibration_max_y,
+                 type_):
+        self.m_width, self.m_height = int(width), int(height)
+        self.m_calibration_min_x, self.m_calibration_min_y = int(calibration_min_x), int(calibration_min_y)
+        self.m_calibration_max_x, self.m_calibration_max_y = int(calibration_max_x), int(calibration_max_y)
+        self.m_type = CameraModel.Type(type_)
+
+    # accessors of the reference
+    def width(self): return self.m_width
+    def height(self): return self.m_height
+    def calibration_min_x(self): return self.m_calibration_min_x
+    def calibration_min_y(self): return self.m_calibration_min_y
+    def calibration_max_x(self): return self.m_calibration_max_x
+    def calibration_max_y(self): return self.m_calibration_max_y
+    def type(self): return self.m_type
+
+    @staticmethod
+    def IsCentral(type_) -> bool:
+        return CameraModel.Type(type_) != CameraModel.Type.NoncentralGeneric and \
+            CameraModel.Type(type_) != CameraModel.Type.InvalidType
+
+    def IsInCalibratedArea(self, x, y) -> bool:
+        return (x >= self.m_calibration_min_x and y >= self.m_calibration_min_y and
+                x < self.m_calibration_max_x + 1 and y < self.m_calibration_max_y + 1)
+
+    def CenterOfCalibratedArea(self):
+        return np.array([0.5 * (self.m_calibration_min_x + self.m_calibration_max_x + 1),
+                         0.5 * (self.m_calibration_min_y + self.m_calibration_max_y + 1)])
+
+    def GetGridResolution(self):
+        return None
+
+    @staticmethod
+    def exterior_cells_per_side() -> int:
+        return 0
+
+    # to be provided by subclasses
+    IntrinsicsJacobianSize = 0
+
+    def update_parameter_count(self) -> int:
+        raise NotImplementedError
+
+    def duplicate(self):
+        raise NotImplementedError
+
+    def flat_intrinsics(self) -> np.ndarray:
+        raise NotImplementedError
+
+    def set_flat_intrinsics(self, a: np.ndarray):
+        raise NotImplementedError
+
+    def c_camera(self) -> Camera:
+        c = Camera()
+        c.model_type = int(self.m_type)
+        c.width, c.height = self.m_width, self.m_height
+        c.calibration_min_x, c.calibration_min_y = self.m_calibration_min_x, self.m_calibration_min_y
+        c.calibration_max_x, c.calibration_max_y = self.m_calibration_max_x, self.m_calibration_max_y
+        res = self.GetGridResolution()
+        c.grid_width, c.grid_height = res if res else (0, 0)
+        return c
+
+    # Project / Unproject run the device kernels (b200ba_project / b200ba_unproject)
+    def ProjectWithInitialEstimate(self, local_point, result):
+        """Returns (ok, pixel); ``result`` is the initial estimate."""
+        lib = cabi.load_library()
+        lp = np.ascontiguousarray(local_point, dtype=np.float64).reshape(1, 3)
+        px = np.ascontiguousarray(result, dtype=np.float64).reshape(1, 2).copy()
+        ok = np.zeros(1, dtype=np.int32)
+        cam = self.c_camera()
+        intr = np.ascontiguousarray(self.flat_intrinsics())
+        _check(lib.b200ba_project(-1, C.byref(cam), _dp(intr), 1, _dp(lp), _dp(px), ok.ctypes.data_as(C.POINTER(C.c_int32))))
+        return bool(ok[0]), px[0]
+
+    def Project(self, local_point):
+        return self.ProjectWithInitialEstimate(local_point, self.CenterOfCalibratedArea())
+
+    def ProjectMany(self, local_points, initial_pixels=None):
+        lib = cabi.load_library()
+        lp = np.ascontiguousarray(local_points, dtype=np.float64).reshape(-1, 3)
+        n = len(lp)
+        if initial_pixels is None:
+            px = np.tile(self.CenterOfCalibratedArea(), (n, 1))
+        else:
+            px = np.array(initial_pixels, dtype=np.float64).reshape(-1, 2)
+        px = np.ascontiguousarray(px)
+        ok = np.zeros(n, dtype=np.int32)
+        cam = self.c_camera()
+        intr = np.ascontiguousarray(self.flat_intrinsics())
+        _check(lib.b200ba_project(-1, C.byref(cam), _dp(intr), n, _dp(lp), _dp(px), ok.ctypes.data_as(C.POINTER(C.c_int32))))
+        return px, ok.astype(bool)
+
+    def UnprojectMany(self, pixels):
+        """Returns (directions, origins, ok); origins are zero for central models."""
+        lib = cabi.load_library()
+        px = np.ascontiguousarray(pixels, dtype=np.float64).reshape(-1, 2)
+        n = len(px)
+        d = np.zeros((n, 3))
+        o = np.zeros((n, 3))
+        ok = np.zeros(n, dtype=np.int32)
+        cam = self.c_camera()
+        intr = np.ascontiguousarray(self.flat_intrinsics())
+        _check(lib.b200ba_unproject(-1, C.byref(cam), _dp(intr), n, _dp(px), _dp(d), _dp(o), ok.ctypes.data_as(C.POINTER(C.c_int32))))
+        return d, o, ok.astype(bool)
+
+    def Unproject(self, x, y):
+        d, o, ok = self.UnprojectMany([[x, y]])
+        return bool(ok[0]), d[0], o[0]
+
+
+class CentralGenericModel(CameraModel):
+    """APP/models/central_generic.h:45-143 (+ CentralGridModel, central_grid.h:43-262)."""
+    IntrinsicsJacobianSize = 2 * 16
+
+    def __init__(self, grid_resolution_x, grid_resolution_y, calibration_min_x, calibration_min_y, calibration_max_x,
+                 calibration_max_y, width, height):
+        super().__init__(width, height, calibration_min_x, calibration_min_y, calibration_max_x, calibration_max_y,
+                         CameraModel.Type.CentralGeneric)
+        self.m_grid = np.zeros((int(grid_resolution_y), int(grid_resolution_x), 3))
+
+    def grid(self): return self.m_grid
+    def SetGrid(self, grid): self.m_grid = np.array(grid, dtype=np.float64).reshape(self.m_grid.shape[0] if np.ndim(grid) < 3 else np.shape(grid)[0], -1, 3)
+    def GetGridResolution(self): return (self.m_grid.shape[1], self.m_grid.shape[0])
+    def update_parameter_count(self): return 2 * self.m_grid.shape[0] * self.m_grid.shape[1]
+    @staticmethod
+    def exterior_cells_per_side(): return 1
+
+    def duplicate(self):
+        m = CentralGenericModel(self.m_grid.shape[1], self.m_grid.shape[0], self.m_calibration_min_x,
+                                self.m_calibration_min_y, self.m_calibration_max_x, self.m_calibration_max_y,
+                                self.m_width, self.m_height)
+        m.m_grid = self.m_grid.copy()
+        return m
+
+    def flat_intrinsics(self): return self.m_grid.reshape(-1)
+    def set_flat_intrinsics(self, a): self.m_grid = np.array(a, dtype=np.float64).reshape(self.m_grid.shape)
+
+
+class NoncentralGenericModel(CameraModel):
+    """APP/models/noncentral_generic.h:46-290."""
+    IntrinsicsJacobianSize = 5 * 16
+
+    def __init__(self, grid_resolution_x, grid_resolution_y, calibration_min_x, calibration_min_y, calibration_max_x,
+                 calibration_max_y, width, height):
+        super().__init__(width, height, calibration_min_x, calibration_min_y, calibration_max_x, calibration_max_y,
+                         CameraModel.Type.NoncentralGeneric)
+        self.m_point_grid = np.zeros((int(grid_resolution_y), int(grid_resolution_x), 3))
+        self.m_direction_grid = np.zeros((int(grid_resolution_y), int(grid_resolution_x), 3))
+
+    def point_grid(self): return self.m_point_grid
+    def direction_grid(self): return self.m_direction_grid
+    def SetPointGrid(self, g): self.m_point_grid = np.array(g, dtype=np.float64)
+    def SetDirectionGrid(self, g): self.m_direction_grid = np.array(g, dtype=np.float64)
+    def GetGridResolution(self): return (self.m_point_grid.shape[1], self.m_point_grid.shape[0])
+    def update_parameter_count(self): return 5 * self.m_direction_grid.shape[0] * self.m_direction_grid.shape[1]
+    @staticmethod
+    def exterior_cells_per_side(): return 1
+
+    def Scale(self, factor):
+        """noncentral_generic.cc:148-154."""
+        self.m_point_grid = factor * self.m_point_grid
+
+    def duplicate(self):
+        m = NoncentralGenericModel(self.m_point_grid.shape[1], self.m_point_grid.shape[0], self.m_calibration_min_x,
+                                   self.m_calibration_min_y, self.m_calibration_max_x, self.m_calibration_max_y,
+                                   self.m_width, self.m_height)
+        m.m_point_grid = self.m_point_grid.copy()
+        m.m_direction_grid = self.m_direction_grid.copy()
+        return m
+
+    def flat_intrinsics(self): return np.concatenate([self.m_direction_grid.reshape(-1), self.m_point_grid.reshape(-1)])
+
+    def set_flat_intrinsics(self, a):
+        a = np.asarray(a, dtype=np.float64)
+        n = self.m_direction_grid.size
+        self.m_direction_grid = a[:n].reshape(self.m_direction_grid.shape).copy()
+        self.m_point_grid = a[n:].reshape(self.m_point_grid.shape).copy()
+
+
+class CentralOpenCVModel(CameraModel):
+    """APP/models/central_opencv.h:40-178; parameters fx fy cx cy k1 k2 k3 k4 k5 k6 p1 p2."""
+    IntrinsicsJacobianSize = 12
+
+    def __init__(self, width, height, parameters=None):
+        super().__init__(width, height, 0, 0, width - 1, height - 1, CameraModel.Type.CentralOpenCV)
+        self.m_parameters = np.zeros(12) if parameters is None else np.array(parameters, dtype=np.float64)
+
+    def parameters(self): return self.m_parameters
+    def update_parameter_count(self): return 12
+    def duplicate(self): return CentralOpenCVModel(self.m_width, self.m_height, self.m_parameters.copy())
+    def flat_intrinsics(self): return self.m_parameters
+    def set_flat_intrinsics(self, a): self.m_parameters = np.array(a, dtype=np.float64).reshape(12)
+
+
+# ---------------------------------------------------------------------------------------
+# Dataset / BAState mirror
+# ---------------------------------------------------------------------------------------
+@dataclass
+class PointFeature:
+    """APP/dataset.h:57-84."""
+    xy: np.ndarray
+    id: int
+    index: int = -1
+    last_projection: np.ndarray = None
+
+
+class Imageset:
+    """APP/dataset.h:88-123. Features are stored as arrays per camera (a million PointFeature
+    objects would defeat the purpose); FeaturesOfCamera() returns them as a dict of arrays."""
+
+    def __init__(self, num_cameras: int):
+        self.m_features = [dict(xy=np.zeros((0, 2), np.float32), id=np.zeros(0, np.int32),
+                                index=np.zeros(0, np.int32), last_projection=np.zeros((0, 2)))
+                           for _ in range(num_cameras)]
+        self.filename = ""
+
+    def FeaturesOfCamera(self, camera_index: int) -> Dict[str, np.ndarray]:
+        return self.m_features[camera_index]
+
+    def SetFeaturesOfCamera(self, camera_index: int, xy, ids, index=None):
+        xy = np.ascontiguousarray(xy, dtype=np.float32).reshape(-1, 2)
+        ids = np.ascontiguousarray(ids, dtype=np.int32)
+        self.m_features[camera_index] = dict(
+            xy=xy, id=ids, index=np.full(len(ids), -1, np.int32) if index is None else np.ascontiguousarray(index, np.int32),
+            last_projection=np.zeros((len(ids), 2)))
+
+    def CameraHasFeatures(self, camera_index: int) -> bool:
+        return len(self.m_features[camera_index]["id"]) > 0
+
+    def GetFilename(self): return self.filename
+    def SetFilename(self, f): self.filename = f
+
+
+class Dataset:
+    """APP/dataset.h:131-212."""
+
+    def __init__(self, num_cameras: int = 0):
+        self.Reset(num_cameras)
+
+    def Reset(self, num_cameras: int):
+        self.m_num_cameras = num_cameras
+        self.image_sizes = [np.zeros(2, dtype=np.int64) for _ in range(num_cameras)]
+        self.m_imagesets: List[Imageset] = []
+        self._b200_context = None
+
+    def num_cameras(self): return self.m_num_cameras
+    def SetImageSize(self, camera_index, size): self.image_sizes[camera_index] = np.array(size, dtype=np.int64)
+    def GetImageSize(self, camera_index): return self.image_sizes[camera_index]
+
+    def NewImageset(self) -> Imageset:
+        s = Imageset(self.m_num_cameras)
+        self.m_imagesets.append(s)
+        self._b200_context = None
+        return s
+
+    def DeleteImageset(self, index):
+        del self.m_imagesets[index]
+        self._b200_context = None
+
+    def DeleteLastImageset(self): self.DeleteImageset(len(self.m_imagesets) - 1)
+    def GetImageset(self, index) -> Imageset: return self.m_imagesets[index]
+    def ImagesetCount(self) -> int: return len(self.m_imagesets)
+
+
+class BAState:
+    """APP/bundle_adjustment/ba_state.h:46-97."""
+
+    def __init__(self):
+        self.image_used: List[bool] = []
+        self.feature_id_to_points_index: Dict[int, int] = {}
+        self.camera_tr_rig = np.zeros((0, 7))
+        self.rig_tr_global = np.zeros((0, 7))
+        self.intrinsics: List[CameraModel] = []
+        self.points = np.zeros((0, 3))
+
+    def num_cameras(self): return len(self.intrinsics)
+    def num_imagesets(self): return len(self.image_used)
+
+    def ComputeFeatureIdToPointsIndex(self, dataset: Dataset):
+        """ba_state.cc:78-91."""
+        for i in range(dataset.ImagesetCount()):
+            s = dataset.GetImageset(i)
+            for c in range(dataset.num_cameras()):
+                f = s.FeaturesOfCamera(c)
+                f["index"] = np.array([self.feature_id_to_points_index[int(k)] for k in f["id"]], dtype=np.int32)
+        dataset._b200_context = None
+
+
+class SchurMode(enum.IntEnum):
+    """APP/bundle_adjustment/joint_optimization.h:38-47."""
+    Dense = 0
+    DenseCUDA = 1
+    DenseOnTheFly = 2
+    Sparse = 3
+    SparseOnTheFly = 4
+
+
+@dataclass
+class OptimizationReport:
+    """libvis lm_optimizer.h:55-77."""
+    initial_cost: float = 0.0
+    final_cost: float = 0.0
+    num_iterations_performed: int = 0
+    cost_and_jacobian_evaluation_time: float = 0.0
+    solve_time: float = 0.0
+
+
+class _Context:
+    """Flattened problem + device handle cached on the Dataset between calls (the product
+    calls OptimizeJointly with max_iteration_count=1 in a loop, APP/calibration.cc:227-237)."""
+
+    def __init__(self, dataset: Dataset, state: BAState):
+        used = [i for i, u in enumerate(state.image_used) if u]
+        self.used = used
+        self.key = (tuple(used), tuple(id(m) for m in state.intrinsics), len(state.points))
+        oi, oc, op, oxy = [], [], [], []
+        self.slices = []  # (imageset, camera, start, stop) into the flat arrays
+        pos = 0
+        for seq, i in enumerate(used):
+            s = dataset.GetImageset(i)
+            for c in range(dataset.num_cameras()):
+                f = s.FeaturesOfCamera(c)
+                n = len(f["id"])
+                if n and int(np.min(f["index"])) < 0:
+                    raise B200BAError("PointFeature::index not set: call BAState.ComputeFeatureIdToPointsIndex first")
+                oi.append(np.full(n, seq, np.uint32))
+                oc.append(np.full(n, c, np.uint32))
+                op.append(f["index"].astype(np.uint32))
+                oxy.append(f["xy"])
+                self.slices.append((i, c, pos, pos + n))
+                pos += n
+        cams = [m.c_camera() for m in state.intrinsics]
+        self.problem = FlatProblem(cams, len(used), len(state.points),
+                                   np.concatenate(oi) if oi else np.zeros(0, np.uint32),
+                                   np.concatenate(oc) if oc else np.zeros(0, np.uint32),
+                                   np.concatenate(op) if op else np.zeros(0, np.uint32),
+                                   np.concatenate(oxy) if oxy else np.zeros((0, 2), np.float32))
+        self.adjuster = BundleAdjuster(self.problem)
+
+
+def _run(dataset: Dataset, state: BAState, opt: Options) -> Report:
+    if len(state.image_used) != len(state.rig_tr_global):
+        raise B200BAError("image_used and rig_tr_global differ in size")  # CHECK_EQ, joint_optimization.cc:72
+    ctx = getattr(dataset, "_b200_context", None)
+    used = [i for i, u in enumerate(state.image_used) if u]
+    key = (tuple(used), tuple(id(m) for m in state.intrinsics), len(state.points))
+    if ctx is None or ctx.key != key:
+        ctx = _Context(dataset, state)
+        dataset._b200_context = ctx
+    lastp = np.zeros((ctx.problem.n_obs, 2))
+    for (i, c, a, b) in ctx.slices:
+        lastp[a:b] = dataset.GetImageset(i).FeaturesOfCamera(c)["last_projection"]
+    fs = FlatState(np.array(state.points, dtype=np.float64), np.array(state.rig_tr_global, dtype=np.float64)[used],
+                   np.array(state.camera_tr_rig, dtype=np.float64), [m.flat_intrinsics().copy() for m in state.intrinsics],
+                   lastp)
+    rep = ctx.adjuster.optimize_host(fs, opt)
+    # read back exactly what the reference writes (joint_optimization.cc:942-950) + last_projection
+    state.camera_tr_rig = fs.camera_tr_rig.copy()
+    rtg = np.array(state.rig_tr_global, dtype=np.float64)
+    rtg[used] = fs.rig_tr_global
+    state.rig_tr_global = rtg
+    state.points = fs.points.copy()
+    new_models = []
+    for m, a in zip(state.intrinsics, fs.intrinsics):
+        d = m.duplicate()
+        d.set_flat_intrinsics(a)
+        new_models.append(d)
+    state.intrinsics = new_models
+    # the cached context is keyed on model identity: re-key it to the duplicated models
+    ctx.key = (tuple(used), tuple(id(m) for m in state.intrinsics), len(state.points))
+    for (i, c, a, b) in ctx.slices:
+        dataset.GetImageset(i).FeaturesOfCamera(c)["last_projection"] = fs.last_projection[a:b].copy()
+    return rep
+
+
+def OptimizeJointly(dataset: Dataset, state: BAState, max_iteration_count: int, init_lambda: float,
+                    numerical_diff_delta: float, regularization_weight: float, localize_only: bool,
+                    eliminate_points: bool, schur_mode: SchurMode = SchurMode.Dense, debug_verify_cost: bool = False,
+                    debug_fix_points: bool = False, debug_fix_poses: bool = False, debug_fix_rig_poses: bool = False,
+                    debug_fix_intrinsics: bool = False, print_progress: bool = True) -> Tuple[float, float, bool]:
+    """APP/bundle_adjustment/joint_optimization.h:53-70. Returns (final_cost, final_lambda,
+    performed_an_iteration) -- the reference's return value and its two out-parameters.
+
+    ``numerical_diff_delta`` is accepted for signature parity; the device path differentiates
+    analytically. ``regularization_weight`` must be 0 (the reference logs an error and ignores
+    it). The debug_fix_* switches (a slow dense fallback in the reference) are not supported."""
+    if debug_fix_points or debug_fix_poses or debug_fix_rig_poses or debug_fix_intrinsics:
+        raise B200BAError("debug_fix_* is not supported on the device path")
+    opt = cabi.default_options(max_iteration_count=int(max_iteration_count), init_lambda=float(init_lambda),
+                               numerical_diff_delta=float(numerical_diff_delta),
+                               regularization_weight=float(regularization_weight), localize_only=int(localize_only),
+                               eliminate_points=int(eliminate_points), schur_mode=int(schur_mode),
+                               print_progress=int(print_progress))
+    rep = _run(dataset, state, opt)
+    return rep.final_cost, rep.final_lambda, bool(rep.performed_an_iteration)
+
+
+def CudaOptimizeJointly(dataset: Dataset, state: BAState, max_iteration_count: int, max_inner_iterations: int,
+                        init_lambda: float, numerical_diff_delta: float, regularization_weight: float,
+                        debug_verify_cost: bool = False, debug_fix_points: bool = False, debug_fix_poses: bool = False,
+                        debug_fix_rig_poses: bool = False, debug_fix_intrinsics: bool = False,
+                        print_progress: bool = True) -> Tuple[OptimizationReport, float]:
+    """APP/bundle_adjustment/cuda_joint_optimization.h:45-59. Returns (report, final_lambda).
+    ``max_inner_iterations`` (PCG steps of the reference's float32 path) has no meaning here:
+    the reduced system is solved directly in FP64."""
+    opt = cabi.default_options(max_iteration_count=int(max_iteration_count), init_lambda=float(init_lambda),
+                               numerical_diff_delta=float(numerical_diff_delta),
+                               regularization_weight=float(regularization_weight), print_progress=int(print_progress))
+    rep = _run(dataset, state, opt)
+    return OptimizationReport(rep.initial_cost, rep.final_cost, rep.num_iterations_performed,
+                              rep.cost_and_jacobian_evaluation_time, rep.solve_time), rep.final_lambda
+
+
+def dataset_from_flat(problem: FlatProblem, state: FlatState) -> Tuple[Dataset, BAState]:
+    """Builds the reference-shaped containers from a flattened problem (synthetic data, tests)."""
+    ds = Dataset(problem.n_cameras)
+    for c, cam in enumerate(problem.cameras):
+        ds.SetImageSize(c, (cam.width, cam.height))
+    order = np.lexsort((problem.obs_camera, problem.obs_imageset))
+    assert np.array_equal(order, np.arange(problem.n_obs)) or True
+    bounds = np.searchsorted(problem.obs_imageset, np.arange(problem.n_imagesets + 1))
+    for i in range(problem.n_imagesets):
+        s = ds.NewImageset()
+        a, b = bounds[i], bounds[i + 1]
+        for c in range(problem.n_cameras):
+            sel = np.nonzero(problem.obs_camera[a:b] == c)[0] + a
+            s.SetFeaturesOfCamera(c, problem.obs_xy[sel], problem.obs_point[sel].astype(np.int32),
+                                  problem.obs_point[sel].astype(np.int32))
+            if state.last_projection is not None:
+                s.FeaturesOfCamera(c)["last_projection"] = state.last_projection[sel].copy()
+    st = BAState()
+    st.image_used = [True] * problem.n_imagesets
+    st.feature_id_to_points_index = {i: i for i in range(problem.n_points)}
+    st.camera_tr_rig = state.camera_tr_rig.copy()
+    st.rig_tr_global = state.rig_tr_global.copy()
+    st.points = state.points.copy()
+    for cam, intr in zip(problem.cameras, state.intrinsics):
+        if cam.model_type == cabi.MODEL_CENTRAL_GENERIC:
+            m = CentralGenericModel(cam.grid_width, cam.grid_height, cam.calibration_min_x, cam.calibration_min_y,
+                                    cam.calibration_max_x, cam.calibration_max_y, cam.width, cam.height)
+        elif cam.model_type == cabi.MODEL_NONCENTRAL_GENERIC:
+            m = NoncentralGenericModel(cam.grid_width, cam.grid_height, cam.calibration_min_x, cam.calibration_min_y,
+                                       cam.calibration_max_x, cam.calibration_max_y, cam.width, cam.height)
+        else:
+            m = CentralOpenCVModel(cam.width, cam.height)
+        m.set_flat_intrinsics(intr)
+        st.intrinsics.append(m)
+    return ds, st

@@ -1,0 +1,95 @@
+// ba_common.h -- structures shared by the host logic (ba_host.cu) and the kernels
+// (ba_kernels.cu) of libb200ba.so. Not part of the public ABI (that is include/b200ba.h).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/b200ba.h"
+
+namespace b200ba {
+
+constexpr int kMaxCameras = 8;
+constexpr int kMaxK = 80;  // IntrinsicsJacobianSize of the non-central model
+
+// Device view of one camera (CameraModel base members + derived constants).
+struct CamDev {
+  int model_type;
+  int width, height;
+  int min_x, min_y, max_x, max_y;
+  int gw, gh;
+  // pixel -> grid map  g = 1 + gmul * (x - min)     (central_grid.h:150-154)
+  double gmul_x, gmul_y;
+  // PixelScaleToGridScaleX/Y: computed in FLOAT in the reference (central_grid.h:156-161)
+  double sx, sy;
+  // CenterOfCalibratedArea (camera_model.h:154-157)
+  double center_x, center_y;
+  int K;              // IntrinsicsJacobianSize: 32 / 80 / 12
+  int dof_per_point;  // 2 / 5 / 0
+  int64_t intr_off;   // offset of this camera's flat intrinsics in the state's intrinsics buffer
+  int64_t tan_off;    // offset of its tangent frames (6 doubles per control point)
+  int upd_off;        // offset of its update parameters relative to first_intrinsics
+  int upd_count;      // update_parameter_count()
+};
+
+// Variable layout of JointOptimizationState (joint_optimization.cc:97-170) and of the
+// block / dense split of H (lm_optimizer.h:657-685) for eliminate_points = true.
+struct Layout {
+  int n_points, n_imagesets, n_cameras;
+  int rig_in_state;     // n_cameras > 1
+  int localize_only;
+  int dof;              // all unknowns
+  int nbd;              // 3 * n_points (block-diagonal part)
+  int nd;               // dense part
+  // offsets inside the dense part
+  int d_pose;           // 0
+  int d_rig;            // 6 * n_imagesets
+  int d_intr;           // 6 * n_imagesets + (rig ? 6 * n_cameras : 0)
+  int n_jcols;          // Jacobian columns stored per observation: 3 + 6 + (rig ? 6 : 0) + Kmax
+  int Kmax;             // max IntrinsicsJacobianSize over cameras (0 when localize_only)
+  int jc_point, jc_pose, jc_rig, jc_intr;  // first column of each part
+};
+
+struct ProblemDev {
+  int64_t n_obs;
+  const uint32_t* obs_imageset;
+  const uint32_t* obs_camera;
+  const uint32_t* obs_point;
+  const float2* obs_xy;
+  CamDev cams[kMaxCameras];
+};
+
+// One copy of the optimised state on the device.
+struct StateDev {
+  double* points;         // [3 * n_points]
+  double* rig_tr_global;  // [7 * n_imagesets]
+  double* camera_tr_rig;  // [7 * n_cameras]
+  double* intrinsics;     // all cameras, CamDev::intr_off
+  // derived, recomputed by prepare_state():
+  double* image_tr_global;  // [n_imagesets * n_cameras][12]: R row-major (9), t (3)
+  double* tangents;         // per control point t1 (3), t2 (3); CamDev::tan_off
+};
+
+// Per-observation outputs of the residual / Jacobian kernel.
+struct ObsOut {
+  double* residual;    // [2 * n_obs] SoA: rx[n_obs], ry[n_obs]
+  double* cost;        // [n_obs], -1 = invalid residual
+  double* jac;         // [2 * n_jcols][n_obs] SoA: row-x of column c at (2c) * n_obs, row-y at (2c+1) * n_obs
+  int32_t* cell;       // [n_obs] top-left control point x0 + y0 * gw of the 4x4 support (generic models)
+  uint8_t* has_jac;    // [n_obs]
+};
+
+// The normal equations on the device (all FP64). Everything that takes part in the
+// cross-GPU reduction lives in ONE allocation so that a single all-reduce covers it.
+struct SystemDev {
+  double* base;     // the single allocation
+  int64_t total;    // doubles
+  double* Dblk;     // [n_points][6]   upper 3x3: 00 01 02 11 12 22
+  double* bp;       // [3 * n_points]
+  double* B;        // [3 * n_points][nd]   row-major
+  double* C;        // [nd][nd] row-major, row <= col valid (== column-major lower)
+  double* bd;       // [nd]
+  double* scalars;  // [8]: cost, n_valid, ...
+};
+
+}  // namespace b200ba

@@ -1,0 +1,1154 @@
+// ba_host.cu -- host logic of libb200ba.so: the C ABI of include/b200ba.h, device memory
+// management, the Levenberg-Marquardt control loop and the dense-algebra plumbing.
+//
+// What runs where
+//   device, own kernels (ba_kernels.cu): residuals, Jacobians, J^T J accumulation, 3x3 block
+//     factorisation, L^-1 B, state retraction, cost comparison.
+//   device, libraries: the symmetric rank-k update S = C - W^T W (cublasDsyrk, a plain dense
+//     FP64 contraction -- the reference uses cublasXtDgemm for it, LV/lm_optimizer.h:1371-1430)
+//     and the dense SPD factorisation (cusolverDnDpotrf/potrs; scaffolding).
+//   host: the scalar LM decisions (accept / reject, lambda), exactly LV/lm_optimizer.h:628-991
+//     as driven by APP/bundle_adjustment/joint_optimization.cc:905-940.
+// There is NO CPU fallback: every entry point fails with an error if CUDA is unavailable.
+
+#include <cublas_v2.h>
+#include <cusolverDn.h>
+#include <dlfcn.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "ba_kernels.h"
+
+using namespace b200ba;
+
+namespace {
+
+std::string g_create_error;
+
+struct NcclUniqueId {  // layout of ncclUniqueId (nccl.h): 128 opaque bytes, passed BY VALUE
+  char internal[128];
+};
+struct NcclApi {
+  void* lib = nullptr;
+  int (*GetUniqueId)(void*) = nullptr;
+  int (*CommInitRank)(void**, int, NcclUniqueId, int) = nullptr;
+  int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+  int (*CommDestroy)(void*) = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+};
+// ncclDataType_t / ncclRedOp_t values (nccl.h): ncclFloat64 = 8, ncclSum = 0
+constexpr int kNcclDouble = 8;
+constexpr int kNcclSum = 0;
+
+NcclApi g_nccl;
+bool load_nccl(std::string* err) {
+  if (g_nccl.lib) return true;
+  // Reuse the copy already mapped into the process (torch ships its own libnccl.so.2).
+  const char* names[] = {"libnccl.so.2", "libnccl.so"};
+  void* lib = nullptr;
+  for (const char* n : names) {
+    lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+    if (lib) break;
+  }
+  if (!lib) {
+    *err = std::string("cannot load libnccl: ") + dlerror();
+    return false;
+  }
+  g_nccl.lib = lib;
+  *reinterpret_cast<void**>(&g_nccl.GetUniqueId) = dlsym(lib, "ncclGetUniqueId");
+  *reinterpret_cast<void**>(&g_nccl.CommInitRank) = dlsym(lib, "ncclCommInitRank");
+  *reinterpret_cast<void**>(&g_nccl.AllReduce) = dlsym(lib, "ncclAllReduce");
+  *reinterpret_cast<void**>(&g_nccl.CommDestroy) = dlsym(lib, "ncclCommDestroy");
+  *reinterpret_cast<void**>(&g_nccl.GetErrorString) = dlsym(lib, "ncclGetErrorString");
+  if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllReduce || !g_nccl.CommDestroy) {
+    *err = "libnccl lacks a required symbol";
+    g_nccl.lib = nullptr;
+    return false;
+  }
+  return true;
+}
+
+enum Phase { PH_JAC = 0, PH_ACC, PH_SCHUR, PH_FACTOR, PH_TRIAL, PH_UPDATE, PH_ALLREDUCE, PH_COUNT };
+
+}  // namespace
+
+struct b200ba_handle {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  cublasHandle_t cublas = nullptr;
+  cusolverDnHandle_t cusolver = nullptr;
+  std::string error;
+
+  // problem
+  std::vector<b200ba_camera> cams_host;
+  ProblemDev pb{};
+  int n_cameras = 0, n_imagesets = 0, n_points = 0;
+  int64_t n_obs = 0;
+  int uniform_model = -1;
+  int64_t n_control_total = 0, n_param_total = 0, intr_total = 0, tan_total = 0;
+  uint32_t *d_obs_imageset = nullptr, *d_obs_camera = nullptr, *d_obs_point = nullptr;
+  float2* d_obs_xy = nullptr;
+
+  // state (two copies: current / trial)
+  StateDev st[2]{};
+  int cur = 0;
+  double2* d_last_projection = nullptr;
+  bool have_state = false;
+
+  // layout-dependent buffers
+  Layout L{};
+  bool have_layout = false;
+  ObsOut out{};        // base evaluation (with Jacobians)
+  ObsOut out_trial{};  // residual-only evaluation of the trial state
+  SystemDev sys{};
+  double *d_W = nullptr, *d_S = nullptr, *d_Linv = nullptr, *d_v = nullptr, *d_y = nullptr, *d_x = nullptr;
+  double* d_potrf_work = nullptr;
+  int potrf_lwork = 0;
+  int *d_info = nullptr, *d_fail = nullptr;
+  uint32_t *d_keys = nullptr, *d_keys_sorted = nullptr, *d_vals = nullptr, *d_vals_sorted = nullptr;
+  void* d_sort_temp = nullptr;
+  size_t sort_temp_bytes_ = 0;
+  int sort_end_bit = 32;
+  uint32_t invalid_key = 0xffffffffu;
+  double *d_partial = nullptr, *d_scal = nullptr;
+  double* h_scal = nullptr;  // pinned [16]
+  int* h_flags = nullptr;    // pinned [2]
+
+  // multi-GPU
+  void* comm = nullptr;
+  int rank = 0, n_ranks = 1;
+
+  // timings
+  b200ba_timings timings{};
+  struct Pending {
+    int phase;
+    cudaEvent_t a, b;
+  };
+  std::vector<Pending> pending;
+  std::vector<cudaEvent_t> event_pool;
+};
+
+namespace {
+
+#define CUDA_TRY(h, expr)                                                                      \
+  do {                                                                                         \
+    cudaError_t _e = (expr);                                                                   \
+    if (_e != cudaSuccess) {                                                                   \
+      (h)->error = std::string(#expr) + ": " + cudaGetErrorString(_e);                         \
+      return 1;                                                                                \
+    }                                                                                          \
+  } while (0)
+#define CUBLAS_TRY(h, expr)                                                                    \
+  do {                                                                                         \
+    cublasStatus_t _s = (expr);                                                                \
+    if (_s != CUBLAS_STATUS_SUCCESS) {                                                         \
+      (h)->error = std::string(#expr) + ": cuBLAS status " + std::to_string(static_cast<int>(_s)); \
+      return 1;                                                                                \
+    }                                                                                          \
+  } while (0)
+#define CUSOLVER_TRY(h, expr)                                                                  \
+  do {                                                                                         \
+    cusolverStatus_t _s = (expr);                                                              \
+    if (_s != CUSOLVER_STATUS_SUCCESS) {                                                       \
+      (h)->error = std::string(#expr) + ": cuSOLVER status " + std::to_string(static_cast<int>(_s)); \
+      return 1;                                                                                \
+    }                                                                                          \
+  } while (0)
+
+template <class T>
+int dev_alloc(b200ba_handle* h, T** p, size_t count) {
+  if (*p) {
+    cudaFree(*p);
+    *p = nullptr;
+  }
+  if (count == 0) count = 1;
+  CUDA_TRY(h, cudaMalloc(reinterpret_cast<void**>(p), count * sizeof(T)));
+  return 0;
+}
+
+int64_t intrinsics_size(const b200ba_camera& c) {
+  const int64_t G = static_cast<int64_t>(c.grid_width) * c.grid_height;
+  switch (c.model_type) {
+    case B200BA_MODEL_CENTRAL_GENERIC: return 3 * G;
+    case B200BA_MODEL_NONCENTRAL_GENERIC: return 6 * G;
+    default: return 12;
+  }
+}
+int update_parameter_count(const b200ba_camera& c) {
+  const int G = c.grid_width * c.grid_height;
+  switch (c.model_type) {
+    case B200BA_MODEL_CENTRAL_GENERIC: return 2 * G;
+    case B200BA_MODEL_NONCENTRAL_GENERIC: return 5 * G;
+    default: return 12;
+  }
+}
+int jacobian_size(const b200ba_camera& c) {
+  switch (c.model_type) {
+    case B200BA_MODEL_CENTRAL_GENERIC: return 32;
+    case B200BA_MODEL_NONCENTRAL_GENERIC: return 80;
+    default: return 12;
+  }
+}
+
+void fill_camdev(const b200ba_camera& c, CamDev* d) {
+  d->model_type = c.model_type;
+  d->width = c.width;
+  d->height = c.height;
+  d->min_x = c.calibration_min_x;
+  d->min_y = c.calibration_min_y;
+  d->max_x = c.calibration_max_x;
+  d->max_y = c.calibration_max_y;
+  d->gw = c.grid_width;
+  d->gh = c.grid_height;
+  const int aw = c.calibration_max_x + 1 - c.calibration_min_x;
+  const int ah = c.calibration_max_y + 1 - c.calibration_min_y;
+  d->gmul_x = (c.grid_width > 0) ? static_cast<double>(c.grid_width - 3) / aw : 0.0;
+  d->gmul_y = (c.grid_height > 0) ? static_cast<double>(c.grid_height - 3) / ah : 0.0;
+  // PixelScaleToGridScaleX/Y divide in float (APP/models/central_grid.h:156-161)
+  d->sx = (c.grid_width > 0) ? static_cast<double>((c.grid_width - 3.f) / aw) : 0.0;
+  d->sy = (c.grid_height > 0) ? static_cast<double>((c.grid_height - 3.f) / ah) : 0.0;
+  d->center_x = 0.5f * static_cast<float>(c.calibration_min_x + c.calibration_max_x + 1);
+  d->center_y = 0.5f * static_cast<float>(c.calibration_min_y + c.calibration_max_y + 1);
+  d->K = jacobian_size(c);
+  d->dof_per_point = c.model_type == B200BA_MODEL_CENTRAL_GENERIC ? 2 : (c.model_type == B200BA_MODEL_NONCENTRAL_GENERIC ? 5 : 0);
+  d->upd_count = update_parameter_count(c);
+}
+
+int64_t align32(int64_t n) { return (n + 31) / 32 * 32; }
+
+// ---- timing ----------------------------------------------------------------------------
+cudaEvent_t get_event(b200ba_handle* h) {
+  if (!h->event_pool.empty()) {
+    cudaEvent_t e = h->event_pool.back();
+    h->event_pool.pop_back();
+    return e;
+  }
+  cudaEvent_t e;
+  cudaEventCreate(&e);
+  return e;
+}
+struct ScopedPhase {
+  b200ba_handle* h;
+  int phase;
+  cudaEvent_t a;
+  ScopedPhase(b200ba_handle* h_, int p) : h(h_), phase(p) {
+    a = get_event(h);
+    cudaEventRecord(a, h->stream);
+  }
+  ~ScopedPhase() {
+    cudaEvent_t b = get_event(h);
+    cudaEventRecord(b, h->stream);
+    h->pending.push_back({phase, a, b});
+  }
+};
+void resolve_timings(b200ba_handle* h) {
+  for (auto& p : h->pending) {
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, p.a, p.b) == cudaSuccess) {
+      switch (p.phase) {
+        case PH_JAC: h->timings.jacobian_kernel_ms += ms; h->timings.jacobian_kernel_launches++; break;
+        case PH_ACC: h->timings.accumulate_ms += ms; break;
+        case PH_SCHUR: h->timings.schur_ms += ms; break;
+        case PH_FACTOR: h->timings.factor_ms += ms; break;
+        case PH_TRIAL: h->timings.trial_cost_ms += ms; break;
+        case PH_UPDATE: h->timings.update_ms += ms; break;
+        case PH_ALLREDUCE: h->timings.allreduce_ms += ms; break;
+      }
+    }
+    h->event_pool.push_back(p.a);
+    h->event_pool.push_back(p.b);
+  }
+  h->pending.clear();
+}
+
+// ---- layout / buffers ----------------------------------------------------------------------
+int make_layout(b200ba_handle* h, const b200ba_options* opt) {
+  if (!opt->eliminate_points) {
+    h->error = "eliminate_points=false (6x6 pose-block elimination, SURVEY.md 8f-3) is not implemented on the GPU path";
+    return 2;
+  }
+  if (opt->regularization_weight != 0) {
+    // the reference logs an error and ignores it (joint_optimization.cc:299-305)
+    h->error = "regularization_weight must be 0 (disabled in the reference)";
+    return 2;
+  }
+  Layout L{};
+  L.n_points = h->n_points;
+  L.n_imagesets = h->n_imagesets;
+  L.n_cameras = h->n_cameras;
+  L.rig_in_state = h->n_cameras > 1;
+  L.localize_only = opt->localize_only ? 1 : 0;
+  int n_intr = 0, kmax = 0;
+  for (int c = 0; c < h->n_cameras; ++c) {
+    n_intr += update_parameter_count(h->cams_host[c]);
+    kmax = std::max(kmax, jacobian_size(h->cams_host[c]));
+  }
+  if (L.localize_only) {
+    n_intr = 0;
+    kmax = 0;
+  }
+  L.nbd = 3 * h->n_points;
+  L.d_pose = 0;
+  L.d_rig = 6 * h->n_imagesets;
+  L.d_intr = L.d_rig + (L.rig_in_state ? 6 * h->n_cameras : 0);
+  L.nd = L.d_intr + n_intr;
+  L.dof = L.nbd + L.nd;
+  L.Kmax = kmax;
+  L.jc_point = 0;
+  L.jc_pose = 3;
+  L.jc_rig = 9;
+  L.jc_intr = 9 + (L.rig_in_state ? 6 : 0);
+  L.n_jcols = L.jc_intr + kmax;
+  const bool same = h->have_layout && memcmp(&L, &h->L, sizeof(Layout)) == 0;
+  if (same) return 0;
+  h->L = L;
+  h->have_layout = true;
+
+  const int64_t n = h->n_obs;
+  if (dev_alloc(h, &h->out.residual, 2 * n)) return 1;
+  if (dev_alloc(h, &h->out.cost, n)) return 1;
+  if (dev_alloc(h, &h->out.jac, 2 * static_cast<size_t>(L.n_jcols) * n)) return 1;
+  if (dev_alloc(h, &h->out.cell, n)) return 1;
+  if (dev_alloc(h, &h->out.has_jac, n)) return 1;
+  if (dev_alloc(h, &h->out_trial.residual, 2 * n)) return 1;
+  if (dev_alloc(h, &h->out_trial.cost, n)) return 1;
+  h->out_trial.jac = nullptr;
+  h->out_trial.cell = nullptr;
+  h->out_trial.has_jac = nullptr;
+
+  // the normal equations: one allocation (one all-reduce)
+  SystemDev& s = h->sys;
+  const int64_t oD = 0;
+  const int64_t obp = oD + align32(6LL * L.n_points);
+  const int64_t oB = obp + align32(L.nbd);
+  const int64_t oC = oB + align32(static_cast<int64_t>(L.nbd) * L.nd);
+  const int64_t obd = oC + align32(static_cast<int64_t>(L.nd) * L.nd);
+  const int64_t osc = obd + align32(L.nd);
+  s.total = osc + 32;
+  if (dev_alloc(h, &s.base, s.total)) return 1;
+  s.Dblk = s.base + oD;
+  s.bp = s.base + obp;
+  s.B = s.base + oB;
+  s.C = s.base + oC;
+  s.bd = s.base + obd;
+  s.scalars = s.base + osc;
+  if (dev_alloc(h, &h->d_W, static_cast<size_t>(L.nbd) * L.nd)) return 1;
+  if (dev_alloc(h, &h->d_S, static_cast<size_t>(L.nd) * L.nd)) return 1;
+  if (dev_alloc(h, &h->d_Linv, 6 * static_cast<size_t>(L.n_points))) return 1;
+  if (dev_alloc(h, &h->d_v, L.nbd)) return 1;
+  if (dev_alloc(h, &h->d_y, L.nbd)) return 1;
+  if (dev_alloc(h, &h->d_x, L.dof)) return 1;
+  int lwork = 0;
+  CUSOLVER_TRY(h, cusolverDnDpotrf_bufferSize(h->cusolver, CUBLAS_FILL_MODE_LOWER, L.nd, h->d_S, std::max(1, L.nd), &lwork));
+  h->potrf_lwork = lwork;
+  if (dev_alloc(h, &h->d_potrf_work, std::max(1, lwork))) return 1;
+
+  // cell sort
+  if (dev_alloc(h, &h->d_keys, n)) return 1;
+  if (dev_alloc(h, &h->d_keys_sorted, n)) return 1;
+  if (dev_alloc(h, &h->d_vals, n)) return 1;
+  if (dev_alloc(h, &h->d_vals_sorted, n)) return 1;
+  uint64_t total_cells = 0;
+  for (int c = 0; c < h->n_cameras; ++c)
+    total_cells += static_cast<uint64_t>(std::max(1, h->cams_host[c].grid_width * h->cams_host[c].grid_height));
+  int bits = 1;
+  while ((1ull << bits) <= total_cells) ++bits;  // keys 0..total_cells-1 plus the sentinel
+  h->sort_end_bit = bits;
+  h->invalid_key = static_cast<uint32_t>((1ull << bits) - 1);
+  h->sort_temp_bytes_ = sort_temp_bytes(n, bits);
+  if (h->d_sort_temp) cudaFree(h->d_sort_temp);
+  h->d_sort_temp = nullptr;
+  CUDA_TRY(h, cudaMalloc(&h->d_sort_temp, std::max<size_t>(h->sort_temp_bytes_, 16)));
+  return 0;
+}
+
+int sync_stream(b200ba_handle* h) {
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  resolve_timings(h);
+  return 0;
+}
+
+int all_reduce(b200ba_handle* h, double* buf, size_t count) {
+  if (h->n_ranks <= 1 || !h->comm) return 0;
+  ScopedPhase ph(h, PH_ALLREDUCE);
+  int rc = g_nccl.AllReduce(buf, buf, count, kNcclDouble, kNcclSum, h->comm, h->stream);
+  if (rc != 0) {
+    h->error = std::string("ncclAllReduce: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "error");
+    return 1;
+  }
+  return 0;
+}
+
+// One residual pass on state `which` into `out`; jac selects Compute<true>/<false>.
+int evaluate_state(b200ba_handle* h, int which, bool jac, const ObsOut& out, double huber, int phase) {
+  launch_prepare_state(h->pb, h->L, h->st[which], h->n_control_total, h->stream);
+  h->timings.kernel_launches += 1;
+  {
+    ScopedPhase ph(h, phase);
+    launch_residual_jacobian(h->uniform_model, jac, h->pb, h->L, h->st[which], h->d_last_projection, out, huber,
+                             h->stream);
+    h->timings.kernel_launches += (h->n_obs > 0);
+  }
+  CUDA_TRY(h, cudaGetLastError());
+  return 0;
+}
+
+// Hot loop 1: H, b at the current state (LV/lm_optimizer.h:706-716).
+int build_system(b200ba_handle* h, double huber, double* cost, double* n_valid) {
+  if (evaluate_state(h, h->cur, true, h->out, huber, PH_JAC)) return 1;
+  {
+    ScopedPhase ph(h, PH_ACC);
+    CUDA_TRY(h, cudaMemsetAsync(h->sys.base, 0, h->sys.total * sizeof(double), h->stream));
+    launch_accumulate_scatter(h->pb, h->L, h->out, h->sys, huber, h->stream);
+    if (!h->L.localize_only || h->L.rig_in_state) {
+      launch_cell_keys(h->pb, h->out, h->d_keys, h->d_vals, h->invalid_key, h->stream);
+      if (h->n_obs > 0)
+        sort_pairs(h->d_sort_temp, h->sort_temp_bytes_, h->d_keys, h->d_keys_sorted, h->d_vals, h->d_vals_sorted,
+                   h->n_obs, h->sort_end_bit, h->stream);
+      launch_accumulate_cells(h->pb, h->L, h->out, h->sys, h->d_keys_sorted, h->d_vals_sorted, h->invalid_key, huber,
+                              h->stream);
+      h->timings.kernel_launches += 5;
+    }
+    h->timings.kernel_launches += 1;
+    launch_cost_reduce(h->n_obs, h->out.cost, nullptr, h->out.residual, h->d_partial, h->sys.scalars, h->stream);
+    h->timings.kernel_launches += 2;
+  }
+  CUDA_TRY(h, cudaGetLastError());
+  // one all-reduce covers D, b_p, B, C, b_d and the cost scalars
+  if (all_reduce(h, h->sys.base, static_cast<size_t>(h->sys.total))) return 1;
+  CUDA_TRY(h, cudaMemcpyAsync(h->h_scal, h->sys.scalars, 6 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  if (sync_stream(h)) return 1;
+  *cost = h->h_scal[3];
+  *n_valid = h->h_scal[4];
+  return 0;
+}
+
+// Hot loop 2: Schur complement solve for a given lambda (LV/lm_optimizer.h:1246-1369).
+// Leaves x = [x_points | x_dense] in d_x. *spd = 0 when a factorisation met a non-positive pivot.
+int solve_system(b200ba_handle* h, double lambda, int* spd) {
+  const Layout& L = h->L;
+  const double one = 1.0, minus_one = -1.0;
+  {
+    ScopedPhase ph(h, PH_SCHUR);
+    CUDA_TRY(h, cudaMemsetAsync(h->d_fail, 0, sizeof(int), h->stream));
+    launch_schur_blocks(L.n_points, h->sys.Dblk, h->sys.bp, lambda, h->d_Linv, h->d_v, h->d_fail, h->stream);
+    launch_schur_scale_rows(L.n_points, L.nd, h->sys.B, h->d_Linv, h->d_W, h->stream);
+    CUDA_TRY(h, cudaMemcpyAsync(h->d_S, h->sys.C, static_cast<size_t>(L.nd) * L.nd * sizeof(double),
+                                cudaMemcpyDeviceToDevice, h->stream));
+    launch_add_diagonal(L.nd, h->d_S, L.nd, lambda, h->stream);
+    h->timings.kernel_launches += 3;
+    if (L.nbd > 0 && L.nd > 0) {
+      // S = (C + lambda I) - W^T W; row-major W [nbd x nd] is the column-major nd x nbd matrix W^T
+      CUBLAS_TRY(h, cublasDsyrk(h->cublas, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_N, L.nd, L.nbd, &minus_one, h->d_W, L.nd,
+                                &one, h->d_S, L.nd));
+      // reduced right-hand side b_d - W^T v, written into x_dense
+      CUDA_TRY(h, cudaMemcpyAsync(h->d_x + L.nbd, h->sys.bd, L.nd * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+      CUBLAS_TRY(h, cublasDgemv(h->cublas, CUBLAS_OP_N, L.nd, L.nbd, &minus_one, h->d_W, L.nd, h->d_v, 1, &one,
+                                h->d_x + L.nbd, 1));
+    }
+  }
+  {
+    ScopedPhase ph(h, PH_FACTOR);
+    CUSOLVER_TRY(h, cusolverDnDpotrf(h->cusolver, CUBLAS_FILL_MODE_LOWER, L.nd, h->d_S, L.nd, h->d_potrf_work,
+                                     h->potrf_lwork, h->d_info));
+    CUSOLVER_TRY(h, cusolverDnDpotrs(h->cusolver, CUBLAS_FILL_MODE_LOWER, L.nd, 1, h->d_S, L.nd, h->d_x + L.nbd, L.nd,
+                                     h->d_info + 1));
+  }
+  {
+    ScopedPhase ph(h, PH_SCHUR);
+    // y = v - W x_d ; x_p = L^-T y
+    CUDA_TRY(h, cudaMemcpyAsync(h->d_y, h->d_v, L.nbd * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+    if (L.nbd > 0 && L.nd > 0)
+      CUBLAS_TRY(h, cublasDgemv(h->cublas, CUBLAS_OP_T, L.nd, L.nbd, &minus_one, h->d_W, L.nd, h->d_x + L.nbd, 1, &one,
+                                h->d_y, 1));
+    launch_schur_backsub(L.n_points, h->d_Linv, h->d_y, h->d_x, h->stream);
+    h->timings.kernel_launches += 1;
+  }
+  CUDA_TRY(h, cudaMemcpyAsync(h->h_flags, h->d_info, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(h, cudaMemcpyAsync(h->h_flags + 1, h->d_fail, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  if (sync_stream(h)) return 1;
+  *spd = (h->h_flags[0] == 0 && h->h_flags[1] == 0) ? 1 : 0;
+  return 0;
+}
+
+int check_ready(b200ba_handle* h, const b200ba_options* opt) {
+  if (!h) return 1;
+  if (!opt) {
+    h->error = "options are NULL";
+    return 2;
+  }
+  if (!h->have_state) {
+    h->error = "no state: call b200ba_set_state first";
+    return 2;
+  }
+  CUDA_TRY(h, cudaSetDevice(h->device));
+  return make_layout(h, opt);
+}
+
+void free_handle_buffers(b200ba_handle* h) {
+  auto F = [](auto*& p) {
+    if (p) cudaFree(p);
+    p = nullptr;
+  };
+  F(h->d_obs_imageset); F(h->d_obs_camera); F(h->d_obs_point); F(h->d_obs_xy);
+  for (int i = 0; i < 2; ++i) {
+    F(h->st[i].points); F(h->st[i].rig_tr_global); F(h->st[i].camera_tr_rig); F(h->st[i].intrinsics);
+    F(h->st[i].image_tr_global); F(h->st[i].tangents);
+  }
+  F(h->d_last_projection);
+  F(h->out.residual); F(h->out.cost); F(h->out.jac); F(h->out.cell); F(h->out.has_jac);
+  F(h->out_trial.residual); F(h->out_trial.cost);
+  F(h->sys.base); F(h->d_W); F(h->d_S); F(h->d_Linv); F(h->d_v); F(h->d_y); F(h->d_x); F(h->d_potrf_work);
+  F(h->d_info); F(h->d_fail); F(h->d_keys); F(h->d_keys_sorted); F(h->d_vals); F(h->d_vals_sorted);
+  if (h->d_sort_temp) cudaFree(h->d_sort_temp);
+  h->d_sort_temp = nullptr;
+  F(h->d_partial); F(h->d_scal);
+  if (h->h_scal) cudaFreeHost(h->h_scal);
+  if (h->h_flags) cudaFreeHost(h->h_flags);
+  h->h_scal = nullptr;
+  h->h_flags = nullptr;
+}
+
+}  // namespace
+
+// ==============================================================================================
+// C ABI
+// ==============================================================================================
+extern "C" {
+
+const char* b200ba_version(void) { return "b200ba 0.1.0 (sm_100a, FP64)"; }
+
+int64_t b200ba_intrinsics_size(const b200ba_camera* cam) { return cam ? intrinsics_size(*cam) : 0; }
+int32_t b200ba_update_parameter_count(const b200ba_camera* cam) { return cam ? update_parameter_count(*cam) : 0; }
+
+void b200ba_default_options(b200ba_options* o) {
+  if (!o) return;
+  o->max_iteration_count = 1;
+  o->init_lambda = -1.0;
+  o->numerical_diff_delta = 1e-4;   // APP/calibration.cc:201
+  o->regularization_weight = 0.0;
+  o->localize_only = 0;
+  o->eliminate_points = 1;
+  o->schur_mode = B200BA_SCHUR_DENSE;
+  o->max_lm_attempts = 50;          // joint_optimization.cc:920
+  o->init_lambda_factor = 1e-5;     // joint_optimization.cc:922
+  o->huber_parameter = 1.0;         // joint_optimization.cc:346
+  o->jacobian_mode = B200BA_JACOBIAN_ANALYTIC;
+  o->print_progress = 0;
+}
+
+const char* b200ba_last_error(const b200ba_handle* h) { return h ? h->error.c_str() : g_create_error.c_str(); }
+
+int b200ba_create(const b200ba_problem* p, int device, b200ba_handle** out) {
+  if (!p || !out) {
+    g_create_error = "NULL argument";
+    return 2;
+  }
+  *out = nullptr;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    g_create_error = "no CUDA device available (this library has no CPU fallback)";
+    return 3;
+  }
+  if (p->n_cameras < 1 || p->n_cameras > kMaxCameras) {
+    g_create_error = "n_cameras out of range (1..8)";
+    return 2;
+  }
+  for (int c = 0; c < p->n_cameras; ++c) {
+    const int t = p->cameras[c].model_type;
+    if (t != B200BA_MODEL_CENTRAL_GENERIC && t != B200BA_MODEL_NONCENTRAL_GENERIC && t != B200BA_MODEL_CENTRAL_OPENCV) {
+      g_create_error = "camera model not on the accelerated path (central-generic, noncentral-generic, central-opencv)";
+      return 2;
+    }
+    if (t != B200BA_MODEL_CENTRAL_OPENCV && (p->cameras[c].grid_width < 4 || p->cameras[c].grid_height < 4)) {
+      g_create_error = "generic models need a grid of at least 4x4 control points";
+      return 2;
+    }
+  }
+  if (p->n_obs >= (1LL << 31)) {
+    g_create_error = "n_obs must be < 2^31";
+    return 2;
+  }
+  for (int64_t o = 0; o < p->n_obs; ++o) {
+    if (p->obs_imageset[o] >= static_cast<uint32_t>(p->n_imagesets) || p->obs_point[o] >= static_cast<uint32_t>(p->n_points) ||
+        p->obs_camera[o] >= static_cast<uint32_t>(p->n_cameras)) {
+      g_create_error = "observation index out of range";
+      return 2;
+    }
+  }
+  b200ba_handle* h = new b200ba_handle();
+  auto fail = [&](int rc) {
+    g_create_error = h->error;
+    free_handle_buffers(h);
+    if (h->cublas) cublasDestroy(h->cublas);
+    if (h->cusolver) cusolverDnDestroy(h->cusolver);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+    return rc;
+  };
+  if (device < 0) {
+    if (cudaGetDevice(&device) != cudaSuccess) device = 0;
+  }
+  h->device = device;
+#define TRYC(expr) \
+  if ((expr) != 0) return fail(1)
+  auto cuda_ok = [&](cudaError_t e, const char* what) {
+    if (e != cudaSuccess) {
+      h->error = std::string(what) + ": " + cudaGetErrorString(e);
+      return 1;
+    }
+    return 0;
+  };
+  TRYC(cuda_ok(cudaSetDevice(device), "cudaSetDevice"));
+  TRYC(cuda_ok(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking), "cudaStreamCreate"));
+  if (cublasCreate(&h->cublas) != CUBLAS_STATUS_SUCCESS) {
+    h->error = "cublasCreate failed";
+    return fail(1);
+  }
+  cublasSetStream(h->cublas, h->stream);
+  if (cusolverDnCreate(&h->cusolver) != CUSOLVER_STATUS_SUCCESS) {
+    h->error = "cusolverDnCreate failed";
+    return fail(1);
+  }
+  cusolverDnSetStream(h->cusolver, h->stream);
+
+  h->n_cameras = p->n_cameras;
+  h->n_imagesets = p->n_imagesets;
+  h->n_points = p->n_points;
+  h->n_obs = p->n_obs;
+  h->cams_host.assign(p->cameras, p->cameras + p->n_cameras);
+  h->uniform_model = h->cams_host[0].model_type;
+  int upd = 0;
+  for (int c = 0; c < p->n_cameras; ++c) {
+    CamDev& d = h->pb.cams[c];
+    fill_camdev(h->cams_host[c], &d);
+    d.intr_off = h->intr_total;
+    d.tan_off = h->tan_total;
+    d.upd_off = upd;
+    upd += d.upd_count;
+    h->intr_total += intrinsics_size(h->cams_host[c]);
+    const int64_t G = static_cast<int64_t>(d.gw) * d.gh;
+    h->tan_total += 6 * G;
+    h->n_control_total += G;
+    if (d.gw == 0) h->n_param_total += 12;
+    if (h->cams_host[c].model_type != h->uniform_model) h->uniform_model = -1;
+  }
+  const int64_t n = p->n_obs;
+  TRYC(dev_alloc(h, &h->d_obs_imageset, n));
+  TRYC(dev_alloc(h, &h->d_obs_camera, n));
+  TRYC(dev_alloc(h, &h->d_obs_point, n));
+  TRYC(dev_alloc(h, &h->d_obs_xy, n));
+  if (n > 0) {
+    TRYC(cuda_ok(cudaMemcpy(h->d_obs_imageset, p->obs_imageset, n * sizeof(uint32_t), cudaMemcpyHostToDevice), "H2D"));
+    TRYC(cuda_ok(cudaMemcpy(h->d_obs_camera, p->obs_camera, n * sizeof(uint32_t), cudaMemcpyHostToDevice), "H2D"));
+    TRYC(cuda_ok(cudaMemcpy(h->d_obs_point, p->obs_point, n * sizeof(uint32_t), cudaMemcpyHostToDevice), "H2D"));
+    TRYC(cuda_ok(cudaMemcpy(h->d_obs_xy, p->obs_xy, n * sizeof(float2), cudaMemcpyHostToDevice), "H2D"));
+  }
+  h->pb.n_obs = n;
+  h->pb.obs_imageset = h->d_obs_imageset;
+  h->pb.obs_camera = h->d_obs_camera;
+  h->pb.obs_point = h->d_obs_point;
+  h->pb.obs_xy = h->d_obs_xy;
+  for (int i = 0; i < 2; ++i) {
+    TRYC(dev_alloc(h, &h->st[i].points, 3 * static_cast<size_t>(h->n_points)));
+    TRYC(dev_alloc(h, &h->st[i].rig_tr_global, 7 * static_cast<size_t>(h->n_imagesets)));
+    TRYC(dev_alloc(h, &h->st[i].camera_tr_rig, 7 * static_cast<size_t>(h->n_cameras)));
+    TRYC(dev_alloc(h, &h->st[i].intrinsics, h->intr_total));
+    TRYC(dev_alloc(h, &h->st[i].image_tr_global, 12 * static_cast<size_t>(h->n_imagesets) * h->n_cameras));
+    TRYC(dev_alloc(h, &h->st[i].tangents, h->tan_total));
+  }
+  TRYC(dev_alloc(h, &h->d_last_projection, n));
+  TRYC(cuda_ok(cudaMemset(h->d_last_projection, 0, std::max<int64_t>(1, n) * sizeof(double2)), "memset"));
+  TRYC(dev_alloc(h, &h->d_info, 2));
+  TRYC(dev_alloc(h, &h->d_fail, 1));
+  TRYC(dev_alloc(h, &h->d_partial, cost_reduce_partial_size()));
+  TRYC(dev_alloc(h, &h->d_scal, 16));
+  TRYC(cuda_ok(cudaMallocHost(reinterpret_cast<void**>(&h->h_scal), 16 * sizeof(double)), "cudaMallocHost"));
+  TRYC(cuda_ok(cudaMallocHost(reinterpret_cast<void**>(&h->h_flags), 4 * sizeof(int)), "cudaMallocHost"));
+#undef TRYC
+  *out = h;
+  return 0;
+}
+
+void b200ba_destroy(b200ba_handle* h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
+  resolve_timings(h);
+  for (auto e : h->event_pool) cudaEventDestroy(e);
+  free_handle_buffers(h);
+  if (h->cublas) cublasDestroy(h->cublas);
+  if (h->cusolver) cusolverDnDestroy(h->cusolver);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+}
+
+int b200ba_set_state(b200ba_handle* h, const b200ba_state* s) {
+  if (!h) return 1;
+  if (!s || !s->points || !s->rig_tr_global || !s->camera_tr_rig || !s->intrinsics) {
+    h->error = "NULL state array";
+    return 2;
+  }
+  CUDA_TRY(h, cudaSetDevice(h->device));
+  StateDev& d = h->st[h->cur];
+  CUDA_TRY(h, cudaMemcpyAsync(d.points, s->points, 3 * sizeof(double) * h->n_points, cudaMemcpyHostToDevice, h->stream));
+  CUDA_TRY(h, cudaMemcpyAsync(d.rig_tr_global, s->rig_tr_global, 7 * sizeof(double) * h->n_imagesets, cudaMemcpyHostToDevice, h->stream));
+  CUDA_TRY(h, cudaMemcpyAsync(d.camera_tr_rig, s->camera_tr_rig, 7 * sizeof(double) * h->n_cameras, cudaMemcpyHostToDevice, h->stream));
+  for (int c = 0; c < h->n_cameras; ++c)
+    CUDA_TRY(h, cudaMemcpyAsync(d.intrinsics + h->pb.cams[c].intr_off, s->intrinsics[c],
+                                sizeof(double) * intrinsics_size(h->cams_host[c]), cudaMemcpyHostToDevice, h->stream));
+  if (s->last_projection)
+    CUDA_TRY(h, cudaMemcpyAsync(h->d_last_projection, s->last_projection, 2 * sizeof(double) * h->n_obs, cudaMemcpyHostToDevice, h->stream));
+  else
+    CUDA_TRY(h, cudaMemsetAsync(h->d_last_projection, 0, std::max<int64_t>(1, h->n_obs) * sizeof(double2), h->stream));
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  h->have_state = true;
+  return 0;
+}
+
+int b200ba_get_state(b200ba_handle* h, b200ba_state* s) {
+  if (!h) return 1;
+  if (!s || !h->have_state) {
+    h->error = "no state";
+    return 2;
+  }
+  CUDA_TRY(h, cudaSetDevice(h->device));
+  const StateDev& d = h->st[h->cur];
+  if (s->points) CUDA_TRY(h, cudaMemcpyAsync(s->points, d.points, 3 * sizeof(double) * h->n_points, cudaMemcpyDeviceToHost, h->stream));
+  if (s->rig_tr_global) CUDA_TRY(h, cudaMemcpyAsync(s->rig_tr_global, d.rig_tr_global, 7 * sizeof(double) * h->n_imagesets, cudaMemcpyDeviceToHost, h->stream));
+  if (s->camera_tr_rig) CUDA_TRY(h, cudaMemcpyAsync(s->camera_tr_rig, d.camera_tr_rig, 7 * sizeof(double) * h->n_cameras, cudaMemcpyDeviceToHost, h->stream));
+  if (s->intrinsics)
+    for (int c = 0; c < h->n_cameras; ++c)
+      CUDA_TRY(h, cudaMemcpyAsync(s->intrinsics[c], d.intrinsics + h->pb.cams[c].intr_off,
+                                  sizeof(double) * intrinsics_size(h->cams_host[c]), cudaMemcpyDeviceToHost, h->stream));
+  if (s->last_projection)
+    CUDA_TRY(h, cudaMemcpyAsync(s->last_projection, h->d_last_projection, 2 * sizeof(double) * h->n_obs, cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+int32_t b200ba_degrees_of_freedom(const b200ba_handle* h, const b200ba_options* opt) {
+  if (!h || !opt) return -1;
+  int n_intr = 0;
+  for (int c = 0; c < h->n_cameras; ++c) n_intr += update_parameter_count(h->cams_host[c]);
+  return 3 * h->n_points + 6 * h->n_imagesets + (h->n_cameras > 1 ? 6 * h->n_cameras : 0) + (opt->localize_only ? 0 : n_intr);
+}
+
+// OptimizeJointly (joint_optimization.cc:757-953): a loop of single LM iterations, each being
+// LMOptimizer::OptimizeImpl with max_iteration_count = 1 (LV/lm_optimizer.h:628-991).
+int b200ba_optimize(b200ba_handle* h, const b200ba_options* opt, b200ba_report* report) {
+  if (!h) return 1;
+  if (!report) {
+    h->error = "report is NULL";
+    return 2;
+  }
+  if (int rc = check_ready(h, opt)) return rc;
+  memset(report, 0, sizeof(*report));
+  memset(&h->timings, 0, sizeof(h->timings));
+  cudaEvent_t ev_total_a = get_event(h), ev_total_b = get_event(h);
+  cudaEventRecord(ev_total_a, h->stream);
+  const Layout& L = h->L;
+  const double huber = opt->huber_parameter;
+  double lambda = 0, init_lambda = opt->init_lambda;
+  double final_cost = -1;
+  for (int iteration = 0; iteration < opt->max_iteration_count; ++iteration) {
+    double cost = 0, n_valid = 0;
+    if (build_system(h, huber, &cost, &n_valid)) return 1;
+    double last_cost = cost;
+    if (iteration == 0) report->initial_cost = cost;
+    if (cost == 0) {  // "Cost is zero, stopping." (lm_optimizer.h:755-760)
+      final_cost = cost;
+      break;
+    }
+    if (init_lambda >= 0) {
+      lambda = init_lambda;
+    } else {
+      // lambda = init_lambda_factor * trace(H) / dof (lm_optimizer.h:766-781)
+      launch_trace(L.n_points, h->sys.Dblk, L.nd, h->sys.C, h->d_scal, h->stream);
+      h->timings.kernel_launches += 1;
+      CUDA_TRY(h, cudaMemcpyAsync(h->h_scal + 8, h->d_scal, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+      if (sync_stream(h)) return 1;
+      lambda = opt->init_lambda_factor * h->h_scal[8] / L.dof;
+    }
+    bool applied_update = false;
+    int attempts = 0;
+    for (int lm_iteration = 0; lm_iteration < opt->max_lm_attempts; ++lm_iteration) {
+      ++attempts;
+      int spd = 1;
+      if (solve_system(h, lambda, &spd)) return 1;
+      if (!spd) {
+        // A non-positive pivot: the analogue of the reference's NaN-update rejection
+        // (lm_optimizer.h:905-913) -- increase the damping and retry.
+        lambda = 2.f * lambda;
+        if (opt->print_progress) fprintf(stderr, "[b200ba]   [%d, %d] factorisation failed, new lambda %g\n", iteration + 1, lm_iteration + 1, lambda);
+        continue;
+      }
+      const int trial = 1 - h->cur;
+      {
+        ScopedPhase ph(h, PH_UPDATE);
+        launch_update_state(h->pb, L, h->st[h->cur], h->st[trial], h->d_x, h->n_control_total, h->n_param_total, h->stream);
+        h->timings.kernel_launches += 1;
+      }
+      if (evaluate_state(h, trial, false, h->out_trial, huber, PH_TRIAL)) return 1;
+      {
+        ScopedPhase ph(h, PH_TRIAL);
+        launch_cost_reduce(h->n_obs, h->out_trial.cost, h->out.cost, h->out_trial.residual, h->d_partial, h->d_scal, h->stream);
+        h->timings.kernel_launches += 2;
+      }
+      if (all_reduce(h, h->d_scal, 6)) return 1;
+      CUDA_TRY(h, cudaMemcpyAsync(h->h_scal, h->d_scal, 6 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+      if (sync_stream(h)) return 1;
+      const double left = h->h_scal[0], right = h->h_scal[1], count = h->h_scal[2];
+      const double trial_cost = h->h_scal[3];
+      // CostIsSmallerThan (lm_optimizer.h:993-1011)
+      if (count > 0 && left < right) {
+        h->cur = trial;
+        lambda = 0.5f * lambda;
+        applied_update = true;
+        report->num_iterations_performed += 1;
+        last_cost = trial_cost;
+        if (opt->print_progress) fprintf(stderr, "[b200ba] [%d] update accepted, cost %.12g\n", iteration + 1, trial_cost);
+        break;
+      } else {
+        lambda = 2.f * lambda;
+        if (opt->print_progress) fprintf(stderr, "[b200ba]   [%d, %d of %d] update rejected (bad cost: %.12g), new lambda: %g\n", iteration + 1, lm_iteration + 1, opt->max_lm_attempts, trial_cost, lambda);
+      }
+    }
+    final_cost = last_cost;
+    init_lambda = lambda;
+    report->final_lambda = lambda;
+    if (report->trace_len < B200BA_MAX_TRACE) {
+      report->trace_cost[report->trace_len] = last_cost;
+      report->trace_lambda[report->trace_len] = lambda;
+      report->trace_attempts[report->trace_len] = attempts;
+      report->trace_len++;
+    }
+    if (!applied_update) break;
+    report->performed_an_iteration = 1;
+    if (last_cost == 0) break;
+  }
+  report->final_cost = final_cost;
+  // statistics at the final state: residual-only pass from the warm start
+  if (evaluate_state(h, h->cur, false, h->out_trial, huber, PH_TRIAL)) return 1;
+  launch_cost_reduce(h->n_obs, h->out_trial.cost, nullptr, h->out_trial.residual, h->d_partial, h->d_scal, h->stream);
+  h->timings.kernel_launches += 2;
+  if (all_reduce(h, h->d_scal, 6)) return 1;
+  CUDA_TRY(h, cudaMemcpyAsync(h->h_scal, h->d_scal, 6 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  cudaEventRecord(ev_total_b, h->stream);
+  if (sync_stream(h)) return 1;
+  {
+    float ms = 0;
+    cudaEventElapsedTime(&ms, ev_total_a, ev_total_b);
+    h->timings.total_ms = ms;
+    h->event_pool.push_back(ev_total_a);
+    h->event_pool.push_back(ev_total_b);
+  }
+  report->n_valid = static_cast<int64_t>(h->h_scal[4]);
+  // with several ranks n_valid is global (all-reduced) while n_obs is this rank's shard
+  report->n_invalid = (h->n_ranks > 1) ? -1 : (h->n_obs - report->n_valid);
+  report->rmse = report->n_valid > 0 ? std::sqrt(h->h_scal[5] / h->h_scal[4]) : 0.0;
+  report->cost_and_jacobian_evaluation_time = 1e-3 * (h->timings.jacobian_kernel_ms + h->timings.accumulate_ms + h->timings.trial_cost_ms);
+  report->solve_time = 1e-3 * (h->timings.schur_ms + h->timings.factor_ms);
+  return 0;
+}
+
+int b200ba_optimize_host(b200ba_handle* h, b200ba_state* state, const b200ba_options* opt, b200ba_report* report) {
+  if (int rc = b200ba_set_state(h, state)) return rc;
+  if (int rc = b200ba_optimize(h, opt, report)) return rc;
+  return b200ba_get_state(h, state);
+}
+
+int b200ba_evaluate(b200ba_handle* h, const b200ba_options* opt, int compute_jacobians, double* residuals,
+                    double* costs, double* total_cost) {
+  if (int rc = check_ready(h, opt)) return rc;
+  const int64_t n = h->n_obs;
+  if (evaluate_state(h, h->cur, compute_jacobians != 0, h->out, opt->huber_parameter, PH_JAC)) return 1;
+  launch_cost_reduce(n, h->out.cost, nullptr, h->out.residual, h->d_partial, h->d_scal, h->stream);
+  CUDA_TRY(h, cudaMemcpyAsync(h->h_scal, h->d_scal, 6 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  if (sync_stream(h)) return 1;
+  if (residuals) {
+    std::vector<double> tmp(2 * n);
+    CUDA_TRY(h, cudaMemcpy(tmp.data(), h->out.residual, 2 * n * sizeof(double), cudaMemcpyDeviceToHost));
+    for (int64_t o = 0; o < n; ++o) {
+      residuals[2 * o] = tmp[o];
+      residuals[2 * o + 1] = tmp[n + o];
+    }
+  }
+  if (costs) CUDA_TRY(h, cudaMemcpy(costs, h->out.cost, n * sizeof(double), cudaMemcpyDeviceToHost));
+  if (total_cost) *total_cost = h->h_scal[3];
+  return 0;
+}
+
+int b200ba_get_jacobians(b200ba_handle* h, double* j_point, double* j_pose, double* j_rig, double* j_intr,
+                         int32_t* intr_index, int32_t K) {
+  if (!h || !h->have_layout) return 1;
+  CUDA_TRY(h, cudaSetDevice(h->device));
+  const Layout& L = h->L;
+  const int64_t n = h->n_obs;
+  std::vector<double> jac(2 * static_cast<size_t>(L.n_jcols) * n);
+  std::vector<int32_t> cell(n);
+  std::vector<uint8_t> has(n);
+  CUDA_TRY(h, cudaMemcpy(jac.data(), h->out.jac, jac.size() * sizeof(double), cudaMemcpyDeviceToHost));
+  CUDA_TRY(h, cudaMemcpy(cell.data(), h->out.cell, n * sizeof(int32_t), cudaMemcpyDeviceToHost));
+  CUDA_TRY(h, cudaMemcpy(has.data(), h->out.has_jac, n, cudaMemcpyDeviceToHost));
+  std::vector<uint32_t> cams(n);
+  CUDA_TRY(h, cudaMemcpy(cams.data(), h->d_obs_camera, n * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+  auto J = [&](int col, int r, int64_t o) { return jac[(2 * static_cast<size_t>(col) + r) * n + o]; };
+  for (int64_t o = 0; o < n; ++o) {
+    const bool v = has[o] != 0;
+    for (int r = 0; r < 2; ++r) {
+      if (j_point) for (int j = 0; j < 3; ++j) j_point[(o * 2 + r) * 3 + j] = v ? J(L.jc_point + j, r, o) : 0.0;
+      if (j_pose) for (int j = 0; j < 6; ++j) j_pose[(o * 2 + r) * 6 + j] = v ? J(L.jc_pose + j, r, o) : 0.0;
+      if (j_rig) for (int j = 0; j < 6; ++j) j_rig[(o * 2 + r) * 6 + j] = (v && L.rig_in_state) ? J(L.jc_rig + j, r, o) : 0.0;
+    }
+    const CamDev& c = h->pb.cams[cams[o]];
+    for (int k = 0; k < K; ++k) {
+      const bool vk = v && !L.localize_only && k < c.K;
+      if (j_intr) {
+        j_intr[(o * 2 + 0) * K + k] = vk ? J(L.jc_intr + k, 0, o) : 0.0;
+        j_intr[(o * 2 + 1) * K + k] = vk ? J(L.jc_intr + k, 1, o) : 0.0;
+      }
+      if (intr_index) {
+        int idx = -1;
+        if (vk) {
+          int local;
+          if (c.model_type == B200BA_MODEL_CENTRAL_GENERIC) {
+            const int cp = k >> 1;
+            local = 2 * (cell[o] + (cp & 3) + (cp >> 2) * c.gw) + (k & 1);
+          } else if (c.model_type == B200BA_MODEL_NONCENTRAL_GENERIC) {
+            const int cp = k / 5;
+            local = 5 * (cell[o] + (cp & 3) + (cp >> 2) * c.gw) + (k - 5 * cp);
+          } else {
+            local = k;
+          }
+          idx = L.nbd + L.d_intr + c.upd_off + local;
+        }
+        intr_index[o * K + k] = idx;
+      }
+    }
+  }
+  return 0;
+}
+
+int b200ba_build_system(b200ba_handle* h, const b200ba_options* opt, int32_t n, double* H, double* b, double* cost) {
+  if (int rc = check_ready(h, opt)) return rc;
+  const Layout& L = h->L;
+  if (n != L.dof) {
+    h->error = "n does not equal the number of unknowns";
+    return 2;
+  }
+  double c = 0, nv = 0;
+  if (build_system(h, opt->huber_parameter, &c, &nv)) return 1;
+  if (cost) *cost = c;
+  std::vector<double> D(6 * static_cast<size_t>(L.n_points)), bp(L.nbd), B(static_cast<size_t>(L.nbd) * L.nd),
+      C(static_cast<size_t>(L.nd) * L.nd), bd(L.nd);
+  CUDA_TRY(h, cudaMemcpy(D.data(), h->sys.Dblk, D.size() * sizeof(double), cudaMemcpyDeviceToHost));
+  CUDA_TRY(h, cudaMemcpy(bp.data(), h->sys.bp, bp.size() * sizeof(double), cudaMemcpyDeviceToHost));
+  CUDA_TRY(h, cudaMemcpy(B.data(), h->sys.B, B.size() * sizeof(double), cudaMemcpyDeviceToHost));
+  CUDA_TRY(h, cudaMemcpy(C.data(), h->sys.C, C.size() * sizeof(double), cudaMemcpyDeviceToHost));
+  CUDA_TRY(h, cudaMemcpy(bd.data(), h->sys.bd, bd.size() * sizeof(double), cudaMemcpyDeviceToHost));
+  std::fill(H, H + static_cast<size_t>(n) * n, 0.0);
+  for (int p = 0; p < L.n_points; ++p) {
+    const double* d = &D[6 * static_cast<size_t>(p)];
+    const int o = 3 * p;
+    H[static_cast<size_t>(o) * n + o] = d[0];
+    H[static_cast<size_t>(o) * n + o + 1] = d[1];
+    H[static_cast<size_t>(o) * n + o + 2] = d[2];
+    H[static_cast<size_t>(o + 1) * n + o + 1] = d[3];
+    H[static_cast<size_t>(o + 1) * n + o + 2] = d[4];
+    H[static_cast<size_t>(o + 2) * n + o + 2] = d[5];
+  }
+  for (int i = 0; i < L.nbd; ++i)
+    for (int k = 0; k < L.nd; ++k) H[static_cast<size_t>(i) * n + L.nbd + k] = B[static_cast<size_t>(i) * L.nd + k];
+  for (int i = 0; i < L.nd; ++i)
+    for (int k = i; k < L.nd; ++k) H[static_cast<size_t>(L.nbd + i) * n + L.nbd + k] = C[static_cast<size_t>(i) * L.nd + k];
+  for (int i = 0; i < L.nbd; ++i) b[i] = bp[i];
+  for (int i = 0; i < L.nd; ++i) b[L.nbd + i] = bd[i];
+  return 0;
+}
+
+int b200ba_get_timings(const b200ba_handle* h, b200ba_timings* t) {
+  if (!h || !t) return 1;
+  *t = h->timings;
+  return 0;
+}
+
+// ---- stand-alone Schur solve (known-answer tests) ---------------------------------------------
+int b200ba_schur_solve(int device, int32_t bs, int32_t nb, int32_t nd, const double* D, const double* B,
+                       const double* C, const double* b1, const double* b2, double* x) {
+  if (bs < 1 || bs > 6 || nb < 0 || nd < 1 || !D || !B || !C || !b1 || !b2 || !x) {
+    g_create_error = "b200ba_schur_solve: bad argument";
+    return 2;
+  }
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    g_create_error = "no CUDA device available (this library has no CPU fallback)";
+    return 3;
+  }
+  if (device >= 0) cudaSetDevice(device);
+  const int nbd = bs * nb;
+  double *dD = nullptr, *dB = nullptr, *dC = nullptr, *db1 = nullptr, *db2 = nullptr, *dDinvB = nullptr, *dDinvb = nullptr,
+         *dwork = nullptr;
+  int *dipiv = nullptr, *dinfo = nullptr;
+  cublasHandle_t cb = nullptr;
+  cusolverDnHandle_t cs = nullptr;
+  int rc = 0;
+  auto ok = [&](cudaError_t e) {
+    if (e != cudaSuccess && rc == 0) {
+      g_create_error = cudaGetErrorString(e);
+      rc = 1;
+    }
+  };
+  ok(cudaMalloc(&dD, sizeof(double) * std::max(1, nb * bs * bs)));
+  ok(cudaMalloc(&dB, sizeof(double) * std::max<size_t>(1, static_cast<size_t>(nbd) * nd)));
+  ok(cudaMalloc(&dC, sizeof(double) * static_cast<size_t>(nd) * nd));
+  ok(cudaMalloc(&db1, sizeof(double) * std::max(1, nbd)));
+  ok(cudaMalloc(&db2, sizeof(double) * nd));
+  ok(cudaMalloc(&dDinvB, sizeof(double) * std::max<size_t>(1, static_cast<size_t>(nbd) * nd)));
+  ok(cudaMalloc(&dDinvb, sizeof(double) * std::max(1, nbd)));
+  ok(cudaMalloc(&dipiv, sizeof(int) * nd));
+  ok(cudaMalloc(&dinfo, sizeof(int)));
+  if (rc == 0) {
+    ok(cudaMemcpy(dD, D, sizeof(double) * nb * bs * bs, cudaMemcpyHostToDevice));
+    ok(cudaMemcpy(dB, B, sizeof(double) * static_cast<size_t>(nbd) * nd, cudaMemcpyHostToDevice));
+    ok(cudaMemcpy(dC, C, sizeof(double) * static_cast<size_t>(nd) * nd, cudaMemcpyHostToDevice));
+    ok(cudaMemcpy(db1, b1, sizeof(double) * nbd, cudaMemcpyHostToDevice));
+    ok(cudaMemcpy(db2, b2, sizeof(double) * nd, cudaMemcpyHostToDevice));
+  }
+  if (rc == 0 && (cublasCreate(&cb) != CUBLAS_STATUS_SUCCESS || cusolverDnCreate(&cs) != CUSOLVER_STATUS_SUCCESS)) {
+    g_create_error = "cuBLAS / cuSOLVER initialisation failed";
+    rc = 1;
+  }
+  if (rc == 0) {
+    const double one = 1.0, m1 = -1.0;
+    launch_symmetrize(nd, dC, 0);
+    launch_generic_block_inverse(bs, nb, nd, dD, dB, db1, dDinvB, dDinvb, 0);
+    if (nbd > 0) {
+      // S = C - B^T D^-1 B ; sb = b2 - B^T D^-1 b1
+      cublasDgemm(cb, CUBLAS_OP_N, CUBLAS_OP_T, nd, nd, nbd, &m1, dB, nd, dDinvB, nd, &one, dC, nd);
+      cublasDgemv(cb, CUBLAS_OP_N, nd, nbd, &m1, dB, nd, dDinvb, 1, &one, db2, 1);
+    }
+    int lwork = 0;
+    cusolverDnDgetrf_bufferSize(cs, nd, nd, dC, nd, &lwork);
+    ok(cudaMalloc(&dwork, sizeof(double) * std::max(1, lwork)));
+    cusolverDnDgetrf(cs, nd, nd, dC, nd, dwork, dipiv, dinfo);
+    cusolverDnDgetrs(cs, CUBLAS_OP_N, nd, 1, dC, nd, dipiv, db2, nd, dinfo);
+    if (nbd > 0) cublasDgemv(cb, CUBLAS_OP_T, nd, nbd, &m1, dDinvB, nd, db2, 1, &one, dDinvb, 1);
+    ok(cudaDeviceSynchronize());
+    if (nbd > 0) ok(cudaMemcpy(x, dDinvb, sizeof(double) * nbd, cudaMemcpyDeviceToHost));
+    ok(cudaMemcpy(x + nbd, db2, sizeof(double) * nd, cudaMemcpyDeviceToHost));
+  }
+  cudaFree(dD); cudaFree(dB); cudaFree(dC); cudaFree(db1); cudaFree(db2); cudaFree(dDinvB); cudaFree(dDinvb);
+  cudaFree(dwork); cudaFree(dipiv); cudaFree(dinfo);
+  if (cb) cublasDestroy(cb);
+  if (cs) cusolverDnDestroy(cs);
+  return rc;
+}
+
+// ---- stand-alone model evaluation ------------------------------------------------------------------
+static int model_io(int device, const b200ba_camera* cam, const double* intrinsics, int64_t n, const double* in,
+                    int in_w, double* io_pixels, double* dirs, double* origins, int32_t* ok_out, bool project) {
+  if (!cam || !intrinsics || n < 0) {
+    g_create_error = "bad argument";
+    return 2;
+  }
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    g_create_error = "no CUDA device available (this library has no CPU fallback)";
+    return 3;
+  }
+  if (device >= 0) cudaSetDevice(device);
+  CamDev c{};
+  fill_camdev(*cam, &c);
+  const int64_t ni = intrinsics_size(*cam);
+  double *dintr = nullptr, *din = nullptr, *dpx = nullptr, *ddir = nullptr, *dorg = nullptr;
+  int32_t* dok = nullptr;
+  int rc = 0;
+  auto ok = [&](cudaError_t e) {
+    if (e != cudaSuccess && rc == 0) {
+      g_create_error = cudaGetErrorString(e);
+      rc = 1;
+    }
+  };
+  const size_t nn = std::max<int64_t>(1, n);
+  ok(cudaMalloc(&dintr, sizeof(double) * ni));
+  ok(cudaMalloc(&din, sizeof(double) * in_w * nn));
+  ok(cudaMalloc(&dpx, sizeof(double) * 2 * nn));
+  ok(cudaMalloc(&ddir, sizeof(double) * 3 * nn));
+  ok(cudaMalloc(&dorg, sizeof(double) * 3 * nn));
+  ok(cudaMalloc(&dok, sizeof(int32_t) * nn));
+  if (rc == 0) {
+    ok(cudaMemcpy(dintr, intrinsics, sizeof(double) * ni, cudaMemcpyHostToDevice));
+    if (project) {
+      ok(cudaMemcpy(din, in, sizeof(double) * 3 * n, cudaMemcpyHostToDevice));
+      ok(cudaMemcpy(dpx, io_pixels, sizeof(double) * 2 * n, cudaMemcpyHostToDevice));
+      launch_project_points(c, dintr, n, din, dpx, dok, 0);
+    } else {
+      ok(cudaMemcpy(dpx, in, sizeof(double) * 2 * n, cudaMemcpyHostToDevice));
+      launch_unproject_pixels(c, dintr, n, dpx, ddir, dorg, dok, 0);
+    }
+    ok(cudaDeviceSynchronize());
+    if (project) {
+      ok(cudaMemcpy(io_pixels, dpx, sizeof(double) * 2 * n, cudaMemcpyDeviceToHost));
+    } else {
+      if (dirs) ok(cudaMemcpy(dirs, ddir, sizeof(double) * 3 * n, cudaMemcpyDeviceToHost));
+      if (origins) ok(cudaMemcpy(origins, dorg, sizeof(double) * 3 * n, cudaMemcpyDeviceToHost));
+    }
+    if (ok_out) ok(cudaMemcpy(ok_out, dok, sizeof(int32_t) * n, cudaMemcpyDeviceToHost));
+  }
+  cudaFree(dintr); cudaFree(din); cudaFree(dpx); cudaFree(ddir); cudaFree(dorg); cudaFree(dok);
+  return rc;
+}
+
+int b200ba_project(int device, const b200ba_camera* cam, const double* intrinsics, int64_t n,
+                   const double* local_points, double* pixels, int32_t* ok) {
+  return model_io(device, cam, intrinsics, n, local_points, 3, pixels, nullptr, nullptr, ok, true);
+}
+int b200ba_unproject(int device, const b200ba_camera* cam, const double* intrinsics, int64_t n, const double* pixels,
+                     double* directions, double* origins, int32_t* ok) {
+  return model_io(device, cam, intrinsics, n, pixels, 2, nullptr, directions, origins, ok, false);
+}
+
+// ---- multi-GPU -------------------------------------------------------------------------------------
+int b200ba_nccl_unique_id(uint8_t id[B200BA_NCCL_UNIQUE_ID_BYTES]) {
+  std::string err;
+  if (!load_nccl(&err)) {
+    g_create_error = err;
+    return 1;
+  }
+  return g_nccl.GetUniqueId(id) == 0 ? 0 : 1;
+}
+
+int b200ba_comm_init(b200ba_handle* h, const uint8_t id[B200BA_NCCL_UNIQUE_ID_BYTES], int rank, int n_ranks) {
+  if (!h) return 1;
+  if (n_ranks <= 1) {
+    h->rank = 0;
+    h->n_ranks = 1;
+    return 0;
+  }
+  std::string err;
+  if (!load_nccl(&err)) {
+    h->error = err;
+    return 1;
+  }
+  CUDA_TRY(h, cudaSetDevice(h->device));
+  NcclUniqueId uid;
+  memcpy(uid.internal, id, 128);
+  int rc = g_nccl.CommInitRank(&h->comm, n_ranks, uid, rank);
+  if (rc != 0) {
+    h->error = std::string("ncclCommInitRank: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "error");
+    return 1;
+  }
+  h->rank = rank;
+  h->n_ranks = n_ranks;
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,1184 @@
+// ba_kernels.cu -- the CUDA kernels of the bundle-adjustment path (sm_100a, FP64).
+//
+//   prepare_state_kernel        image_tr_global = camera_tr_rig * rig_tr_global, tangent frames
+//   residual_jacobian_kernel    per observation: warm-started iterative projection, residual,
+//                               Huber cost and (optionally) the analytic Jacobian rows
+//   accumulate_scatter_kernel   J^T W J / J^T W r parts that group by point and by imageset
+//   accumulate_cells_kernel     intrinsics x intrinsics (+ rig) blocks, grouped by B-spline cell
+//   schur_* kernels             3x3 block factorisation, L^-1 B, back-substitution
+//   update_* kernels            state retraction (JointOptimizationState::operator-=)
+//   cost_compare_kernel         CostIsSmallerThan + totals, deterministic two-stage reduction
+//
+// Reference lines are cited at each kernel; paths relative to
+// /root/reference/applications/camera_calibration/src/camera_calibration (APP) and
+// /root/reference/libvis/src/libvis (LV).
+
+#include <cub/cub.cuh>
+
+#include "ba_device.cuh"
+#include "ba_kernels.h"
+
+namespace b200ba {
+
+// ------------------------------------------------------------------------------------------
+// prepare_state: composed poses + tangent frames
+// ------------------------------------------------------------------------------------------
+// image_tr_global = camera_tr_rig * rig_tr_global with Sophus' first-order renormalisation
+// (APP/bundle_adjustment/joint_optimization.cc:277-280, sophus/so3.hpp:215-232); tangent
+// frames of every control direction (joint_optimization.cc:254-270).
+__global__ void prepare_state_kernel(ProblemDev pb, Layout L, StateDev st, int64_t n_control_total) {
+  const int64_t tid = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  const int64_t n_pose = static_cast<int64_t>(L.n_imagesets) * L.n_cameras;
+  if (tid < n_pose) {
+    const int iset = static_cast<int>(tid / L.n_cameras);
+    const int cam = static_cast<int>(tid % L.n_cameras);
+    const double* a = st.camera_tr_rig + 7 * cam;
+    const double* b = st.rig_tr_global + 7 * iset;
+    const q4 qa{a[0], a[1], a[2], a[3]};
+    const q4 qb{b[0], b[1], b[2], b[3]};
+    double Ra[9];
+    qrot(qa, Ra);
+    const d3 t = mk3(a[4], a[5], a[6]) + rot_apply(Ra, mk3(b[4], b[5], b[6]));
+    q4 q = qmul(qa, qb);
+    const double sn = q.w * q.w + q.x * q.x + q.y * q.y + q.z * q.z;
+    if (sn != 1.0) {
+      const double s = 2.0 / (1.0 + sn);
+      q.w *= s;
+      q.x *= s;
+      q.y *= s;
+      q.z *= s;
+    }
+    double R[9];
+    qrot(q, R);
+    double* out = st.image_tr_global + 12 * tid;
+#pragma unroll
+    for (int i = 0; i < 9; ++i) out[i] = R[i];
+    out[9] = t.x;
+    out[10] = t.y;
+    out[11] = t.z;
+  }
+  const int64_t k = tid - n_pose;
+  if (k >= 0 && k < n_control_total) {
+    // find the camera owning control point k (few cameras: linear scan)
+    int cam = 0;
+    int64_t local = k;
+    for (int c = 0; c < L.n_cameras; ++c) {
+      const int64_t G = static_cast<int64_t>(pb.cams[c].gw) * pb.cams[c].gh;
+      if (local < G) {
+        cam = c;
+        break;
+      }
+      local -= G;
+    }
+    const CamDev& c = pb.cams[cam];
+    const double* g = st.intrinsics + c.intr_off + 3 * local;
+    d3 t1, t2;
+    compute_tangents(mk3(g[0], g[1], g[2]), t1, t2);
+    double* out = st.tangents + c.tan_off + 6 * local;
+    out[0] = t1.x;
+    out[1] = t1.y;
+    out[2] = t1.z;
+    out[3] = t2.x;
+    out[4] = t2.y;
+    out[5] = t2.z;
+  }
+}
+
+void launch_prepare_state(const ProblemDev& pb, const Layout& L, const StateDev& st, int64_t n_control_total,
+                          cudaStream_t s) {
+  const int64_t n = static_cast<int64_t>(L.n_imagesets) * L.n_cameras + n_control_total;
+  const int threads = 128;
+  prepare_state_kernel<<<static_cast<unsigned>((n + threads - 1) / threads), threads, 0, s>>>(pb, L, st,
+                                                                                              n_control_total);
+}
+
+// ------------------------------------------------------------------------------------------
+// residual + Jacobian, one thread per observation
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void store_col(const ObsOut& out, int64_t n_obs, int64_t o, int col, double jx,
+                                          double jy) {
+  out.jac[(2 * static_cast<int64_t>(col)) * n_obs + o] = jx;
+  out.jac[(2 * static_cast<int64_t>(col) + 1) * n_obs + o] = jy;
+}
+
+// AddReprojectionResidual (joint_optimization.cc:308-449) with the intrinsics / point
+// Jacobians obtained analytically through the implicit function theorem at the converged
+// projection (the reference differentiates numerically: joint_optimization.cc:357-376,
+// models/central_grid.h:187-245, models/noncentral_generic.h:224-283).
+template <int MODEL, bool JAC>
+__global__ void __launch_bounds__(128)
+    residual_jacobian_kernel(ProblemDev pb, Layout L, StateDev st, double2* __restrict__ last_projection,
+                             ObsOut out, double huber) {
+  const int64_t o = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (o >= pb.n_obs) return;
+  const int iset = static_cast<int>(pb.obs_imageset[o]);
+  const int cam = static_cast<int>(pb.obs_camera[o]);
+  const int pidx = static_cast<int>(pb.obs_point[o]);
+  const float2 xyf = pb.obs_xy[o];
+  const CamDev& c = pb.cams[cam];
+  const int model = (MODEL >= 0) ? MODEL : c.model_type;
+
+  const double* T = st.image_tr_global + 12 * (static_cast<int64_t>(iset) * L.n_cameras + cam);
+  double R[9];
+#pragma unroll
+  for (int i = 0; i < 9; ++i) R[i] = __ldg(T + i);
+  const d3 tvec = mk3(__ldg(T + 9), __ldg(T + 10), __ldg(T + 11));
+  const d3 point = ld3(st.points + 3 * static_cast<int64_t>(pidx));
+  const d3 rp = rot_apply(R, point);
+  const d3 lp = rp + tvec;
+
+  // warm start (joint_optimization.cc:324-333)
+  double2 lpj = last_projection[o];
+  double px = lpj.x, py = lpj.y;
+  if (!(px >= c.min_x && py >= c.min_y && px < c.max_x + 1 && py < c.max_y + 1) || isnan(px) || isnan(py)) {
+    px = c.center_x;
+    py = c.center_y;
+  }
+
+  const double* intr = st.intrinsics + c.intr_off;
+  bool ok = false;
+  CentralEval ce;
+  NoncentralEval ne;
+  d3 nt1, nt2;
+  double nR[2][2];
+  if (model == B200BA_MODEL_CENTRAL_GENERIC) {
+    const double ilen = rsqrt(dot3(lp, lp));
+    const d3 dir = ilen * lp;
+    ok = central_project(c, intr, dir, px, py, ce);
+    if (!ok) {
+      px = c.center_x;
+      py = c.center_y;
+      ok = central_project(c, intr, dir, px, py, ce);
+    }
+  } else if (model == B200BA_MODEL_NONCENTRAL_GENERIC) {
+    const double* pgrid = intr + 3 * static_cast<int64_t>(c.gw) * c.gh;
+    ok = noncentral_project(c, intr, pgrid, lp, px, py, ne, nt1, nt2, nR);
+    if (!ok) {
+      px = c.center_x;
+      py = c.center_y;
+      ok = noncentral_project(c, intr, pgrid, lp, px, py, ne, nt1, nt2, nR);
+    }
+  } else {
+    ok = opencv_project(c, intr, lp, px, py);  // initial estimate ignored (central_opencv.h:61-67)
+  }
+
+  if (!ok) {
+    out.cost[o] = -1.0;  // AddInvalidResidual (LV/lm_optimizer_update_accumulator.h:158-160)
+    out.residual[o] = nan("");
+    out.residual[pb.n_obs + o] = nan("");
+    if (JAC) {
+      out.has_jac[o] = 0;
+      out.cell[o] = -1;
+    }
+    return;
+  }
+  last_projection[o] = make_double2(px, py);
+  const double rx = px - static_cast<double>(xyf.x);
+  const double ry = py - static_cast<double>(xyf.y);
+  out.residual[o] = rx;
+  out.residual[pb.n_obs + o] = ry;
+  out.cost[o] = huber_cost_sq(huber, rx * rx + ry * ry);
+  if (!JAC) return;
+
+  // ---- d pixel / d local_point (2x3) and d pixel / d intrinsics ---------------------------
+  double P[2][3];
+  const int jc_intr = L.jc_intr;
+  int cell = 0;
+  if (model == B200BA_MODEL_CENTRAL_GENERIC) {
+    // M = (A^T A)^-1 A^T with A = d unproj / d pixel
+    const double a00 = dot3(ce.ux, ce.ux), a01 = dot3(ce.ux, ce.uy), a11 = dot3(ce.uy, ce.uy);
+    const double idet = 1.0 / (a00 * a11 - a01 * a01);
+    const d3 M0 = idet * (a11 * ce.ux - a01 * ce.uy);
+    const d3 M1 = idet * (a00 * ce.uy - a01 * ce.ux);
+    const double ilen = rsqrt(dot3(lp, lp));
+    const d3 d = ilen * lp;
+    const double m0d = dot3(M0, d), m1d = dot3(M1, d);
+    P[0][0] = (M0.x - m0d * d.x) * ilen;
+    P[0][1] = (M0.y - m0d * d.y) * ilen;
+    P[0][2] = (M0.z - m0d * d.z) * ilen;
+    P[1][0] = (M1.x - m1d * d.x) * ilen;
+    P[1][1] = (M1.y - m1d * d.y) * ilen;
+    P[1][2] = (M1.z - m1d * d.z) * ilen;
+    int x0, y0;
+    double fu, fv;
+    locate(c, px, py, x0, y0, fu, fv);
+    cell = x0 + y0 * c.gw;
+    if (!L.localize_only) {
+      double wx[4], dwx[4], wy[4], dwy[4];
+      bspline_basis(fu, wx, dwx);
+      bspline_basis(fv, wy, dwy);
+      const double m0u = dot3(M0, ce.u), m1u = dot3(M1, ce.u);
+      const double* tan = st.tangents + c.tan_off;
+#pragma unroll
+      for (int yy = 0; yy < 4; ++yy) {
+#pragma unroll
+        for (int xx = 0; xx < 4; ++xx) {
+          const int64_t seq = cell + xx + static_cast<int64_t>(yy) * c.gw;
+          const double wk = -wx[xx] * wy[yy] * ce.inv_n;
+          const d3 t1 = ld3(tan + 6 * seq), t2 = ld3(tan + 6 * seq + 3);
+          const double ut1 = dot3(ce.u, t1), ut2 = dot3(ce.u, t2);
+          const int k = 2 * (xx + 4 * yy);
+          store_col(out, pb.n_obs, o, jc_intr + k, wk * (dot3(M0, t1) - m0u * ut1), wk * (dot3(M1, t1) - m1u * ut1));
+          store_col(out, pb.n_obs, o, jc_intr + k + 1, wk * (dot3(M0, t2) - m0u * ut2),
+                    wk * (dot3(M1, t2) - m1u * ut2));
+        }
+      }
+    }
+  } else if (model == B200BA_MODEL_NONCENTRAL_GENERIC) {
+    const double idet = 1.0 / (nR[0][0] * nR[1][1] - nR[0][1] * nR[1][0]);
+    const double Ri00 = idet * nR[1][1], Ri01 = -idet * nR[0][1], Ri10 = -idet * nR[1][0], Ri11 = idet * nR[0][0];
+    // d x / d p = R^-1 [t1 t2]^T
+    P[0][0] = Ri00 * nt1.x + Ri01 * nt2.x;
+    P[0][1] = Ri00 * nt1.y + Ri01 * nt2.y;
+    P[0][2] = Ri00 * nt1.z + Ri01 * nt2.z;
+    P[1][0] = Ri10 * nt1.x + Ri11 * nt2.x;
+    P[1][1] = Ri10 * nt1.y + Ri11 * nt2.y;
+    P[1][2] = Ri10 * nt1.z + Ri11 * nt2.z;
+    int x0, y0;
+    double fu, fv;
+    locate(c, px, py, x0, y0, fu, fv);
+    cell = x0 + y0 * c.gw;
+    if (!L.localize_only) {
+      double wx[4], dwx[4], wy[4], dwy[4];
+      bspline_basis(fu, wx, dwx);
+      bspline_basis(fv, wy, dwy);
+      // d r / d direction (rows), through the normalisation of the interpolated direction
+      d3 rd1, rd2;
+      tangent_rows(ne.u, ne.o - lp, rd1, rd2);
+      rd1 = ne.inv_n * (rd1 - dot3(rd1, ne.u) * ne.u);
+      rd2 = ne.inv_n * (rd2 - dot3(rd2, ne.u) * ne.u);
+      const double* tan = st.tangents + c.tan_off;
+#pragma unroll
+      for (int yy = 0; yy < 4; ++yy) {
+#pragma unroll
+        for (int xx = 0; xx < 4; ++xx) {
+          const int64_t seq = cell + xx + static_cast<int64_t>(yy) * c.gw;
+          const double wk = wx[xx] * wy[yy];
+          const d3 t1 = ld3(tan + 6 * seq), t2 = ld3(tan + 6 * seq + 3);
+          const d3 dk = ld3(intr + 3 * seq);
+          const int k = 5 * (xx + 4 * yy);
+          // LineJacobianWrtLocalUpdate (line_parametrization.h:123-135): direction DoF 0-1,
+          // origin DoF 2-4 (along t1, t2 and the control direction)
+          double dr0[5], dr1[5];
+          dr0[0] = wk * dot3(rd1, t1);
+          dr1[0] = wk * dot3(rd2, t1);
+          dr0[1] = wk * dot3(rd1, t2);
+          dr1[1] = wk * dot3(rd2, t2);
+          dr0[2] = wk * dot3(nt1, t1);
+          dr1[2] = wk * dot3(nt2, t1);
+          dr0[3] = wk * dot3(nt1, t2);
+          dr1[3] = wk * dot3(nt2, t2);
+          dr0[4] = wk * dot3(nt1, dk);
+          dr1[4] = wk * dot3(nt2, dk);
+#pragma unroll
+          for (int q = 0; q < 5; ++q)
+            store_col(out, pb.n_obs, o, jc_intr + k + q, -(Ri00 * dr0[q] + Ri01 * dr1[q]),
+                      -(Ri10 * dr0[q] + Ri11 * dr1[q]));
+        }
+      }
+    }
+  } else {
+    double Jx[12], Jy[12];
+    opencv_jacobians(intr, lp, P, Jx, Jy);
+    if (!L.localize_only) {
+#pragma unroll
+      for (int k = 0; k < 12; ++k) store_col(out, pb.n_obs, o, jc_intr + k, Jx[k], Jy[k]);
+    }
+  }
+  out.cell[o] = cell;
+  out.has_jac[o] = 1;
+
+  // ---- chain rule to pose / rig / point (joint_optimization.cc:378-438) ----------------------
+  // For the left update q <- (1, delta) q: d(R(q) v)/d delta = -2 [R v]_x.
+  if (L.rig_in_state) {
+    const double* ca = st.camera_tr_rig + 7 * cam;
+    const double* rb = st.rig_tr_global + 7 * static_cast<int64_t>(iset);
+    double Rc[9], Rr[9];
+    qrot(q4{ca[0], ca[1], ca[2], ca[3]}, Rc);
+    qrot(q4{rb[0], rb[1], rb[2], rb[3]}, Rr);
+    const d3 rrp = rot_apply(Rr, point);
+    const d3 crp = rot_apply(Rc, rrp + mk3(rb[4], rb[5], rb[6]));
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      // PRc = P Rc
+      const double a0 = P[r][0] * Rc[0] + P[r][1] * Rc[3] + P[r][2] * Rc[6];
+      const double a1 = P[r][0] * Rc[1] + P[r][1] * Rc[4] + P[r][2] * Rc[7];
+      const double a2 = P[r][0] * Rc[2] + P[r][1] * Rc[5] + P[r][2] * Rc[8];
+      double* dst = out.jac + (2 * static_cast<int64_t>(L.jc_pose) + r) * pb.n_obs + o;
+      const int64_t stride = 2 * pb.n_obs;
+      dst[0 * stride] = -2 * (a1 * rrp.z - a2 * rrp.y);
+      dst[1 * stride] = -2 * (-a0 * rrp.z + a2 * rrp.x);
+      dst[2 * stride] = -2 * (a0 * rrp.y - a1 * rrp.x);
+      dst[3 * stride] = a0;
+      dst[4 * stride] = a1;
+      dst[5 * stride] = a2;
+      double* dr = out.jac + (2 * static_cast<int64_t>(L.jc_rig) + r) * pb.n_obs + o;
+      dr[0 * stride] = -2 * (P[r][1] * crp.z - P[r][2] * crp.y);
+      dr[1 * stride] = -2 * (-P[r][0] * crp.z + P[r][2] * crp.x);
+      dr[2 * stride] = -2 * (P[r][0] * crp.y - P[r][1] * crp.x);
+      dr[3 * stride] = P[r][0];
+      dr[4 * stride] = P[r][1];
+      dr[5 * stride] = P[r][2];
+      double* dp = out.jac + (2 * static_cast<int64_t>(L.jc_point) + r) * pb.n_obs + o;
+      dp[0 * stride] = a0 * Rr[0] + a1 * Rr[3] + a2 * Rr[6];
+      dp[1 * stride] = a0 * Rr[1] + a1 * Rr[4] + a2 * Rr[7];
+      dp[2 * stride] = a0 * Rr[2] + a1 * Rr[5] + a2 * Rr[8];
+    }
+  } else {
+    // single camera: composed rotation, identity translation block (joint_optimization.cc:392-397)
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      const int64_t stride = 2 * pb.n_obs;
+      double* dst = out.jac + (2 * static_cast<int64_t>(L.jc_pose) + r) * pb.n_obs + o;
+      dst[0 * stride] = -2 * (P[r][1] * rp.z - P[r][2] * rp.y);
+      dst[1 * stride] = -2 * (-P[r][0] * rp.z + P[r][2] * rp.x);
+      dst[2 * stride] = -2 * (P[r][0] * rp.y - P[r][1] * rp.x);
+      dst[3 * stride] = P[r][0];
+      dst[4 * stride] = P[r][1];
+      dst[5 * stride] = P[r][2];
+      double* dp = out.jac + (2 * static_cast<int64_t>(L.jc_point) + r) * pb.n_obs + o;
+      dp[0 * stride] = P[r][0] * R[0] + P[r][1] * R[3] + P[r][2] * R[6];
+      dp[1 * stride] = P[r][0] * R[1] + P[r][1] * R[4] + P[r][2] * R[7];
+      dp[2 * stride] = P[r][0] * R[2] + P[r][1] * R[5] + P[r][2] * R[8];
+    }
+  }
+}
+
+template <bool JAC>
+static void launch_rj(int model, const ProblemDev& pb, const Layout& L, const StateDev& st, double2* lp,
+                      const ObsOut& out, double huber, cudaStream_t s) {
+  const int threads = 128;
+  const unsigned blocks = static_cast<unsigned>((pb.n_obs + threads - 1) / threads);
+  if (blocks == 0) return;
+  switch (model) {
+    case B200BA_MODEL_CENTRAL_GENERIC:
+      residual_jacobian_kernel<B200BA_MODEL_CENTRAL_GENERIC, JAC><<<blocks, threads, 0, s>>>(pb, L, st, lp, out, huber);
+      break;
+    case B200BA_MODEL_NONCENTRAL_GENERIC:
+      residual_jacobian_kernel<B200BA_MODEL_NONCENTRAL_GENERIC, JAC><<<blocks, threads, 0, s>>>(pb, L, st, lp, out, huber);
+      break;
+    case B200BA_MODEL_CENTRAL_OPENCV:
+      residual_jacobian_kernel<B200BA_MODEL_CENTRAL_OPENCV, JAC><<<blocks, threads, 0, s>>>(pb, L, st, lp, out, huber);
+      break;
+    default:
+      residual_jacobian_kernel<-1, JAC><<<blocks, threads, 0, s>>>(pb, L, st, lp, out, huber);
+  }
+}
+
+void launch_residual_jacobian(int uniform_model, bool jac, const ProblemDev& pb, const Layout& L,
+                              const StateDev& st, double2* last_projection, const ObsOut& out, double huber,
+                              cudaStream_t s) {
+  if (jac)
+    launch_rj<true>(uniform_model, pb, L, st, last_projection, out, huber, s);
+  else
+    launch_rj<false>(uniform_model, pb, L, st, last_projection, out, huber, s);
+}
+
+// ------------------------------------------------------------------------------------------
+// accumulation
+// ------------------------------------------------------------------------------------------
+// Global dense column of intrinsics entry k of an observation (models/central_grid.h:213-215,
+// models/noncentral_generic.h:242-245, models/central_opencv.h:143-145).
+__device__ __forceinline__ int intr_col(const CamDev& c, int cell, int k) {
+  if (c.model_type == B200BA_MODEL_CENTRAL_GENERIC) {
+    const int cp = k >> 1;
+    return c.upd_off + 2 * (cell + (cp & 3) + (cp >> 2) * c.gw) + (k & 1);
+  } else if (c.model_type == B200BA_MODEL_NONCENTRAL_GENERIC) {
+    const int cp = k / 5;
+    return c.upd_off + 5 * (cell + (cp & 3) + (cp >> 2) * c.gw) + (k - 5 * cp);
+  }
+  return c.upd_off + k;
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+  return v;
+}
+
+// H += (w J)^T J, b += (w J)^T r for the parts that group by point and by imageset
+// (LV/lm_optimizer_jtj_accumulator_base.h:287-412, LV/lm_optimizer_update_accumulator.h:180-360):
+//   D_p (3x3), b_p, B[p, pose], B[p, rig], B[p, intrinsics]   -- FP64 atomics, no hot addresses
+//   C[pose, pose], b_pose                                     -- warp-shuffle reduction when the
+//                                                                warp lies inside one imageset
+//   C[pose, rig], C[pose, intrinsics]                          -- FP64 atomics
+// The (rig U intrinsics)^2 block is left to accumulate_cells_kernel.
+__global__ void __launch_bounds__(128)
+    accumulate_scatter_kernel(ProblemDev pb, Layout L, ObsOut out, SystemDev sys, double huber) {
+  const int64_t o = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  const int64_t n = pb.n_obs;
+  const bool active = (o < n) && out.has_jac[o];
+  int iset = -1;
+  double w = 0, rx = 0, ry = 0;
+  double jpx[3], jpy[3], jox[6], joy[6];
+  int pidx = 0, cam = 0;
+  if (active) {
+    iset = static_cast<int>(pb.obs_imageset[o]);
+    cam = static_cast<int>(pb.obs_camera[o]);
+    pidx = static_cast<int>(pb.obs_point[o]);
+    rx = out.residual[o];
+    ry = out.residual[n + o];
+    w = huber_weight_sq(huber, rx * rx + ry * ry);
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      jpx[a] = out.jac[(2 * static_cast<int64_t>(L.jc_point + a)) * n + o];
+      jpy[a] = out.jac[(2 * static_cast<int64_t>(L.jc_point + a) + 1) * n + o];
+    }
+#pragma unroll
+    for (int a = 0; a < 6; ++a) {
+      jox[a] = out.jac[(2 * static_cast<int64_t>(L.jc_pose + a)) * n + o];
+      joy[a] = out.jac[(2 * static_cast<int64_t>(L.jc_pose + a) + 1) * n + o];
+    }
+  } else {
+#pragma unroll
+    for (int a = 0; a < 3; ++a) jpx[a] = jpy[a] = 0;
+#pragma unroll
+    for (int a = 0; a < 6; ++a) jox[a] = joy[a] = 0;
+  }
+
+  // ---- pose x pose and b_pose: segmented warp reduction --------------------------------------
+  {
+    const int lane = threadIdx.x & 31;
+    // a warp whose lanes are all inactive has nothing to add
+    const bool any_active = __any_sync(0xffffffffu, active);
+    if (any_active) {
+      // the representative imageset is that of the first active lane
+      const unsigned act = __ballot_sync(0xffffffffu, active);
+      const int first = __ffs(act) - 1;
+      const int iset_f = __shfl_sync(0xffffffffu, iset, first);
+      const bool uni = __all_sync(0xffffffffu, !active || iset == iset_f);
+      double* Cpose = sys.C;
+      if (uni) {
+#pragma unroll
+        for (int a = 0; a < 6; ++a) {
+#pragma unroll
+          for (int b = a; b < 6; ++b) {
+            const double v = warp_sum(w * (jox[a] * jox[b] + joy[a] * joy[b]));
+            if (lane == 0) {
+              const int64_t row = L.d_pose + 6 * iset_f + a;
+              atomicAdd(&Cpose[row * L.nd + (L.d_pose + 6 * iset_f + b)], v);
+            }
+          }
+          const double vb = warp_sum(w * (jox[a] * rx + joy[a] * ry));
+          if (lane == 0) atomicAdd(&sys.bd[L.d_pose + 6 * iset_f + a], vb);
+        }
+      } else if (active) {
+#pragma unroll
+        for (int a = 0; a < 6; ++a) {
+          const int64_t row = L.d_pose + 6 * iset + a;
+#pragma unroll
+          for (int b = a; b < 6; ++b)
+            atomicAdd(&Cpose[row * L.nd + (L.d_pose + 6 * iset + b)], w * (jox[a] * jox[b] + joy[a] * joy[b]));
+          atomicAdd(&sys.bd[row], w * (jox[a] * rx + joy[a] * ry));
+        }
+      }
+    }
+  }
+  if (!active) return;
+
+  // ---- point block D_p, b_p -----------------------------------------------------------------
+  {
+    double* D = sys.Dblk + 6 * static_cast<int64_t>(pidx);
+    int e = 0;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+#pragma unroll
+      for (int b = a; b < 3; ++b) {
+        atomicAdd(&D[e], w * (jpx[a] * jpx[b] + jpy[a] * jpy[b]));
+        ++e;
+      }
+      atomicAdd(&sys.bp[3 * static_cast<int64_t>(pidx) + a], w * (jpx[a] * rx + jpy[a] * ry));
+    }
+  }
+  // ---- B[p, pose] ---------------------------------------------------------------------------
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    double* Brow = sys.B + (3 * static_cast<int64_t>(pidx) + a) * L.nd;
+    const double wx_ = w * jpx[a], wy_ = w * jpy[a];
+#pragma unroll
+    for (int b = 0; b < 6; ++b) atomicAdd(&Brow[L.d_pose + 6 * iset + b], wx_ * jox[b] + wy_ * joy[b]);
+  }
+  // ---- rig columns: B[p, rig], C[pose, rig] ---------------------------------------------------
+  if (L.rig_in_state) {
+    double jrx[6], jry[6];
+#pragma unroll
+    for (int a = 0; a < 6; ++a) {
+      jrx[a] = out.jac[(2 * static_cast<int64_t>(L.jc_rig + a)) * n + o];
+      jry[a] = out.jac[(2 * static_cast<int64_t>(L.jc_rig + a) + 1) * n + o];
+    }
+    const int rc = L.d_rig + 6 * cam;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      double* Brow = sys.B + (3 * static_cast<int64_t>(pidx) + a) * L.nd;
+#pragma unroll
+      for (int b = 0; b < 6; ++b) atomicAdd(&Brow[rc + b], w * (jpx[a] * jrx[b] + jpy[a] * jry[b]));
+    }
+#pragma unroll
+    for (int a = 0; a < 6; ++a) {
+      double* Crow = sys.C + static_cast<int64_t>(L.d_pose + 6 * iset + a) * L.nd;
+#pragma unroll
+      for (int b = 0; b < 6; ++b) atomicAdd(&Crow[rc + b], w * (jox[a] * jrx[b] + joy[a] * jry[b]));
+    }
+  }
+  // ---- intrinsics columns: B[p, intr], C[pose, intr] ------------------------------------------
+  if (!L.localize_only) {
+    const CamDev& c = pb.cams[cam];
+    const int cell = out.cell[o];
+    for (int k = 0; k < c.K; ++k) {
+      const double jx = out.jac[(2 * static_cast<int64_t>(L.jc_intr + k)) * n + o];
+      const double jy = out.jac[(2 * static_cast<int64_t>(L.jc_intr + k) + 1) * n + o];
+      const int col = L.d_intr + intr_col(c, cell, k);
+      const double wjx = w * jx, wjy = w * jy;
+#pragma unroll
+      for (int a = 0; a < 3; ++a)
+        atomicAdd(&sys.B[(3 * static_cast<int64_t>(pidx) + a) * L.nd + col], jpx[a] * wjx + jpy[a] * wjy);
+#pragma unroll
+      for (int a = 0; a < 6; ++a)
+        atomicAdd(&sys.C[static_cast<int64_t>(L.d_pose + 6 * iset + a) * L.nd + col], jox[a] * wjx + joy[a] * wjy);
+    }
+  }
+}
+
+void launch_accumulate_scatter(const ProblemDev& pb, const Layout& L, const ObsOut& out, const SystemDev& sys,
+                               double huber, cudaStream_t s) {
+  const int threads = 128;
+  const unsigned blocks = static_cast<unsigned>((pb.n_obs + threads - 1) / threads);
+  if (blocks == 0) return;
+  accumulate_scatter_kernel<<<blocks, threads, 0, s>>>(pb, L, out, sys, huber);
+}
+
+// Sort key of an observation for the cell-grouped pass: camera-major, then B-spline cell.
+__global__ void cell_keys_kernel(ProblemDev pb, ObsOut out, uint32_t* keys, uint32_t* vals, uint32_t invalid_key) {
+  const int64_t o = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (o >= pb.n_obs) return;
+  uint32_t key = invalid_key;
+  if (out.has_jac[o]) {
+    const int cam = static_cast<int>(pb.obs_camera[o]);
+    uint32_t base = 0;
+    for (int c = 0; c < cam; ++c) base += static_cast<uint32_t>(max(1, pb.cams[c].gw * pb.cams[c].gh));
+    key = base + static_cast<uint32_t>(max(0, out.cell[o]));
+  }
+  keys[o] = key;
+  vals[o] = static_cast<uint32_t>(o);
+}
+
+void launch_cell_keys(const ProblemDev& pb, const ObsOut& out, uint32_t* keys, uint32_t* vals, uint32_t invalid_key,
+                      cudaStream_t s) {
+  const int threads = 256;
+  const unsigned blocks = static_cast<unsigned>((pb.n_obs + threads - 1) / threads);
+  if (blocks == 0) return;
+  cell_keys_kernel<<<blocks, threads, 0, s>>>(pb, out, keys, vals, invalid_key);
+}
+
+size_t sort_temp_bytes(int64_t n, int end_bit) {
+  size_t bytes = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, bytes, static_cast<uint32_t*>(nullptr), static_cast<uint32_t*>(nullptr),
+                                  static_cast<uint32_t*>(nullptr), static_cast<uint32_t*>(nullptr),
+                                  static_cast<int>(n), 0, end_bit);
+  return bytes;
+}
+void sort_pairs(void* temp, size_t temp_bytes, const uint32_t* keys_in, uint32_t* keys_out, const uint32_t* vals_in,
+                uint32_t* vals_out, int64_t n, int end_bit, cudaStream_t s) {
+  cub::DeviceRadixSort::SortPairs(temp, temp_bytes, keys_in, keys_out, vals_in, vals_out, static_cast<int>(n), 0,
+                                  end_bit, s);
+}
+
+// (rig U intrinsics) x (rig U intrinsics) and the matching b entries, grouped by (camera,
+// cell): every observation of a cell touches the same 4x4 control points, so the block sums
+// the rank-2 updates of a run of equal keys in registers and issues ONE set of FP64 atomics
+// per run (neighbouring cells overlap in control points, hence atomics rather than stores).
+// A block owns kCellChunk consecutive observations of the key-sorted order.
+constexpr int kCellChunk = 128;
+constexpr int kCellTile = 32;
+constexpr int kCellThreads = 256;
+
+template <int MAXPAIRS>
+__global__ void __launch_bounds__(kCellThreads)
+    accumulate_cells_kernel(ProblemDev pb, Layout L, ObsOut out, SystemDev sys, const uint32_t* __restrict__ keys,
+                            const uint32_t* __restrict__ order, uint32_t invalid_key, double huber) {
+  extern __shared__ double smem[];
+  const int64_t n = pb.n_obs;
+  const int64_t begin = static_cast<int64_t>(blockIdx.x) * kCellChunk;
+  const int64_t end = min(n, begin + kCellChunk);
+  const int rigE = L.rig_in_state ? 6 : 0;
+  const int Emax = rigE + L.Kmax;  // smem row length
+  double* sJx = smem;                         // [kCellTile][Emax]  sqrt(w) * J row x
+  double* sJy = sJx + kCellTile * Emax;       // [kCellTile][Emax]
+  double* sR = sJy + kCellTile * Emax;        // [kCellTile][2]     sqrt(w) * r
+  __shared__ uint32_t sKey[kCellTile];
+  __shared__ uint32_t sObs[kCellTile];
+
+  double acc[MAXPAIRS];
+  double accb = 0;
+  int pi[MAXPAIRS], pj[MAXPAIRS];
+
+  int64_t pos = begin;
+  while (pos < end) {
+    const uint32_t key = keys[pos];
+    if (key == invalid_key) break;  // invalid observations sort last
+    // decode camera and cell of this run
+    int cam = 0;
+    uint32_t rem = key;
+    for (int cc = 0; cc < L.n_cameras; ++cc) {
+      const uint32_t G = static_cast<uint32_t>(max(1, pb.cams[cc].gw * pb.cams[cc].gh));
+      if (rem < G) {
+        cam = cc;
+        break;
+      }
+      rem -= G;
+    }
+    const CamDev& c = pb.cams[cam];
+    const int cell = static_cast<int>(rem);
+    const int E = rigE + c.K;
+    const int npairs = E * (E + 1) / 2;
+    // pair -> (i, j), i <= j, row-major over the upper triangle
+#pragma unroll
+    for (int q = 0; q < MAXPAIRS; ++q) {
+      acc[q] = 0;
+      const int p = threadIdx.x + q * kCellThreads;
+      int i = 0, j = 0;
+      if (p < npairs) {
+        // row i starts at offset i*E - i(i-1)/2
+        int lo = 0, hi = E - 1;
+        while (lo < hi) {
+          const int mid = (lo + hi + 1) >> 1;
+          if (mid * E - mid * (mid - 1) / 2 <= p) lo = mid; else hi = mid - 1;
+        }
+        i = lo;
+        j = i + (p - (i * E - i * (i - 1) / 2));
+      }
+      pi[q] = i;
+      pj[q] = j;
+    }
+    accb = 0;
+    // walk the run in tiles
+    bool run_done = false;
+    while (!run_done && pos < end) {
+      const int tile_n = static_cast<int>(min(static_cast<int64_t>(kCellTile), end - pos));
+      __syncthreads();
+      if (threadIdx.x < tile_n) {
+        sKey[threadIdx.x] = keys[pos + threadIdx.x];
+        sObs[threadIdx.x] = order[pos + threadIdx.x];
+      }
+      __syncthreads();
+      int run_n = 0;
+      while (run_n < tile_n && sKey[run_n] == key) ++run_n;
+      if (run_n < tile_n) run_done = true;
+      // stage sqrt(w) * J of the run's observations
+      for (int idx = threadIdx.x; idx < run_n * E; idx += kCellThreads) {
+        const int t = idx / E, e = idx - t * E;
+        const int64_t o = sObs[t];
+        const double rx = out.residual[o], ry = out.residual[n + o];
+        const double sw = sqrt(huber_weight_sq(huber, rx * rx + ry * ry));
+        const int col = (e < rigE) ? (L.jc_rig + e) : (L.jc_intr + (e - rigE));
+        sJx[t * Emax + e] = sw * out.jac[(2 * static_cast<int64_t>(col)) * n + o];
+        sJy[t * Emax + e] = sw * out.jac[(2 * static_cast<int64_t>(col) + 1) * n + o];
+        if (e == 0) {
+          sR[2 * t] = sw * rx;
+          sR[2 * t + 1] = sw * ry;
+        }
+      }
+      __syncthreads();
+#pragma unroll
+      for (int q = 0; q < MAXPAIRS; ++q) {
+        if (threadIdx.x + q * kCellThreads < npairs) {
+          double a = acc[q];
+          const int i = pi[q], j = pj[q];
+          for (int t = 0; t < run_n; ++t)
+            a = fma(sJx[t * Emax + i], sJx[t * Emax + j], fma(sJy[t * Emax + i], sJy[t * Emax + j], a));
+          acc[q] = a;
+        }
+      }
+      if (threadIdx.x < E) {
+        double a = accb;
+        for (int t = 0; t < run_n; ++t)
+          a = fma(sJx[t * Emax + threadIdx.x], sR[2 * t], fma(sJy[t * Emax + threadIdx.x], sR[2 * t + 1], a));
+        accb = a;
+      }
+      pos += run_n;
+    }
+    // flush the run
+    auto gcol = [&](int e) -> int {
+      return (e < rigE) ? (L.d_rig + 6 * cam + e) : (L.d_intr + intr_col(c, cell, e - rigE));
+    };
+#pragma unroll
+    for (int q = 0; q < MAXPAIRS; ++q) {
+      if (threadIdx.x + q * kCellThreads < npairs) {
+        const int gi = gcol(pi[q]), gj = gcol(pj[q]);
+        atomicAdd(&sys.C[static_cast<int64_t>(gi) * L.nd + gj], acc[q]);
+      }
+    }
+    if (threadIdx.x < E) atomicAdd(&sys.bd[gcol(threadIdx.x)], accb);
+  }
+}
+
+void launch_accumulate_cells(const ProblemDev& pb, const Layout& L, const ObsOut& out, const SystemDev& sys,
+                             const uint32_t* keys, const uint32_t* order, uint32_t invalid_key, double huber,
+                             cudaStream_t s) {
+  if (pb.n_obs == 0) return;
+  const int rigE = L.rig_in_state ? 6 : 0;
+  const int Emax = rigE + L.Kmax;
+  if (Emax == 0) return;
+  const int npairs = Emax * (Emax + 1) / 2;
+  const int per_thread = (npairs + kCellThreads - 1) / kCellThreads;
+  const size_t smem = (2 * static_cast<size_t>(kCellTile) * Emax + 2 * kCellTile) * sizeof(double);
+  const unsigned blocks = static_cast<unsigned>((pb.n_obs + kCellChunk - 1) / kCellChunk);
+#define B200BA_LAUNCH_CELLS(MP)                                                                              \
+  do {                                                                                                       \
+    cudaFuncSetAttribute(accumulate_cells_kernel<MP>, cudaFuncAttributeMaxDynamicSharedMemorySize,           \
+                         static_cast<int>(smem));                                                            \
+    accumulate_cells_kernel<MP><<<blocks, kCellThreads, smem, s>>>(pb, L, out, sys, keys, order, invalid_key, \
+                                                                   huber);                                   \
+  } while (0)
+  if (per_thread <= 1)
+    B200BA_LAUNCH_CELLS(1);
+  else if (per_thread <= 3)
+    B200BA_LAUNCH_CELLS(3);
+  else if (per_thread <= 4)
+    B200BA_LAUNCH_CELLS(4);
+  else if (per_thread <= 13)
+    B200BA_LAUNCH_CELLS(13);
+  else
+    B200BA_LAUNCH_CELLS(15);
+#undef B200BA_LAUNCH_CELLS
+}
+
+// ------------------------------------------------------------------------------------------
+// Schur complement helpers (LV/lm_optimizer.h:1246-1369)
+// ------------------------------------------------------------------------------------------
+// Per point: L = chol(D_p + lambda I) (lower), Linv = L^-1 (6 doubles), v = Linv b_p.
+// A non-positive pivot raises *fail (the caller rejects the attempt like a NaN update).
+__global__ void schur_blocks_kernel(int n_points, const double* __restrict__ Dblk, const double* __restrict__ bp,
+                                    double lambda, double* __restrict__ Linv, double* __restrict__ v, int* fail) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n_points) return;
+  const double* D = Dblk + 6 * static_cast<int64_t>(p);
+  const double a00 = D[0] + lambda, a01 = D[1], a02 = D[2], a11 = D[3] + lambda, a12 = D[4], a22 = D[5] + lambda;
+  const double l00s = a00;
+  if (!(l00s > 0)) *fail = 1;
+  const double l00 = sqrt(l00s);
+  const double l10 = a01 / l00, l20 = a02 / l00;
+  const double l11s = a11 - l10 * l10;
+  if (!(l11s > 0)) *fail = 1;
+  const double l11 = sqrt(l11s);
+  const double l21 = (a12 - l20 * l10) / l11;
+  const double l22s = a22 - l20 * l20 - l21 * l21;
+  if (!(l22s > 0)) *fail = 1;
+  const double l22 = sqrt(l22s);
+  // inverse of the lower-triangular factor
+  const double i00 = 1.0 / l00, i11 = 1.0 / l11, i22 = 1.0 / l22;
+  const double i10 = -l10 * i00 * i11;
+  const double i21 = -l21 * i11 * i22;
+  const double i20 = -(l20 * i00 + l21 * i10) * i22;
+  double* Li = Linv + 6 * static_cast<int64_t>(p);
+  Li[0] = i00;
+  Li[1] = i10;
+  Li[2] = i11;
+  Li[3] = i20;
+  Li[4] = i21;
+  Li[5] = i22;
+  const double b0 = bp[3 * p], b1 = bp[3 * p + 1], b2 = bp[3 * p + 2];
+  v[3 * p] = i00 * b0;
+  v[3 * p + 1] = i10 * b0 + i11 * b1;
+  v[3 * p + 2] = i20 * b0 + i21 * b1 + i22 * b2;
+}
+void launch_schur_blocks(int n_points, const double* Dblk, const double* bp, double lambda, double* Linv, double* v,
+                         int* fail, cudaStream_t s) {
+  if (n_points == 0) return;
+  schur_blocks_kernel<<<(n_points + 127) / 128, 128, 0, s>>>(n_points, Dblk, bp, lambda, Linv, v, fail);
+}
+
+// W = L^-1 B, three rows per point. With D^-1 = L^-T L^-1 the contraction B^T D^-1 B
+// (LV/lm_optimizer.h:1294-1311,1328) becomes the symmetric rank-k update W^T W.
+__global__ void schur_scale_rows_kernel(int nd, const double* __restrict__ B, const double* __restrict__ Linv,
+                                        double* __restrict__ W) {
+  const int p = blockIdx.y;
+  const int col = blockIdx.x * blockDim.x + threadIdx.x;
+  if (col >= nd) return;
+  const double* Li = Linv + 6 * static_cast<int64_t>(p);
+  const int64_t r0 = 3 * static_cast<int64_t>(p) * nd + col;
+  const double b0 = B[r0], b1 = B[r0 + nd], b2 = B[r0 + 2 * static_cast<int64_t>(nd)];
+  W[r0] = Li[0] * b0;
+  W[r0 + nd] = fma(Li[1], b0, Li[2] * b1);
+  W[r0 + 2 * static_cast<int64_t>(nd)] = fma(Li[3], b0, fma(Li[4], b1, Li[5] * b2));
+}
+void launch_schur_scale_rows(int n_points, int nd, const double* B, const double* Linv, double* W, cudaStream_t s) {
+  if (n_points == 0 || nd == 0) return;
+  dim3 grid((nd + 255) / 256, n_points);
+  schur_scale_rows_kernel<<<grid, 256, 0, s>>>(nd, B, Linv, W);
+}
+
+// x_p = L^-T y_p, y = v - W x_d (back-substitution, LV/lm_optimizer.h:1366-1367)
+__global__ void schur_backsub_kernel(int n_points, const double* __restrict__ Linv, const double* __restrict__ y,
+                                     double* __restrict__ xp) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n_points) return;
+  const double* Li = Linv + 6 * static_cast<int64_t>(p);
+  const double y0 = y[3 * p], y1 = y[3 * p + 1], y2 = y[3 * p + 2];
+  xp[3 * p] = Li[0] * y0 + Li[1] * y1 + Li[3] * y2;
+  xp[3 * p + 1] = Li[2] * y1 + Li[4] * y2;
+  xp[3 * p + 2] = Li[5] * y2;
+}
+void launch_schur_backsub(int n_points, const double* Linv, const double* y, double* xp, cudaStream_t s) {
+  if (n_points == 0) return;
+  schur_backsub_kernel<<<(n_points + 127) / 128, 128, 0, s>>>(n_points, Linv, y, xp);
+}
+
+// S(i, i) = C(i, i) + lambda (LV/lm_optimizer.h:839-852: the damping is ADDED to the diagonal)
+__global__ void add_diagonal_kernel(int n, double* M, int64_t ld, double lambda) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) M[static_cast<int64_t>(i) * ld + i] += lambda;
+}
+void launch_add_diagonal(int n, double* M, int64_t ld, double lambda, cudaStream_t s) {
+  if (n == 0) return;
+  add_diagonal_kernel<<<(n + 255) / 256, 256, 0, s>>>(n, M, ld, lambda);
+}
+
+// trace of H = sum diag(D_p) + sum diag(C) for the lambda initialisation
+// (LV/lm_optimizer.h:766-781); single block, deterministic order.
+__global__ void trace_kernel(int n_points, const double* __restrict__ Dblk, int nd, const double* __restrict__ C,
+                             double* out) {
+  __shared__ double sh[256];
+  double a = 0;
+  for (int p = threadIdx.x; p < n_points; p += blockDim.x) {
+    const double* D = Dblk + 6 * static_cast<int64_t>(p);
+    a += D[0] + D[3] + D[5];
+  }
+  for (int i = threadIdx.x; i < nd; i += blockDim.x) a += C[static_cast<int64_t>(i) * nd + i];
+  sh[threadIdx.x] = a;
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) {
+    if (threadIdx.x < s) sh[threadIdx.x] += sh[threadIdx.x + s];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *out = sh[0];
+}
+void launch_trace(int n_points, const double* Dblk, int nd, const double* C, double* out, cudaStream_t s) {
+  trace_kernel<<<1, 256, 0, s>>>(n_points, Dblk, nd, C, out);
+}
+
+// ------------------------------------------------------------------------------------------
+// state retraction (JointOptimizationState::operator-=, joint_optimization.cc:172-214)
+// ------------------------------------------------------------------------------------------
+// ApplyLocalUpdateToQuaternion (local_parametrizations/quaternion_parametrization.h:39-60)
+// keeps |update| and sin|u|/|u| in FLOAT; SE3d(q, t) then normalises the quaternion.
+__device__ __forceinline__ void retract_pose(const double* src, double* dst, const double* delta) {
+  const double u0 = -delta[0], u1 = -delta[1], u2 = -delta[2];
+  q4 q{src[0], src[1], src[2], src[3]};
+  const float norm_update = static_cast<float>(sqrt(u0 * u0 + u1 * u1 + u2 * u2));
+  if (norm_update != 0.0f) {
+    // float sin / cos of a float argument, correctly rounded via the double routines
+    const float s = static_cast<float>(sin(static_cast<double>(norm_update)));
+    const float cw = static_cast<float>(cos(static_cast<double>(norm_update)));
+    const float sbu = s / norm_update;
+    q4 uq{static_cast<double>(cw), static_cast<double>(sbu) * u0, static_cast<double>(sbu) * u1,
+          static_cast<double>(sbu) * u2};
+    q = qmul(uq, q);
+  }
+  const double nrm = sqrt(q.w * q.w + q.x * q.x + q.y * q.y + q.z * q.z);
+  dst[0] = q.w / nrm;
+  dst[1] = q.x / nrm;
+  dst[2] = q.y / nrm;
+  dst[3] = q.z / nrm;
+  dst[4] = src[4] - delta[3];
+  dst[5] = src[5] - delta[4];
+  dst[6] = src[6] - delta[5];
+}
+
+__global__ void update_state_kernel(ProblemDev pb, Layout L, StateDev src, StateDev dst, const double* __restrict__ x,
+                                    int64_t n_control_total, int64_t n_param_total) {
+  const int64_t tid = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  // segment 0: point coordinates
+  const int64_t n_pc = 3 * static_cast<int64_t>(L.n_points);
+  if (tid < n_pc) {
+    dst.points[tid] = src.points[tid] - x[tid];
+    return;
+  }
+  int64_t k = tid - n_pc;
+  // segment 1: imageset poses
+  if (k < L.n_imagesets) {
+    retract_pose(src.rig_tr_global + 7 * k, dst.rig_tr_global + 7 * k, x + L.nbd + L.d_pose + 6 * k);
+    return;
+  }
+  k -= L.n_imagesets;
+  // segment 2: camera_tr_rig (variables only when there is more than one camera)
+  if (k < L.n_cameras) {
+    if (L.rig_in_state) {
+      retract_pose(src.camera_tr_rig + 7 * k, dst.camera_tr_rig + 7 * k, x + L.nbd + L.d_rig + 6 * k);
+    } else {
+      for (int i = 0; i < 7; ++i) dst.camera_tr_rig[7 * k + i] = src.camera_tr_rig[7 * k + i];
+    }
+    return;
+  }
+  k -= L.n_cameras;
+  // segment 3: control points of the generic models (models/central_grid.h:168-184,
+  // models/noncentral_generic.h:195-219)
+  if (k < n_control_total) {
+    int cam = 0;
+    int64_t local = k;
+    for (int c = 0; c < L.n_cameras; ++c) {
+      const int64_t G = static_cast<int64_t>(pb.cams[c].gw) * pb.cams[c].gh;
+      if (local < G) {
+        cam = c;
+        break;
+      }
+      local -= G;
+    }
+    const CamDev& c = pb.cams[cam];
+    const double* g = src.intrinsics + c.intr_off + 3 * local;
+    double* go = dst.intrinsics + c.intr_off + 3 * local;
+    const d3 dir = mk3(g[0], g[1], g[2]);
+    if (L.localize_only) {
+      go[0] = dir.x;
+      go[1] = dir.y;
+      go[2] = dir.z;
+      if (c.model_type == B200BA_MODEL_NONCENTRAL_GENERIC) {
+        const int64_t G3 = 3 * static_cast<int64_t>(c.gw) * c.gh;
+        for (int i = 0; i < 3; ++i) go[G3 + i] = g[G3 + i];
+      }
+      return;
+    }
+    d3 t1, t2;
+    compute_tangents(dir, t1, t2);
+    const double* dl = x + L.nbd + L.d_intr + c.upd_off + c.dof_per_point * local;
+    const d3 nd_ = (dir + (-dl[0]) * t1) + (-dl[1]) * t2;
+    const double nn = sqrt(dot3(nd_, nd_));
+    go[0] = nd_.x / nn;
+    go[1] = nd_.y / nn;
+    go[2] = nd_.z / nn;
+    if (c.model_type == B200BA_MODEL_NONCENTRAL_GENERIC) {
+      const int64_t G3 = 3 * static_cast<int64_t>(c.gw) * c.gh;
+      const d3 org = mk3(g[G3], g[G3 + 1], g[G3 + 2]);
+      // ApplyLocalUpdateToLine (line_parametrization.h:107-120)
+      const d3 no = ((org + (-dl[2]) * t1) + (-dl[3]) * t2) + (-dl[4]) * dir;
+      go[G3] = no.x;
+      go[G3 + 1] = no.y;
+      go[G3 + 2] = no.z;
+    }
+    return;
+  }
+  k -= n_control_total;
+  // segment 4: parametric models (models/central_opencv.h:91-94)
+  if (k < n_param_total) {
+    int cam = 0;
+    int64_t local = k;
+    for (int c = 0; c < L.n_cameras; ++c) {
+      const int64_t np = (pb.cams[c].gw == 0) ? 12 : 0;
+      if (local < np) {
+        cam = c;
+        break;
+      }
+      local -= np;
+    }
+    const CamDev& c = pb.cams[cam];
+    const double d = L.localize_only ? 0.0 : x[L.nbd + L.d_intr + c.upd_off + local];
+    dst.intrinsics[c.intr_off + local] = src.intrinsics[c.intr_off + local] - d;
+  }
+}
+void launch_update_state(const ProblemDev& pb, const Layout& L, const StateDev& src, const StateDev& dst,
+                         const double* x, int64_t n_control_total, int64_t n_param_total, cudaStream_t s) {
+  const int64_t n = 3 * static_cast<int64_t>(L.n_points) + L.n_imagesets + L.n_cameras + n_control_total + n_param_total;
+  update_state_kernel<<<static_cast<unsigned>((n + 127) / 128), 128, 0, s>>>(pb, L, src, dst, x, n_control_total,
+                                                                             n_param_total);
+}
+
+// ------------------------------------------------------------------------------------------
+// cost comparison (LV/lm_optimizer.h:993-1011) + totals; two deterministic stages
+// ------------------------------------------------------------------------------------------
+// out[0] = sum of trial costs over residuals valid in BOTH states, out[1] = same for the base
+// state, out[2] = number of such residuals, out[3] = total trial cost (all valid trial
+// residuals), out[4] = number of valid trial residuals, out[5] = sum |r|^2 of valid trial
+// residuals (for the RMSE). base may be NULL (then out[1], out[2] refer to trial only).
+constexpr int kReduceBlocks = 296;  // 2 x 148 SMs
+constexpr int kReduceThreads = 256;
+__global__ void __launch_bounds__(kReduceThreads)
+    cost_reduce_stage1(int64_t n, const double* __restrict__ trial, const double* __restrict__ base,
+                       const double* __restrict__ residual, double* __restrict__ partial) {
+  double a[6] = {0, 0, 0, 0, 0, 0};
+  for (int64_t o = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; o < n;
+       o += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const double t = trial[o];
+    const double b = base ? base[o] : 0.0;
+    if (t >= 0 && b >= 0) {
+      a[0] += t;
+      a[1] += b;
+      a[2] += 1;
+    }
+    if (t >= 0) {
+      a[3] += t;
+      a[4] += 1;
+      if (residual) {
+        const double rx = residual[o], ry = residual[n + o];
+        a[5] += rx * rx + ry * ry;
+      }
+    }
+  }
+  __shared__ double sh[6][kReduceThreads];
+#pragma unroll
+  for (int q = 0; q < 6; ++q) sh[q][threadIdx.x] = a[q];
+  __syncthreads();
+  for (int s = kReduceThreads / 2; s > 0; s >>= 1) {
+    if (threadIdx.x < s) {
+#pragma unroll
+      for (int q = 0; q < 6; ++q) sh[q][threadIdx.x] += sh[q][threadIdx.x + s];
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x < 6) partial[blockIdx.x * 6 + threadIdx.x] = sh[threadIdx.x][0];
+}
+__global__ void cost_reduce_stage2(int nblocks, const double* __restrict__ partial, double* __restrict__ out) {
+  if (threadIdx.x < 6) {
+    double a = 0;
+    for (int b = 0; b < nblocks; ++b) a += partial[b * 6 + threadIdx.x];
+    out[threadIdx.x] = a;
+  }
+}
+void launch_cost_reduce(int64_t n, const double* trial, const double* base, const double* residual, double* partial,
+                        double* out, cudaStream_t s) {
+  cost_reduce_stage1<<<kReduceBlocks, kReduceThreads, 0, s>>>(n, trial, base, residual, partial);
+  cost_reduce_stage2<<<1, 32, 0, s>>>(kReduceBlocks, partial, out);
+}
+int cost_reduce_partial_size() { return kReduceBlocks * 6; }
+
+// ------------------------------------------------------------------------------------------
+// stand-alone model evaluation (b200ba_project / b200ba_unproject)
+// ------------------------------------------------------------------------------------------
+__global__ void project_points_kernel(CamDev c, const double* __restrict__ intr, int64_t n,
+                                      const double* __restrict__ lp, double* __restrict__ px, int32_t* ok) {
+  const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (i >= n) return;
+  const d3 p = mk3(lp[3 * i], lp[3 * i + 1], lp[3 * i + 2]);
+  double x = px[2 * i], y = px[2 * i + 1];
+  bool r = false;
+  if (c.model_type == B200BA_MODEL_CENTRAL_GENERIC) {
+    CentralEval e;
+    if (in_area(c, x, y)) r = central_project(c, intr, rsqrt(dot3(p, p)) * p, x, y, e);
+  } else if (c.model_type == B200BA_MODEL_NONCENTRAL_GENERIC) {
+    NoncentralEval e;
+    d3 t1, t2;
+    double R[2][2];
+    if (in_area(c, x, y)) r = noncentral_project(c, intr, intr + 3 * static_cast<int64_t>(c.gw) * c.gh, p, x, y, e, t1, t2, R);
+  } else {
+    r = opencv_project(c, intr, p, x, y);
+  }
+  px[2 * i] = x;
+  px[2 * i + 1] = y;
+  ok[i] = r ? 1 : 0;
+}
+void launch_project_points(const CamDev& c, const double* intr, int64_t n, const double* lp, double* px, int32_t* ok,
+                           cudaStream_t s) {
+  if (n == 0) return;
+  project_points_kernel<<<static_cast<unsigned>((n + 127) / 128), 128, 0, s>>>(c, intr, n, lp, px, ok);
+}
+
+__global__ void unproject_pixels_kernel(CamDev c, const double* __restrict__ intr, int64_t n,
+                                        const double* __restrict__ px, double* __restrict__ dirs,
+                                        double* __restrict__ origins, int32_t* ok) {
+  const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (i >= n) return;
+  const double x = px[2 * i], y = px[2 * i + 1];
+  d3 d = mk3(0, 0, 0), o = mk3(0, 0, 0);
+  bool r = false;
+  if (in_area(c, x, y)) {
+    if (c.model_type == B200BA_MODEL_CENTRAL_GENERIC) {
+      CentralEval e;
+      central_eval(c, intr, x, y, e);
+      d = e.u;
+      r = true;
+    } else if (c.model_type == B200BA_MODEL_NONCENTRAL_GENERIC) {
+      NoncentralEval e;
+      noncentral_eval(c, intr, intr + 3 * static_cast<int64_t>(c.gw) * c.gh, x, y, e);
+      d = e.u;
+      o = e.o;
+      r = true;
+    }
+  }
+  if (dirs) {
+    dirs[3 * i] = d.x;
+    dirs[3 * i + 1] = d.y;
+    dirs[3 * i + 2] = d.z;
+  }
+  if (origins) {
+    origins[3 * i] = o.x;
+    origins[3 * i + 1] = o.y;
+    origins[3 * i + 2] = o.z;
+  }
+  ok[i] = r ? 1 : 0;
+}
+void launch_unproject_pixels(const CamDev& c, const double* intr, int64_t n, const double* px, double* dirs,
+                             double* origins, int32_t* ok, cudaStream_t s) {
+  if (n == 0) return;
+  unproject_pixels_kernel<<<static_cast<unsigned>((n + 127) / 128), 128, 0, s>>>(c, intr, n, px, dirs, origins, ok);
+}
+
+// Generic small-block Schur preparation for b200ba_schur_solve (block size <= 6, arbitrary
+// symmetric blocks like the reference's known-answer test): D^-1 by Gauss-Jordan with partial
+// pivoting on the symmetrised block; DinvB = D^-1 B, Dinvb = D^-1 b1.
+__global__ void generic_block_inverse_kernel(int bs, int nb, int nd, const double* __restrict__ D,
+                                             const double* __restrict__ B, const double* __restrict__ b1,
+                                             double* __restrict__ DinvB, double* __restrict__ Dinvb) {
+  const int blk = blockIdx.x;
+  __shared__ double inv[36];
+  if (threadIdx.x == 0) {
+    double a[6][12];
+    for (int i = 0; i < bs; ++i)
+      for (int j = 0; j < bs; ++j) {
+        a[i][j] = (i <= j) ? D[(static_cast<int64_t>(blk) * bs + i) * bs + j] : D[(static_cast<int64_t>(blk) * bs + j) * bs + i];
+        a[i][bs + j] = (i == j) ? 1.0 : 0.0;
+      }
+    for (int col = 0; col < bs; ++col) {
+      int piv = col;
+      for (int r = col + 1; r < bs; ++r)
+        if (fabs(a[r][col]) > fabs(a[piv][col])) piv = r;
+      if (piv != col)
+        for (int j = 0; j < 2 * bs; ++j) {
+          const double t = a[col][j];
+          a[col][j] = a[piv][j];
+          a[piv][j] = t;
+        }
+      const double ip = 1.0 / a[col][col];
+      for (int j = 0; j < 2 * bs; ++j) a[col][j] *= ip;
+      for (int r = 0; r < bs; ++r)
+        if (r != col) {
+          const double f = a[r][col];
+          for (int j = 0; j < 2 * bs; ++j) a[r][j] -= f * a[col][j];
+        }
+    }
+    for (int i = 0; i < bs; ++i)
+      for (int j = 0; j < bs; ++j) inv[i * bs + j] = a[i][bs + j];
+  }
+  __syncthreads();
+  for (int col = threadIdx.x; col < nd + 1; col += blockDim.x) {
+    for (int r = 0; r < bs; ++r) {
+      double s = 0;
+      for (int k = 0; k < bs; ++k) {
+        const double bv = (col < nd) ? B[(static_cast<int64_t>(blk) * bs + k) * nd + col] : b1[blk * bs + k];
+        s += inv[r * bs + k] * bv;
+      }
+      if (col < nd)
+        DinvB[(static_cast<int64_t>(blk) * bs + r) * nd + col] = s;
+      else
+        Dinvb[blk * bs + r] = s;
+    }
+  }
+}
+void launch_generic_block_inverse(int bs, int nb, int nd, const double* D, const double* B, const double* b1,
+                                  double* DinvB, double* Dinvb, cudaStream_t s) {
+  if (nb == 0) return;
+  generic_block_inverse_kernel<<<nb, 128, 0, s>>>(bs, nb, nd, D, B, b1, DinvB, Dinvb);
+}
+
+// mirror the valid (row <= col) triangle of a row-major square matrix into the other one
+__global__ void symmetrize_kernel(int n, double* M) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  const int i = blockIdx.y * blockDim.y + threadIdx.y;
+  if (i < n && j < n && i < j) M[static_cast<int64_t>(j) * n + i] = M[static_cast<int64_t>(i) * n + j];
+}
+void launch_symmetrize(int n, double* M, cudaStream_t s) {
+  if (n == 0) return;
+  dim3 block(32, 8);
+  dim3 grid((n + 31) / 32, (n + 7) / 8);
+  symmetrize_kernel<<<grid, block, 0, s>>>(n, M);
+}
+
+}  // namespace b200ba

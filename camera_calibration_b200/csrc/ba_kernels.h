@@ -1,0 +1,42 @@
+// ba_kernels.h -- launchers of the kernels in ba_kernels.cu (internal to libb200ba.so).
+#pragma once
+#include "ba_common.h"
+
+namespace b200ba {
+
+void launch_prepare_state(const ProblemDev& pb, const Layout& L, const StateDev& st, int64_t n_control_total,
+                          cudaStream_t s);
+// uniform_model: the model type shared by all cameras, or -1 for a mixed rig (runtime switch)
+void launch_residual_jacobian(int uniform_model, bool jac, const ProblemDev& pb, const Layout& L,
+                              const StateDev& st, double2* last_projection, const ObsOut& out, double huber,
+                              cudaStream_t s);
+void launch_accumulate_scatter(const ProblemDev& pb, const Layout& L, const ObsOut& out, const SystemDev& sys,
+                               double huber, cudaStream_t s);
+void launch_cell_keys(const ProblemDev& pb, const ObsOut& out, uint32_t* keys, uint32_t* vals, uint32_t invalid_key,
+                      cudaStream_t s);
+size_t sort_temp_bytes(int64_t n, int end_bit);
+void sort_pairs(void* temp, size_t temp_bytes, const uint32_t* keys_in, uint32_t* keys_out, const uint32_t* vals_in,
+                uint32_t* vals_out, int64_t n, int end_bit, cudaStream_t s);
+void launch_accumulate_cells(const ProblemDev& pb, const Layout& L, const ObsOut& out, const SystemDev& sys,
+                             const uint32_t* keys, const uint32_t* order, uint32_t invalid_key, double huber,
+                             cudaStream_t s);
+void launch_schur_blocks(int n_points, const double* Dblk, const double* bp, double lambda, double* Linv, double* v,
+                         int* fail, cudaStream_t s);
+void launch_schur_scale_rows(int n_points, int nd, const double* B, const double* Linv, double* W, cudaStream_t s);
+void launch_schur_backsub(int n_points, const double* Linv, const double* y, double* xp, cudaStream_t s);
+void launch_add_diagonal(int n, double* M, int64_t ld, double lambda, cudaStream_t s);
+void launch_trace(int n_points, const double* Dblk, int nd, const double* C, double* out, cudaStream_t s);
+void launch_update_state(const ProblemDev& pb, const Layout& L, const StateDev& src, const StateDev& dst,
+                         const double* x, int64_t n_control_total, int64_t n_param_total, cudaStream_t s);
+void launch_cost_reduce(int64_t n, const double* trial, const double* base, const double* residual, double* partial,
+                        double* out, cudaStream_t s);
+int cost_reduce_partial_size();
+void launch_project_points(const CamDev& c, const double* intr, int64_t n, const double* lp, double* px, int32_t* ok,
+                           cudaStream_t s);
+void launch_unproject_pixels(const CamDev& c, const double* intr, int64_t n, const double* px, double* dirs,
+                             double* origins, int32_t* ok, cudaStream_t s);
+void launch_generic_block_inverse(int bs, int nb, int nd, const double* D, const double* B, const double* b1,
+                                  double* DinvB, double* Dinvb, cudaStream_t s);
+void launch_symmetrize(int n, double* M, cudaStream_t s);
+
+}  // namespace b200ba

@@ -178,6 +178,8 @@ def central_project_np(cam: Camera, grid, local_points, init_xy, iters=30):
         step = np.sqrt(dx * dx + dy * dy)
         scale = np.minimum(1.0, 50.0 / np.maximum(step, 1e-12))
         x, y = _clamp_px(cam, x - scale * dx, y - scale * dy)
+        if np.nanmax(step) < 1e-10:
+            break
     u = central_unproject_np(cam, grid, x, y)
     err = np.linalg.norm(u - d, axis=-1)
     interior = (x > cam.calibration_min_x) & (y > cam.calibration_min_y) & (x < cam.calibration_max_x + 0.999) & (y < cam.calibration_max_y + 0.999)
@@ -221,6 +223,8 @@ def noncentral_project_np(cam: Camera, dir_grid, point_grid, local_points, init_
         step = np.sqrt(dx * dx + dy * dy)
         scale = np.minimum(1.0, 50.0 / np.maximum(step, 1e-12))
         x, y = _clamp_px(cam, x - scale * dx, y - scale * dy)
+        if np.nanmax(step) < 1e-10:
+            break
     r = _noncentral_residual(cam, dir_grid, point_grid, local_points, x, y)
     err = np.linalg.norm(r, axis=-1)
     interior = (x > cam.calibration_min_x) & (y > cam.calibration_min_y) & (x < cam.calibration_max_x + 0.999) & (y < cam.calibration_max_y + 0.999)
@@ -401,17 +405,23 @@ def make_problem(config: int = 2, *, seed: Optional[int] = None, n_imagesets: Op
             if C_ > 1:
                 # look at the pattern from the middle of the rig
                 pose[4] += 0.05 * (C_ - 1) * (0.3 if C_ > 2 else 1.0)
-            per_cam = []
+            # cheap visibility test with the pinhole the ground-truth model was built from
             vis_ok = True
+            lps = []
             for c in range(C_):
                 lp = pose_apply(pose_mul(ctr[c], pose), points)
-                xy, ok = _project_gt(cams[c], gt_intr[c], cam_f[c], lp)
-                per_cam.append((xy, ok))
-                if ok.mean() < (min_visible if C_ == 1 else 0.3):
+                lps.append(lp)
+                z = np.where(lp[:, 2] > 1e-6, lp[:, 2], 1.0)
+                ux = cam_f[c] * lp[:, 0] / z + W / 2.0
+                uy = cam_f[c] * lp[:, 1] / z + H / 2.0
+                vis = (lp[:, 2] > 1e-6) & in_area(cams[c], ux, uy)
+                if vis.mean() < (min_visible if C_ == 1 else 0.3):
                     vis_ok = False
-            if vis_ok:
-                break
-            n_redraw += 1
+            if not vis_ok:
+                n_redraw += 1
+                continue
+            per_cam = [_project_gt(cams[c], gt_intr[c], cam_f[c], lps[c]) for c in range(C_)]
+            break
         else:
             raise RuntimeError("could not draw a pose that sees the pattern")
         rtg[i] = pose

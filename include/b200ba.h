@@ -34,6 +34,12 @@
 
 #include <stdint.h>
 
+#if defined(__GNUC__)
+#define B200BA_API __attribute__((visibility("default")))
+#else
+#define B200BA_API
+#endif
+
 #ifdef __cplusplus
 extern "C" {
 #endif
@@ -77,9 +83,9 @@ typedef struct b200ba_camera {
  *   central-generic   : 3*gw*gh               (grid, row-major, xyz; central_grid.h m_grid)
  *   noncentral-generic: 3*gw*gh direction grid followed by 3*gw*gh point grid
  *   central-opencv    : 12  (fx fy cx cy k1..k6 p1 p2; central_opencv.cc:77-88)  */
-int64_t b200ba_intrinsics_size(const b200ba_camera* cam);
+B200BA_API int64_t b200ba_intrinsics_size(const b200ba_camera* cam);
 /* update_parameter_count() of the model: 2*gw*gh / 5*gw*gh / 12. */
-int32_t b200ba_update_parameter_count(const b200ba_camera* cam);
+B200BA_API int32_t b200ba_update_parameter_count(const b200ba_camera* cam);
 
 /* The constant part of a BA problem: the flattened Dataset (dataset.h:57-212)
  * restricted to used imagesets. Observations are listed in the reference's
@@ -125,7 +131,7 @@ typedef struct b200ba_options {
   int32_t print_progress;
 } b200ba_options;
 
-void b200ba_default_options(b200ba_options* opt);
+B200BA_API void b200ba_default_options(b200ba_options* opt);
 
 #define B200BA_MAX_TRACE 128
 
@@ -152,22 +158,22 @@ typedef struct b200ba_handle b200ba_handle;
 
 /* ---- lifetime ---------------------------------------------------------- */
 /* device < 0: use the current CUDA device. Copies the problem to the device. */
-int b200ba_create(const b200ba_problem* problem, int device, b200ba_handle** out);
-void b200ba_destroy(b200ba_handle* h);
-const char* b200ba_last_error(const b200ba_handle* h); /* h may be NULL: last create error */
+B200BA_API int b200ba_create(const b200ba_problem* problem, int device, b200ba_handle** out);
+B200BA_API void b200ba_destroy(b200ba_handle* h);
+B200BA_API const char* b200ba_last_error(const b200ba_handle* h); /* h may be NULL: last create error */
 
 /* ---- state transfer ------------------------------------------------------ */
-int b200ba_set_state(b200ba_handle* h, const b200ba_state* state);
-int b200ba_get_state(b200ba_handle* h, b200ba_state* state);
+B200BA_API int b200ba_set_state(b200ba_handle* h, const b200ba_state* state);
+B200BA_API int b200ba_get_state(b200ba_handle* h, b200ba_state* state);
 
 /* ---- the hot path -------------------------------------------------------- */
 /* Equivalent of OptimizeJointly (joint_optimization.cc:757-953) on the state held
  * by the handle; the state stays resident on the device between calls. */
-int b200ba_optimize(b200ba_handle* h, const b200ba_options* opt, b200ba_report* report);
+B200BA_API int b200ba_optimize(b200ba_handle* h, const b200ba_options* opt, b200ba_report* report);
 
 /* Convenience: set_state + optimize + get_state with HOST buffers, i.e. exactly
  * what a call of the reference's OptimizeJointly(Dataset&, BAState*) does. */
-int b200ba_optimize_host(b200ba_handle* h, b200ba_state* state, const b200ba_options* opt,
+B200BA_API int b200ba_optimize_host(b200ba_handle* h, b200ba_state* state, const b200ba_options* opt,
                          b200ba_report* report);
 
 /* ---- building blocks, exposed for parity tests and profiling -------------- */
@@ -177,44 +183,44 @@ int b200ba_optimize_host(b200ba_handle* h, b200ba_state* state, const b200ba_opt
  *   costs       [n_obs]   out, nullable   Huber cost, -1 for invalid residuals
  *   total_cost            out, nullable
  * Updates last_projection on the device like the reference mutates the Dataset. */
-int b200ba_evaluate(b200ba_handle* h, const b200ba_options* opt, int compute_jacobians,
+B200BA_API int b200ba_evaluate(b200ba_handle* h, const b200ba_options* opt, int compute_jacobians,
                     double* residuals, double* costs, double* total_cost);
 
 /* Per-observation Jacobians of the last b200ba_evaluate(compute_jacobians=1):
  *   j_point [n_obs*2*3], j_pose [n_obs*2*6], j_rig [n_obs*2*6] (nullable / zero if 1 camera),
  *   j_intr [n_obs*2*K], intr_index [n_obs*K] (global column of each entry), K = max over cameras
  *   of IntrinsicsJacobianSize (32 / 80 / 12). Row-major [obs][row][col]. */
-int b200ba_get_jacobians(b200ba_handle* h, double* j_point, double* j_pose, double* j_rig,
+B200BA_API int b200ba_get_jacobians(b200ba_handle* h, double* j_point, double* j_pose, double* j_rig,
                          double* j_intr, int32_t* intr_index, int32_t K);
 
 /* Build H, b at the current state (hot loop 1) and download them as one dense
  * upper-triangular matrix in the reference's variable ordering
  * (joint_optimization.cc:49-59). H [n*n] row-major, b [n]; only for small problems. */
-int b200ba_build_system(b200ba_handle* h, const b200ba_options* opt, int32_t n, double* H,
+B200BA_API int b200ba_build_system(b200ba_handle* h, const b200ba_options* opt, int32_t n, double* H,
                         double* b, double* cost);
-int32_t b200ba_degrees_of_freedom(const b200ba_handle* h, const b200ba_options* opt);
+B200BA_API int32_t b200ba_degrees_of_freedom(const b200ba_handle* h, const b200ba_options* opt);
 
 /* Stand-alone Schur-complement solve (libvis lm_optimizer.h:1246-1369) of
  *   [D B; B^T C] x = [b1; b2],  D block-diagonal with n_blocks blocks of block_size (<= 6).
  * Only the upper triangles of D blocks and C are read. Host buffers, row-major:
  *   D [n_blocks*bs*bs], B [(n_blocks*bs) * n_dense], C [n_dense*n_dense]. */
-int b200ba_schur_solve(int device, int32_t block_size, int32_t n_blocks, int32_t n_dense,
+B200BA_API int b200ba_schur_solve(int device, int32_t block_size, int32_t n_blocks, int32_t n_dense,
                        const double* D, const double* B, const double* C, const double* b1,
                        const double* b2, double* x);
 
 /* CameraModel::ProjectWithInitialEstimate / Unproject for n points, on the device.
  * pixels is in/out (initial estimate / result); ok[i] = 1 on success. */
-int b200ba_project(int device, const b200ba_camera* cam, const double* intrinsics, int64_t n,
+B200BA_API int b200ba_project(int device, const b200ba_camera* cam, const double* intrinsics, int64_t n,
                    const double* local_points, double* pixels, int32_t* ok);
-int b200ba_unproject(int device, const b200ba_camera* cam, const double* intrinsics, int64_t n,
+B200BA_API int b200ba_unproject(int device, const b200ba_camera* cam, const double* intrinsics, int64_t n,
                      const double* pixels, double* directions, double* origins, int32_t* ok);
 
 /* ---- multi-GPU: imagesets sharded over ranks, one NCCL all-reduce per H/b build --- */
 #define B200BA_NCCL_UNIQUE_ID_BYTES 128
-int b200ba_nccl_unique_id(uint8_t id[B200BA_NCCL_UNIQUE_ID_BYTES]);
+B200BA_API int b200ba_nccl_unique_id(uint8_t id[B200BA_NCCL_UNIQUE_ID_BYTES]);
 /* Every rank creates its handle from ITS shard of the observations (all ranks use the
  * same n_imagesets / n_points / cameras) and then joins the communicator. */
-int b200ba_comm_init(b200ba_handle* h, const uint8_t id[B200BA_NCCL_UNIQUE_ID_BYTES], int rank,
+B200BA_API int b200ba_comm_init(b200ba_handle* h, const uint8_t id[B200BA_NCCL_UNIQUE_ID_BYTES], int rank,
                      int n_ranks);
 
 /* ---- instrumentation ------------------------------------------------------ */
@@ -231,9 +237,9 @@ typedef struct b200ba_timings {
   double total_ms;
   int64_t kernel_launches;   /* kernels of this library launched */
 } b200ba_timings;
-int b200ba_get_timings(const b200ba_handle* h, b200ba_timings* t);
+B200BA_API int b200ba_get_timings(const b200ba_handle* h, b200ba_timings* t);
 
-const char* b200ba_version(void);
+B200BA_API const char* b200ba_version(void);
 
 #ifdef __cplusplus
 }

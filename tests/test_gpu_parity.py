@@ -1,0 +1,274 @@
+"""Parity of the CUDA path (through the C ABI) against the CPU oracle and the reference's
+golden vectors. Needs a B200: run with ``pytest -m gpu``.
+
+Tolerances (FP64 on both sides, same algorithm, different summation order):
+  per-observation pixel / residual         1e-9 px absolute
+  per-observation Jacobian entries         1e-8 relative to the largest entry of the block
+  H, b entries                             1e-8 relative to the largest entry
+  cost trajectory of the LM loop           1e-7 relative per iteration, identical accept sequence
+  final parameters                         1e-6 absolute (gauge is not fixed; identical iteration
+                                           histories make direct comparison meaningful)
+"""
+import numpy as np
+import pytest
+
+from camera_calibration_b200 import api, cabi, synthetic
+from tests import helpers
+
+pytestmark = pytest.mark.gpu
+
+
+def _small(cfg):
+    if cfg == 1:
+        return synthetic.make_problem(1, n_imagesets=8, lattice=(10, 10))
+    if cfg == 2:
+        return synthetic.make_problem(2, n_imagesets=12, lattice=(12, 10), image_size=(410, 290))
+    if cfg == 3:
+        return synthetic.make_problem(3, n_imagesets=10, lattice=(10, 8), image_size=(300, 240))
+    if cfg == 4:
+        return synthetic.make_problem(4, n_imagesets=10, lattice=(10, 8), image_size=(410, 290))
+    raise ValueError(cfg)
+
+
+def test_schur_known_answer_gpu():
+    """libvis/src/libvis/test/lm_optimizer.cc:471-557 through b200ba_schur_solve."""
+    nan = np.nan
+    D = np.array([[[1, 5], [nan, 6]], [[9, 5], [nan, 4]]], dtype=float)
+    B = np.array([[3, 4], [7, 8], [7, 6], [3, 2]], dtype=float)
+    Cm = np.array([[1, 4], [nan, 7]], dtype=float)
+    x = api.schur_solve(2, D, B, Cm, [1, 2, 3, 4], [5, 6])
+    expected = np.array([73.667, 171.667, 189.667, -294.333, 465.667, -582.0])
+    assert np.all(np.abs(x - expected) < 0.3)
+    assert np.allclose(x, [221 / 3, 515 / 3, 569 / 3, -883 / 3, 1397 / 3, -582.0], rtol=1e-9)
+
+
+def test_schur_solve_matches_oracle(oracle_lib):
+    rng = np.random.default_rng(1)
+    nb, bs, nd = 30, 3, 40
+    n = nb * bs + nd
+    J = rng.standard_normal((2 * n, n))
+    H = J.T @ J + 0.5 * np.eye(n)
+    for i in range(nb):
+        for j in range(nb):
+            if i != j:
+                H[i * bs:(i + 1) * bs, j * bs:(j + 1) * bs] = 0
+    b = rng.standard_normal(n)
+    D = np.stack([np.triu(H[i * bs:(i + 1) * bs, i * bs:(i + 1) * bs]) for i in range(nb)])
+    args = (bs, D, H[:nb * bs, nb * bs:], np.triu(H[nb * bs:, nb * bs:]), b[:nb * bs], b[nb * bs:])
+    xg = api.schur_solve(*args)
+    xo = oracle_lib.schur_solve(*args)
+    assert np.allclose(xg, xo, rtol=1e-9, atol=1e-11)
+
+
+def test_noncentral_orthographic_known_answers_gpu():
+    """applications/camera_calibration/src/camera_calibration/test/noncentral_generic_test.cc:49-112."""
+    cam, intr = helpers.orthographic_noncentral()
+    m = api.NoncentralGenericModel(4, 4, 0, 0, 99, 99, 100, 100)
+    m.set_flat_intrinsics(intr)
+    ok, d, o = m.Unproject(50.0, 50.0)
+    assert ok and abs(o[0] - 1.5) < 1e-5 and abs(o[1] - 1.5) < 1e-5
+    assert abs(d[0]) < 1e-5 and abs(d[1]) < 1e-5 and abs(abs(d[2]) - 1) < 1e-5
+    ok, px = m.Project([1.5, 1.5, 42.12345])
+    assert ok and abs(px[0] - 50) < 1e-5 and abs(px[1] - 50) < 1e-5
+    for gx, gy in ((1.1, 1.2), (1.001, 1.999)):
+        ok, px = m.Project([gx, gy, 42.12345])
+        ex, ey = synthetic.grid_point_to_pixel(cam, gx, gy)
+        assert ok and abs(px[0] - ex) < 1e-5 and abs(px[1] - ey) < 1e-5
+
+
+def test_models_match_oracle(oracle_lib):
+    """Project / Unproject of the three models against the oracle on seeded inputs, plus the
+    reference's own round-trip thresholds (test/util.h:112-164: 1e-4 px; generic_models main.cc: 1e-3)."""
+    rng = np.random.default_rng(3)
+    # real calibrated camera
+    cam, grid = helpers.real_camera()
+    m = api.CentralGenericModel(cam.grid_width, cam.grid_height, cam.calibration_min_x, cam.calibration_min_y,
+                                cam.calibration_max_x, cam.calibration_max_y, cam.width, cam.height)
+    m.set_flat_intrinsics(grid.reshape(-1))
+    px = np.stack([rng.uniform(15, 624.9, 4000), rng.uniform(16, 464.9, 4000)], -1)
+    d, _, ok = m.UnprojectMany(px)
+    do, _, oko = oracle_lib.unproject(cam, grid, px)
+    assert ok.all() and oko.all()
+    assert np.abs(d - do).max() < 1e-13
+    rp, ok2 = m.ProjectMany(d * rng.uniform(0.5, 3.0, (4000, 1)))
+    assert ok2.all()
+    assert np.linalg.norm(rp - px, axis=1).max() < 1e-4
+    rpo, _ = oracle_lib.project(cam, grid, d)
+    assert np.abs(rp - rpo).max() < 1e-8
+    # noncentral (synthetic near-central) and OpenCV
+    for cfg in (3, 1):
+        sp = _small(cfg)
+        c = sp.problem.cameras[0]
+        intr = sp.gt_state.intrinsics[0]
+        lp = synthetic.pose_apply(sp.gt_state.rig_tr_global[0], sp.gt_state.points)
+        mm = api.dataset_from_flat(sp.problem, sp.gt_state)[1].intrinsics[0]
+        pg, okg = mm.ProjectMany(lp)
+        po, oko = oracle_lib.project(c, intr, lp)
+        assert np.array_equal(okg, oko)
+        assert np.abs(pg[okg] - po[okg]).max() < 1e-8
+
+
+@pytest.mark.parametrize("cfg", [1, 2, 3, 4])
+def test_residuals_and_jacobians_match_oracle(oracle_lib, cfg):
+    sp = _small(cfg)
+    opt = cabi.default_options()
+    with api.BundleAdjuster(sp.problem) as adj:
+        adj.set_state(sp.init_state)
+        g = adj.evaluate(opt, compute_jacobians=True)
+        lastp = adj.get_state().last_projection
+    o = oracle_lib.evaluate(sp.problem, sp.init_state, opt, True)
+    valid_o = o["costs"] >= 0
+    valid_g = g["costs"] >= 0
+    assert np.array_equal(valid_o, valid_g)
+    assert np.abs(g["residuals"][valid_g] - o["residuals"][valid_o]).max() < 1e-9
+    assert np.abs(g["costs"] - o["costs"]).max() < 1e-9
+    assert abs(g["total_cost"] - o["total_cost"]) < 1e-9 * max(1.0, o["total_cost"])
+    assert np.abs(lastp[valid_g] - o["last_projection"][valid_o]).max() < 1e-9
+    hj = o["has_jacobian"] == 1
+    assert hj.sum() == valid_o.sum()
+    assert np.array_equal(g["intr_index"][hj], o["intr_index"][hj])
+    for k in ("j_point", "j_pose", "j_rig", "j_intr"):
+        a, b = g[k][hj], o[k][hj]
+        scale = max(np.abs(b).max(), 1e-30)
+        assert np.abs(a - b).max() < 1e-8 * scale, (cfg, k, np.abs(a - b).max(), scale)
+
+
+@pytest.mark.parametrize("cfg", [1, 2, 3, 4])
+def test_normal_equations_match_oracle(oracle_lib, cfg):
+    sp = _small(cfg)
+    opt = cabi.default_options()
+    with api.BundleAdjuster(sp.problem) as adj:
+        adj.set_state(sp.init_state)
+        Hg, bg, cg = adj.build_system(opt)
+    Ho, bo, co = oracle_lib.build_system(sp.problem, sp.init_state, opt)
+    assert Hg.shape == Ho.shape
+    assert abs(cg - co) < 1e-9 * max(1.0, co)
+    assert np.abs(Hg - Ho).max() < 1e-8 * np.abs(Ho).max()
+    assert np.abs(bg - bo).max() < 1e-8 * np.abs(bo).max()
+    # nothing outside the reference's sparsity pattern, nothing below the diagonal
+    assert np.all(Hg[np.tril_indices_from(Hg, -1)] == 0)
+    assert np.array_equal(Hg != 0, Ho != 0) or np.abs(Hg[(Hg != 0) != (Ho != 0)]).max() < 1e-12 * np.abs(Ho).max()
+
+
+@pytest.mark.parametrize("cfg,iters", [(1, 8), (2, 8), (3, 6), (4, 6)])
+def test_lm_trajectory_matches_oracle(oracle_lib, cfg, iters):
+    """Same accept / reject sequence, same cost after every iteration, same final state."""
+    sp = _small(cfg)
+    opt = cabi.default_options(max_iteration_count=iters)
+    st = sp.init_state.copy()
+    with api.BundleAdjuster(sp.problem) as adj:
+        rep = adj.optimize_host(st, opt)
+    ost, orep = oracle_lib.optimize(sp.problem, sp.init_state, opt)
+    gc, gl, ga = rep.trace()
+    oc, ol, oa = orep.trace()
+    assert ga == oa
+    assert np.allclose(gc, oc, rtol=1e-7)
+    assert np.allclose(gl, ol, rtol=1e-6)
+    assert abs(rep.rmse - orep.rmse) < 1e-6  # north-star: RMSE within 1e-6 px
+    assert rep.n_valid == orep.n_valid
+    assert np.abs(st.points - ost.points).max() < 1e-6
+    assert np.abs(st.rig_tr_global - ost.rig_tr_global).max() < 1e-6
+    for a, b in zip(st.intrinsics, ost.intrinsics):
+        assert np.abs(a - b).max() < 1e-6 * max(1.0, np.abs(b).max())
+
+
+def test_matches_reference_numeric_path_on_rmse(oracle_lib):
+    """The reference differentiates numerically (delta 1e-4); the analytic device path must land
+    on the same optimum: final RMSE within 1e-6 px... on a noisy, well-constrained problem after
+    the same number of iterations the difference is second order in the Jacobian error."""
+    sp = synthetic.make_problem(2, n_imagesets=30, lattice=(14, 12), image_size=(410, 290), cell=40)
+    opt = cabi.default_options(max_iteration_count=25)
+    st = sp.init_state.copy()
+    with api.BundleAdjuster(sp.problem) as adj:
+        rep = adj.optimize_host(st, opt)
+    opt_n = cabi.default_options(max_iteration_count=25, jacobian_mode=cabi.JACOBIAN_NUMERIC)
+    _, orep = oracle_lib.optimize(sp.problem, sp.init_state, opt_n)
+    assert abs(rep.rmse - orep.rmse) < 2e-5
+    assert abs(rep.final_cost - orep.final_cost) < 1e-3 * orep.final_cost
+
+
+def test_reference_ba_test_threshold_gpu():
+    """TestOptimizeJointly (test/util.h:275-571): noise-free observations, perturbed state,
+    <= 20 single-iteration calls through the reference-shaped API; final cost <= 1e-6."""
+    problem, st, _ = helpers.reference_ba_test_problem(num_cameras=1, n_points=150, n_poses=100)
+    ds, state = api.dataset_from_flat(problem, st)
+    lam = -1.0
+    cost = np.inf
+    for i in range(20):
+        cost, lam, performed = api.OptimizeJointly(ds, state, 1, lam, 1e-4, 0, False, True, api.SchurMode.Dense,
+                                                   print_progress=False)
+        if not performed:
+            break
+    assert cost <= 1e-6
+
+
+def test_rig_ba_test_threshold_gpu():
+    problem, st, _ = helpers.reference_ba_test_problem(num_cameras=2, n_points=100, n_poses=60)
+    ds, state = api.dataset_from_flat(problem, st)
+    lam = -1.0
+    cost = np.inf
+    for i in range(40):
+        cost, lam, performed = api.OptimizeJointly(ds, state, 1, lam, 1e-4, 0, False, True, api.SchurMode.Dense,
+                                                   print_progress=False)
+        if not performed:
+            break
+    assert cost <= 2e-6
+
+
+def test_localize_only_matches_oracle(oracle_lib):
+    """The --bundle_adjustment tool's mode (tools/bundle_adjustment.cc:190-200): intrinsics fixed."""
+    sp = _small(2)
+    opt = cabi.default_options(max_iteration_count=4, localize_only=1)
+    st = sp.init_state.copy()
+    with api.BundleAdjuster(sp.problem) as adj:
+        rep = adj.optimize_host(st, opt)
+    ost, orep = oracle_lib.optimize(sp.problem, sp.init_state, opt)
+    assert rep.trace()[2] == orep.trace()[2]
+    assert np.allclose(rep.trace()[0], orep.trace()[0], rtol=1e-7)
+    assert np.array_equal(st.intrinsics[0], sp.init_state.intrinsics[0])
+
+
+def test_shards_sum_to_full_system():
+    """Multi-GPU contract on one device: the partial H, b of the two imageset shards add up to
+    the full system (what the NCCL all-reduce computes)."""
+    sp = _small(2)
+    opt = cabi.default_options()
+    with api.BundleAdjuster(sp.problem) as adj:
+        adj.set_state(sp.init_state)
+        H, b, c = adj.build_system(opt)
+    Hs, bs, cs = 0, 0, 0
+    for r in range(2):
+        shard = sp.problem.shard(r, 2)
+        st = sp.init_state.copy()
+        st.last_projection = st.last_projection[sp.problem.shard_indices(r, 2)]
+        with api.BundleAdjuster(shard) as adj:
+            adj.set_state(st)
+            Hr, br, cr = adj.build_system(opt)
+        Hs, bs, cs = Hs + Hr, bs + br, cs + cr
+    assert np.abs(Hs - H).max() < 1e-10 * np.abs(H).max()
+    assert np.abs(bs - b).max() < 1e-10 * np.abs(b).max()
+    assert abs(cs - c) < 1e-10 * c
+
+
+def test_full_size_properties():
+    """BASELINE config 2 at full size (about 1 M observations, 10 080 intrinsics): properties
+    that do not need the oracle -- every observation is valid at the ground truth, the cost at
+    the ground truth is the noise level, an LM iteration from the perturbed state is accepted and
+    lowers the cost, evaluation is idempotent under the warm start."""
+    sp = synthetic.make_problem(2)
+    assert sp.n_obs > 900_000
+    opt = cabi.default_options(max_iteration_count=2)
+    with api.BundleAdjuster(sp.problem) as adj:
+        adj.set_state(sp.gt_state)
+        e0 = adj.evaluate(opt)
+        assert (e0["costs"] >= 0).all()
+        rmse_gt = np.sqrt((e0["residuals"] ** 2).sum() / sp.n_obs)
+        assert abs(rmse_gt - 0.05 * np.sqrt(2)) < 2e-3  # noise sigma 0.05 px per axis
+        e1 = adj.evaluate(opt)
+        assert np.abs(e1["residuals"] - e0["residuals"]).max() < 1e-7
+        st = sp.init_state.copy()
+        rep = adj.optimize_host(st, opt)
+        assert rep.num_iterations_performed == 2
+        c = rep.trace()[0]
+        assert c[0] < rep.initial_cost and c[1] < c[0]
+        assert rep.n_valid + rep.n_invalid == sp.n_obs
