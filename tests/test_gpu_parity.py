@@ -265,7 +265,12 @@ def test_full_size_properties():
         rmse_gt = np.sqrt((e0["residuals"] ** 2).sum() / sp.n_obs)
         assert abs(rmse_gt - 0.05 * np.sqrt(2)) < 2e-3  # noise sigma 0.05 px per axis
         e1 = adj.evaluate(opt)
-        assert np.abs(e1["residuals"] - e0["residuals"]).max() < 1e-7
+        # cold start (image centre) vs. warm start: both stop at the reference's projection
+        # threshold (squared direction error < 1e-12 before the last step); the reference's own
+        # re-projection tests allow 1e-4 px (test/util.h:157-158)
+        assert np.abs(e1["residuals"] - e0["residuals"]).max() < 1e-4
+        e2 = adj.evaluate(opt)
+        assert np.abs(e2["residuals"] - e1["residuals"]).max() < 1e-6
         st = sp.init_state.copy()
         rep = adj.optimize_host(st, opt)
         assert rep.num_iterations_performed == 2
