@@ -1,0 +1,311 @@
+// b200ba_shim.hpp -- C++ host side above the C ABI: OptimizeJointly() with the reference's own
+// parameter list (applications/camera_calibration/src/camera_calibration/bundle_adjustment/
+// joint_optimization.h:53-70) over containers shaped like the reference's Dataset / BAState /
+// CameraModel (dataset.h:57-212, ba_state.h:46-97, models/camera_model.h:42-204).
+//
+// The reference builds against Eigen / Sophus, which this repository must not depend on, so the
+// containers here are minimal look-alikes (same member names and meaning). In the reference tree
+// the same 60 lines of flattening are written against the real classes -- INTEGRATION.md shows it.
+//
+// Header-only; link with -lb200ba. No oracle, no CPU fallback: errors are returned, not hidden.
+#pragma once
+
+#include <cmath>
+#include <cstdint>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "b200ba.h"
+
+namespace b200ba_shim {
+
+struct Vec2f { float x, y; };
+struct Vec2d { double x, y; };
+struct Vec3d { double x, y, z; };
+
+// SE3d look-alike: unit quaternion (w, x, y, z) + translation. (Eigen::Quaterniond::coeffs() is
+// ordered x, y, z, w -- convert when adapting the real class.)
+struct SE3d {
+  double qw = 1, qx = 0, qy = 0, qz = 0;
+  double tx = 0, ty = 0, tz = 0;
+};
+
+// models/camera_model.h:42-204 (only what the BA path touches)
+class CameraModel {
+ public:
+  enum class Type { CentralGeneric = 0, NoncentralGeneric = 1, CentralRadial = 4, CentralThinPrismFisheye = 2,
+                    CentralOpenCV = 3, InvalidType = 5 };
+  CameraModel(int width, int height, int min_x, int min_y, int max_x, int max_y, Type type)
+      : m_width(width), m_height(height), m_calibration_min_x(min_x), m_calibration_min_y(min_y),
+        m_calibration_max_x(max_x), m_calibration_max_y(max_y), m_type(type) {}
+  virtual ~CameraModel() {}
+  virtual CameraModel* duplicate() = 0;
+  virtual int update_parameter_count() const = 0;
+  virtual bool GetGridResolution(int* rx, int* ry) const { (void)rx; (void)ry; return false; }
+  // flat intrinsics in the layout include/b200ba.h documents
+  virtual std::vector<double>& flat_intrinsics() = 0;
+  int width() const { return m_width; }
+  int height() const { return m_height; }
+  int calibration_min_x() const { return m_calibration_min_x; }
+  int calibration_min_y() const { return m_calibration_min_y; }
+  int calibration_max_x() const { return m_calibration_max_x; }
+  int calibration_max_y() const { return m_calibration_max_y; }
+  Type type() const { return m_type; }
+ protected:
+  int m_width, m_height, m_calibration_min_x, m_calibration_min_y, m_calibration_max_x, m_calibration_max_y;
+  Type m_type;
+};
+
+// models/central_generic.h: grid of unit directions, row-major, xyz
+class CentralGenericModel : public CameraModel {
+ public:
+  CentralGenericModel(int grid_resolution_x, int grid_resolution_y, int min_x, int min_y, int max_x, int max_y,
+                      int width, int height)
+      : CameraModel(width, height, min_x, min_y, max_x, max_y, Type::CentralGeneric), gw(grid_resolution_x),
+        gh(grid_resolution_y), grid(3 * static_cast<size_t>(gw) * gh, 0.0) {}
+  CameraModel* duplicate() override { return new CentralGenericModel(*this); }
+  int update_parameter_count() const override { return 2 * gw * gh; }
+  bool GetGridResolution(int* rx, int* ry) const override { *rx = gw; *ry = gh; return true; }
+  std::vector<double>& flat_intrinsics() override { return grid; }
+  static constexpr int IntrinsicsJacobianSize = 2 * 16;
+  int gw, gh;
+  std::vector<double> grid;
+};
+
+// models/noncentral_generic.h: direction grid followed by point grid
+class NoncentralGenericModel : public CameraModel {
+ public:
+  NoncentralGenericModel(int grid_resolution_x, int grid_resolution_y, int min_x, int min_y, int max_x, int max_y,
+                         int width, int height)
+      : CameraModel(width, height, min_x, min_y, max_x, max_y, Type::NoncentralGeneric), gw(grid_resolution_x),
+        gh(grid_resolution_y), grids(6 * static_cast<size_t>(gw) * gh, 0.0) {}
+  CameraModel* duplicate() override { return new NoncentralGenericModel(*this); }
+  int update_parameter_count() const override { return 5 * gw * gh; }
+  bool GetGridResolution(int* rx, int* ry) const override { *rx = gw; *ry = gh; return true; }
+  std::vector<double>& flat_intrinsics() override { return grids; }
+  static constexpr int IntrinsicsJacobianSize = 5 * 16;
+  int gw, gh;
+  std::vector<double> grids;
+};
+
+// models/central_opencv.h: fx fy cx cy k1..k6 p1 p2
+class CentralOpenCVModel : public CameraModel {
+ public:
+  CentralOpenCVModel(int width, int height)
+      : CameraModel(width, height, 0, 0, width - 1, height - 1, Type::CentralOpenCV), parameters(12, 0.0) {}
+  CameraModel* duplicate() override { return new CentralOpenCVModel(*this); }
+  int update_parameter_count() const override { return 12; }
+  std::vector<double>& flat_intrinsics() override { return parameters; }
+  static constexpr int IntrinsicsJacobianSize = 12;
+  std::vector<double> parameters;
+};
+
+// dataset.h:57-84
+struct PointFeature {
+  Vec2f xy{0, 0};
+  int id = -1;
+  int index = -1;
+  Vec2d last_projection{0, 0};
+};
+
+// dataset.h:88-123
+class Imageset {
+ public:
+  explicit Imageset(int num_cameras) : m_features(num_cameras) {}
+  std::vector<PointFeature>& FeaturesOfCamera(int c) { return m_features[c]; }
+  const std::vector<PointFeature>& FeaturesOfCamera(int c) const { return m_features[c]; }
+ private:
+  std::vector<std::vector<PointFeature>> m_features;
+};
+
+// dataset.h:131-212
+class Dataset {
+ public:
+  explicit Dataset(int num_cameras) : m_num_cameras(num_cameras) {}
+  std::shared_ptr<Imageset> NewImageset() {
+    m_imagesets.emplace_back(new Imageset(m_num_cameras));
+    return m_imagesets.back();
+  }
+  std::shared_ptr<Imageset> GetImageset(int i) { return m_imagesets[i]; }
+  int ImagesetCount() const { return static_cast<int>(m_imagesets.size()); }
+  int num_cameras() const { return m_num_cameras; }
+ private:
+  int m_num_cameras;
+  std::vector<std::shared_ptr<Imageset>> m_imagesets;
+};
+
+// ba_state.h:46-97
+struct BAState {
+  std::vector<bool> image_used;
+  std::unordered_map<int, int> feature_id_to_points_index;
+  std::vector<SE3d> camera_tr_rig;
+  std::vector<SE3d> rig_tr_global;
+  std::vector<std::shared_ptr<CameraModel>> intrinsics;
+  std::vector<Vec3d> points;
+  int num_cameras() const { return static_cast<int>(intrinsics.size()); }
+  // ba_state.cc:78-91
+  void ComputeFeatureIdToPointsIndex(Dataset* dataset) {
+    for (int i = 0; i < dataset->ImagesetCount(); ++i)
+      for (int c = 0; c < dataset->num_cameras(); ++c)
+        for (PointFeature& f : dataset->GetImageset(i)->FeaturesOfCamera(c)) f.index = feature_id_to_points_index.at(f.id);
+  }
+};
+
+// joint_optimization.h:38-47
+enum class SchurMode { Dense = 0, DenseCUDA, DenseOnTheFly, Sparse, SparseOnTheFly };
+
+// libvis lm_optimizer.h:55-77
+struct OptimizationReport {
+  double initial_cost = 0, final_cost = 0;
+  int num_iterations_performed = 0;
+  double cost_and_jacobian_evaluation_time = 0, solve_time = 0;
+};
+
+namespace detail {
+struct Flat {
+  std::vector<b200ba_camera> cams;
+  std::vector<uint32_t> oi, oc, op;
+  std::vector<float> oxy;
+  std::vector<double> points, rtg, ctr, lastp;
+  std::vector<double*> intr;
+  std::vector<int> used;
+};
+inline void flatten(Dataset& dataset, BAState* state, Flat* f) {
+  if (state->image_used.size() != state->rig_tr_global.size())
+    throw std::runtime_error("image_used / rig_tr_global size mismatch");  // CHECK_EQ, joint_optimization.cc:72
+  for (size_t i = 0; i < state->image_used.size(); ++i)
+    if (state->image_used[i]) f->used.push_back(static_cast<int>(i));
+  for (auto& m : state->intrinsics) {
+    b200ba_camera c{};
+    c.model_type = static_cast<int32_t>(m->type());
+    c.width = m->width();
+    c.height = m->height();
+    c.calibration_min_x = m->calibration_min_x();
+    c.calibration_min_y = m->calibration_min_y();
+    c.calibration_max_x = m->calibration_max_x();
+    c.calibration_max_y = m->calibration_max_y();
+    int rx = 0, ry = 0;
+    if (m->GetGridResolution(&rx, &ry)) { c.grid_width = rx; c.grid_height = ry; }
+    f->cams.push_back(c);
+    f->intr.push_back(m->flat_intrinsics().data());
+  }
+  // reference residual order: imageset, camera, feature (joint_optimization.cc:273-290)
+  for (size_t seq = 0; seq < f->used.size(); ++seq)
+    for (int c = 0; c < dataset.num_cameras(); ++c)
+      for (const PointFeature& ft : dataset.GetImageset(f->used[seq])->FeaturesOfCamera(c)) {
+        f->oi.push_back(static_cast<uint32_t>(seq));
+        f->oc.push_back(static_cast<uint32_t>(c));
+        f->op.push_back(static_cast<uint32_t>(ft.index));
+        f->oxy.push_back(ft.xy.x);
+        f->oxy.push_back(ft.xy.y);
+        f->lastp.push_back(ft.last_projection.x);
+        f->lastp.push_back(ft.last_projection.y);
+      }
+  for (const Vec3d& p : state->points) { f->points.push_back(p.x); f->points.push_back(p.y); f->points.push_back(p.z); }
+  auto push_pose = [](std::vector<double>& v, const SE3d& T) {
+    v.insert(v.end(), {T.qw, T.qx, T.qy, T.qz, T.tx, T.ty, T.tz});
+  };
+  for (int i : f->used) push_pose(f->rtg, state->rig_tr_global[i]);
+  for (const SE3d& T : state->camera_tr_rig) push_pose(f->ctr, T);
+}
+inline SE3d pose_at(const std::vector<double>& v, size_t i) {
+  SE3d T;
+  T.qw = v[7 * i]; T.qx = v[7 * i + 1]; T.qy = v[7 * i + 2]; T.qz = v[7 * i + 3];
+  T.tx = v[7 * i + 4]; T.ty = v[7 * i + 5]; T.tz = v[7 * i + 6];
+  return T;
+}
+inline void run(Dataset& dataset, BAState* state, const b200ba_options& opt, b200ba_report* rep) {
+  Flat f;
+  flatten(dataset, state, &f);
+  b200ba_problem pb{};
+  pb.n_cameras = static_cast<int32_t>(f.cams.size());
+  pb.cameras = f.cams.data();
+  pb.n_imagesets = static_cast<int32_t>(f.used.size());
+  pb.n_points = static_cast<int32_t>(state->points.size());
+  pb.n_obs = static_cast<int64_t>(f.oi.size());
+  pb.obs_imageset = f.oi.data();
+  pb.obs_camera = f.oc.data();
+  pb.obs_point = f.op.data();
+  pb.obs_xy = f.oxy.data();
+  b200ba_handle* h = nullptr;
+  if (b200ba_create(&pb, -1, &h) != 0) throw std::runtime_error(std::string("b200ba_create: ") + b200ba_last_error(nullptr));
+  b200ba_state st{f.points.data(), f.rtg.data(), f.ctr.data(), f.intr.data(), f.lastp.data()};
+  const int rc = b200ba_optimize_host(h, &st, &opt, rep);
+  const std::string err = rc ? b200ba_last_error(h) : "";
+  b200ba_destroy(h);
+  if (rc) throw std::runtime_error("b200ba_optimize_host: " + err);
+  // read back what the reference writes (joint_optimization.cc:942-950) + last_projection;
+  // the intrinsics were updated in place through flat_intrinsics()
+  for (size_t c = 0; c < state->camera_tr_rig.size(); ++c) state->camera_tr_rig[c] = pose_at(f.ctr, c);
+  for (size_t s = 0; s < f.used.size(); ++s) state->rig_tr_global[f.used[s]] = pose_at(f.rtg, s);
+  for (size_t p = 0; p < state->points.size(); ++p) state->points[p] = Vec3d{f.points[3 * p], f.points[3 * p + 1], f.points[3 * p + 2]};
+  size_t o = 0;
+  for (size_t seq = 0; seq < f.used.size(); ++seq)
+    for (int c = 0; c < dataset.num_cameras(); ++c)
+      for (PointFeature& ft : dataset.GetImageset(f.used[seq])->FeaturesOfCamera(c)) {
+        ft.last_projection = Vec2d{f.lastp[2 * o], f.lastp[2 * o + 1]};
+        ++o;
+      }
+}
+}  // namespace detail
+
+// joint_optimization.h:53-70 -- same parameters, same meaning. numerical_diff_delta is accepted
+// for signature parity (the device path differentiates analytically); debug_* are not supported.
+inline double OptimizeJointly(Dataset& dataset, BAState* state, int max_iteration_count, double init_lambda,
+                              double numerical_diff_delta, double regularization_weight, bool localize_only,
+                              bool eliminate_points, SchurMode schur_mode, double* final_lambda,
+                              bool* performed_an_iteration = nullptr, bool debug_verify_cost = false,
+                              bool debug_fix_points = false, bool debug_fix_poses = false,
+                              bool debug_fix_rig_poses = false, bool debug_fix_intrinsics = false,
+                              bool print_progress = true) {
+  (void)debug_verify_cost;
+  if (debug_fix_points || debug_fix_poses || debug_fix_rig_poses || debug_fix_intrinsics)
+    throw std::runtime_error("debug_fix_* is not supported on the device path");
+  if (performed_an_iteration) *performed_an_iteration = false;
+  b200ba_options opt;
+  b200ba_default_options(&opt);
+  opt.max_iteration_count = max_iteration_count;
+  opt.init_lambda = init_lambda;
+  opt.numerical_diff_delta = numerical_diff_delta;
+  opt.regularization_weight = regularization_weight;
+  opt.localize_only = localize_only ? 1 : 0;
+  opt.eliminate_points = eliminate_points ? 1 : 0;
+  opt.schur_mode = static_cast<int32_t>(schur_mode);
+  opt.print_progress = print_progress ? 1 : 0;
+  b200ba_report rep;
+  detail::run(dataset, state, opt, &rep);
+  if (final_lambda) *final_lambda = rep.final_lambda;
+  if (performed_an_iteration) *performed_an_iteration = rep.performed_an_iteration != 0;
+  return rep.final_cost;
+}
+
+// cuda_joint_optimization.h:45-59
+inline OptimizationReport CudaOptimizeJointly(Dataset& dataset, BAState* state, int max_iteration_count,
+                                              int /*max_inner_iterations*/, double init_lambda,
+                                              double numerical_diff_delta, double regularization_weight,
+                                              double* final_lambda, bool /*debug_verify_cost*/ = false,
+                                              bool = false, bool = false, bool = false, bool = false,
+                                              bool print_progress = true) {
+  b200ba_options opt;
+  b200ba_default_options(&opt);
+  opt.max_iteration_count = max_iteration_count;
+  opt.init_lambda = init_lambda;
+  opt.numerical_diff_delta = numerical_diff_delta;
+  opt.regularization_weight = regularization_weight;
+  opt.print_progress = print_progress ? 1 : 0;
+  b200ba_report rep;
+  detail::run(dataset, state, opt, &rep);
+  if (final_lambda) *final_lambda = rep.final_lambda;
+  OptimizationReport r;
+  r.initial_cost = rep.initial_cost;
+  r.final_cost = rep.final_cost;
+  r.num_iterations_performed = rep.num_iterations_performed;
+  r.cost_and_jacobian_evaluation_time = rep.cost_and_jacobian_evaluation_time;
+  r.solve_time = rep.solve_time;
+  return r;
+}
+
+}  // namespace b200ba_shim
