@@ -108,6 +108,8 @@ struct b200ba_handle {
   ObsOut out_trial{};  // residual-only evaluation of the trial state
   SystemDev sys{};
   double *d_W = nullptr, *d_S = nullptr, *d_Linv = nullptr, *d_v = nullptr, *d_y = nullptr, *d_x = nullptr;
+  double trace_H = 0;
+  int64_t reduce_count = 0;  // doubles of sys.base covered by the per-build all-reduce
   double* d_potrf_work = nullptr;
   int potrf_lwork = 0;
   int *d_info = nullptr, *d_fail = nullptr;
@@ -324,13 +326,17 @@ int make_layout(b200ba_handle* h, const b200ba_options* opt) {
 
   // the normal equations: one allocation (one all-reduce)
   SystemDev& s = h->sys;
+  // [D | b_p | B | b_d | scalars] are all-reduced after every build; C comes last and is NOT:
+  // with several ranks each rank folds its partial C into its partial Schur complement, and the
+  // all-reduce of S makes it global (see solve_system).
   const int64_t oD = 0;
   const int64_t obp = oD + align32(6LL * L.n_points);
   const int64_t oB = obp + align32(L.nbd);
-  const int64_t oC = oB + align32(static_cast<int64_t>(L.nbd) * L.nd);
-  const int64_t obd = oC + align32(static_cast<int64_t>(L.nd) * L.nd);
+  const int64_t obd = oB + align32(static_cast<int64_t>(L.nbd) * L.nd);
   const int64_t osc = obd + align32(L.nd);
-  s.total = osc + 32;
+  const int64_t oC = osc + 32;
+  s.total = oC + align32(static_cast<int64_t>(L.nd) * L.nd);
+  h->reduce_count = oC;
   if (dev_alloc(h, &s.base, s.total)) return 1;
   s.Dblk = s.base + oD;
   s.bp = s.base + obp;
@@ -339,7 +345,7 @@ int make_layout(b200ba_handle* h, const b200ba_options* opt) {
   s.bd = s.base + obd;
   s.scalars = s.base + osc;
   if (dev_alloc(h, &h->d_W, static_cast<size_t>(L.nbd) * L.nd)) return 1;
-  if (dev_alloc(h, &h->d_S, static_cast<size_t>(L.nd) * L.nd)) return 1;
+  if (dev_alloc(h, &h->d_S, static_cast<size_t>(L.nd) * L.nd + L.nd)) return 1;  // + partial rhs tail
   if (dev_alloc(h, &h->d_Linv, 6 * static_cast<size_t>(L.n_points))) return 1;
   if (dev_alloc(h, &h->d_v, L.nbd)) return 1;
   if (dev_alloc(h, &h->d_y, L.nbd)) return 1;
@@ -417,15 +423,18 @@ int build_system(b200ba_handle* h, double huber, double* cost, double* n_valid) 
     }
     h->timings.kernel_launches += 1;
     launch_cost_reduce(h->n_obs, h->out.cost, nullptr, h->out.residual, h->d_partial, h->sys.scalars, h->stream);
-    h->timings.kernel_launches += 2;
+    // trace(H) of this rank's partial system, for the lambda initialisation (lm_optimizer.h:766-781)
+    launch_trace(h->L.n_points, h->sys.Dblk, h->L.nd, h->sys.C, h->sys.scalars + 8, h->stream);
+    h->timings.kernel_launches += 3;
   }
   CUDA_TRY(h, cudaGetLastError());
-  // one all-reduce covers D, b_p, B, C, b_d and the cost scalars
-  if (all_reduce(h, h->sys.base, static_cast<size_t>(h->sys.total))) return 1;
-  CUDA_TRY(h, cudaMemcpyAsync(h->h_scal, h->sys.scalars, 6 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  // ONE all-reduce per build covers D, b_p, B, b_d, the cost scalars and the trace
+  if (all_reduce(h, h->sys.base, static_cast<size_t>(h->reduce_count))) return 1;
+  CUDA_TRY(h, cudaMemcpyAsync(h->h_scal, h->sys.scalars, 9 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
   if (sync_stream(h)) return 1;
   *cost = h->h_scal[3];
   *n_valid = h->h_scal[4];
+  h->trace_H = h->h_scal[8];
   return 0;
 }
 
@@ -434,6 +443,13 @@ int build_system(b200ba_handle* h, double huber, double* cost, double* n_valid) 
 int solve_system(b200ba_handle* h, double lambda, int* spd) {
   const Layout& L = h->L;
   const double one = 1.0, minus_one = -1.0;
+  // Point range of this rank for the contraction: S = sum_r (C_r - W_r^T W_r) + lambda I, where
+  // C_r is the rank's partial dense block and W_r the rows of W = L^-1 B of its points (B, D are
+  // global after the per-build all-reduce). With one rank this is the plain S = C + lambda I - W^T W.
+  const int p0 = static_cast<int>(static_cast<int64_t>(L.n_points) * h->rank / h->n_ranks);
+  const int p1 = static_cast<int>(static_cast<int64_t>(L.n_points) * (h->rank + 1) / h->n_ranks);
+  const int k_rows = 3 * (p1 - p0);
+  double* rhs_tail = h->d_S + static_cast<size_t>(L.nd) * L.nd;
   {
     ScopedPhase ph(h, PH_SCHUR);
     CUDA_TRY(h, cudaMemsetAsync(h->d_fail, 0, sizeof(int), h->stream));
@@ -441,17 +457,29 @@ int solve_system(b200ba_handle* h, double lambda, int* spd) {
     launch_schur_scale_rows(L.n_points, L.nd, h->sys.B, h->d_Linv, h->d_W, h->stream);
     CUDA_TRY(h, cudaMemcpyAsync(h->d_S, h->sys.C, static_cast<size_t>(L.nd) * L.nd * sizeof(double),
                                 cudaMemcpyDeviceToDevice, h->stream));
-    launch_add_diagonal(L.nd, h->d_S, L.nd, lambda, h->stream);
-    h->timings.kernel_launches += 3;
-    if (L.nbd > 0 && L.nd > 0) {
-      // S = (C + lambda I) - W^T W; row-major W [nbd x nd] is the column-major nd x nbd matrix W^T
-      CUBLAS_TRY(h, cublasDsyrk(h->cublas, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_N, L.nd, L.nbd, &minus_one, h->d_W, L.nd,
+    CUDA_TRY(h, cudaMemsetAsync(rhs_tail, 0, L.nd * sizeof(double), h->stream));
+    h->timings.kernel_launches += 2;
+    if (k_rows > 0 && L.nd > 0) {
+      const double zero = 0.0;
+      const double* Wr = h->d_W + static_cast<size_t>(3 * p0) * L.nd;
+      // row-major W [nbd x nd] is the column-major nd x nbd matrix W^T: S -= W_r^T W_r (lower)
+      CUBLAS_TRY(h, cublasDsyrk(h->cublas, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_N, L.nd, k_rows, &minus_one, Wr, L.nd,
                                 &one, h->d_S, L.nd));
-      // reduced right-hand side b_d - W^T v, written into x_dense
-      CUDA_TRY(h, cudaMemcpyAsync(h->d_x + L.nbd, h->sys.bd, L.nd * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
-      CUBLAS_TRY(h, cublasDgemv(h->cublas, CUBLAS_OP_N, L.nd, L.nbd, &minus_one, h->d_W, L.nd, h->d_v, 1, &one,
-                                h->d_x + L.nbd, 1));
+      // partial reduced right-hand side: -W_r^T v_r
+      CUBLAS_TRY(h, cublasDgemv(h->cublas, CUBLAS_OP_N, L.nd, k_rows, &minus_one, Wr, L.nd, h->d_v + 3 * p0, 1, &zero,
+                                rhs_tail, 1));
     }
+  }
+  if (h->n_ranks > 1) {
+    if (all_reduce(h, h->d_S, static_cast<size_t>(L.nd) * L.nd + L.nd)) return 1;
+  }
+  {
+    ScopedPhase ph(h, PH_SCHUR);
+    launch_add_diagonal(L.nd, h->d_S, L.nd, lambda, h->stream);
+    // x_dense <- b_d - W^T v
+    CUDA_TRY(h, cudaMemcpyAsync(h->d_x + L.nbd, h->sys.bd, L.nd * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+    CUBLAS_TRY(h, cublasDaxpy(h->cublas, L.nd, &one, rhs_tail, 1, h->d_x + L.nbd, 1));
+    h->timings.kernel_launches += 1;
   }
   {
     ScopedPhase ph(h, PH_FACTOR);
@@ -771,11 +799,7 @@ int b200ba_optimize(b200ba_handle* h, const b200ba_options* opt, b200ba_report* 
       lambda = init_lambda;
     } else {
       // lambda = init_lambda_factor * trace(H) / dof (lm_optimizer.h:766-781)
-      launch_trace(L.n_points, h->sys.Dblk, L.nd, h->sys.C, h->d_scal, h->stream);
-      h->timings.kernel_launches += 1;
-      CUDA_TRY(h, cudaMemcpyAsync(h->h_scal + 8, h->d_scal, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-      if (sync_stream(h)) return 1;
-      lambda = opt->init_lambda_factor * h->h_scal[8] / L.dof;
+      lambda = opt->init_lambda_factor * h->trace_H / L.dof;
     }
     bool applied_update = false;
     int attempts = 0;

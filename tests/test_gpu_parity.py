@@ -277,3 +277,19 @@ def test_full_size_properties():
         c = rep.trace()[0]
         assert c[0] < rep.initial_cost and c[1] < c[0]
         assert rep.n_valid + rep.n_invalid == sp.n_obs
+
+
+def test_multi_gpu_matches_single_gpu():
+    """world_size 2 over NCCL: sharded accumulation + all-reduce + point-range split of the Schur
+    contraction reproduce the single-GPU LM loop. Skipped on a single-GPU box."""
+    import os
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+           "127.0.0.1", "--master-port", "29533", os.path.join(root, "tests", "mgpu_check.py")]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0 and "MGPU_OK" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
