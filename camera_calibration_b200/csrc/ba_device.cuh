@@ -63,14 +63,21 @@ __device__ __forceinline__ bool in_area(const CamDev& c, double x, double y) {
   return x >= c.min_x && y >= c.min_y && x < c.max_x + 1 && y < c.max_y + 1;
 }
 
-// value, d/dgx, d/dgy of a 3-vector spline surface; control points streamed row by row
+// select element r of a 4-vector held in registers (no local-memory indexing)
+__device__ __forceinline__ double sel4(const double w[4], int r) {
+  return r == 0 ? w[0] : (r == 1 ? w[1] : (r == 2 ? w[2] : w[3]));
+}
+
+// value, d/dgx, d/dgy of a 3-vector spline surface. The 16 control points are streamed row by
+// row; the row loop is deliberately NOT unrolled: 12 loads in flight per thread are enough at 16
+// resident warps per SM, and hoisting all 48 loads costs ~100 registers (measured: 254 -> 128).
 __device__ __forceinline__ void spline3(const double* __restrict__ g, int gw, int x0, int y0, const double wx[4],
                                         const double dwx[4], const double wy[4], const double dwy[4], d3& v,
                                         d3& vx, d3& vy) {
   v = vx = vy = mk3(0, 0, 0);
-#pragma unroll
+  const double* row = g + 3 * (static_cast<int64_t>(y0) * gw + x0);
+#pragma unroll 1
   for (int r = 0; r < 4; ++r) {
-    const double* row = g + 3 * (static_cast<int64_t>(y0 + r) * gw + x0);
     d3 a = mk3(0, 0, 0), ax = mk3(0, 0, 0);
 #pragma unroll
     for (int cidx = 0; cidx < 4; ++cidx) {
@@ -78,9 +85,11 @@ __device__ __forceinline__ void spline3(const double* __restrict__ g, int gw, in
       a = fma3(wx[cidx], p, a);
       ax = fma3(dwx[cidx], p, ax);
     }
-    v = fma3(wy[r], a, v);
-    vx = fma3(wy[r], ax, vx);
-    vy = fma3(dwy[r], a, vy);
+    const double wyr = sel4(wy, r), dwyr = sel4(dwy, r);
+    v = fma3(wyr, a, v);
+    vx = fma3(wyr, ax, vx);
+    vy = fma3(dwyr, a, vy);
+    row += 3 * static_cast<int64_t>(gw);
   }
 }
 
@@ -111,42 +120,54 @@ __device__ __forceinline__ void central_eval(const CamDev& c, const double* __re
 // squared residual, <= 100 outer iterations, lambda0 = 0.01 * 0.5 * tr(H) once, <= 10
 // attempts (x2 / x0.5), trial clamped to [min, max + 0.999], success as soon as the cost
 // measured before a step is < eps. On return e is the evaluation at the final pixel.
+//
+// Written as ONE loop over spline evaluations (a single inlined call site): the reference
+// evaluates "value + Jacobian at the current pixel" and "value at the trial pixel" separately;
+// here every evaluation yields both, so the evaluation of an accepted trial IS the next
+// iteration's current evaluation. Control flow and results are those of the reference.
 __device__ __forceinline__ bool central_project(const CamDev& c, const double* __restrict__ grid, d3 dir,
                                                 double& px, double& py, CentralEval& e) {
   constexpr double kEpsilon = 1e-12;
-  central_eval(c, grid, px, py, e);
-  double lambda = -1.0;
-  for (int it = 0; it < 100; ++it) {
-    const d3 r = e.u - dir;
-    const double cost = dot3(r, r);
-    const double H00 = dot3(e.ux, e.ux), H01 = dot3(e.ux, e.uy), H11 = dot3(e.uy, e.uy);
-    const double b0 = dot3(r, e.ux), b1 = dot3(r, e.uy);
-    if (lambda < 0) lambda = 0.01 * 0.5 * (H00 + H11);
-    bool accepted = false;
-    for (int k = 0; k < 10; ++k) {
-      const double H00l = H00 + lambda, H11l = H11 + lambda;
-      const double x1 = (b1 - H01 / H00l * b0) / (H11l - H01 * H01 / H00l);
-      const double x0 = (b0 - H01 * x1) / H00l;
-      const double tx = fmax(static_cast<double>(c.min_x), fmin(c.max_x + 0.999, px - x0));
-      const double ty = fmax(static_cast<double>(c.min_y), fmin(c.max_y + 0.999, py - x1));
-      CentralEval t;
-      central_eval(c, grid, tx, ty, t);
-      const d3 tr = t.u - dir;
-      const double tcost = dot3(tr, tr);
-      if (tcost < cost) {
+  double tx = px, ty = py;
+  double lambda = -1.0, cost = 0, H00 = 0, H01 = 0, H11 = 0, b0 = 0, b1 = 0;
+  bool have_cur = false;
+  int outer = 0, attempt = 0;
+  const double lo_x = c.min_x, lo_y = c.min_y, hi_x = c.max_x + 0.999, hi_y = c.max_y + 0.999;
+  while (true) {
+    CentralEval t;
+    central_eval(c, grid, tx, ty, t);
+    const d3 r = t.u - dir;
+    const double tcost = dot3(r, r);
+    if (!have_cur || tcost < cost) {
+      // first evaluation, or an accepted trial step
+      px = tx;
+      py = ty;
+      e = t;
+      if (have_cur) {
         lambda *= 0.5;
-        px = tx;
-        py = ty;
-        e = t;
-        accepted = true;
-        break;
+        if (cost < kEpsilon) return true;  // cost measured BEFORE the step
+        if (outer >= 100) return false;
       }
+      have_cur = true;
+      ++outer;
+      attempt = 0;
+      cost = tcost;
+      H00 = dot3(t.ux, t.ux);
+      H01 = dot3(t.ux, t.uy);
+      H11 = dot3(t.uy, t.uy);
+      b0 = dot3(r, t.ux);
+      b1 = dot3(r, t.uy);
+      if (lambda < 0) lambda = 0.01 * 0.5 * (H00 + H11);
+    } else {
       lambda *= 2.0;
+      if (++attempt >= 10) return cost < kEpsilon;
     }
-    if (!accepted) return cost < kEpsilon;
-    if (cost < kEpsilon) return true;
+    const double H00l = H00 + lambda, H11l = H11 + lambda;
+    const double x1 = (b1 - H01 / H00l * b0) / (H11l - H01 * H01 / H00l);
+    const double x0 = (b0 - H01 * x1) / H00l;
+    tx = fmax(lo_x, fmin(hi_x, px - x0));
+    ty = fmax(lo_y, fmin(hi_y, py - x1));
   }
-  return false;
 }
 
 // ---- tangent frames (local_parametrizations/line_parametrization.h:54-60) -----------------
@@ -231,59 +252,58 @@ __device__ __forceinline__ void noncentral_residual_jac(const NoncentralEval& e,
   R[1][0] = dot3(rd2, e.ux) + dot3(t2, e.ox);
   R[1][1] = dot3(rd2, e.uy) + dot3(t2, e.oy);
 }
-// NoncentralGenericModel::ProjectWithInitialEstimate (noncentral_generic.cc:156-264)
+// NoncentralGenericModel::ProjectWithInitialEstimate (noncentral_generic.cc:156-264); same
+// single-evaluation-site formulation as central_project. On success R is the 2x2 residual
+// Jacobian and (t1, t2) the tangent frame at the final pixel (inputs of the implicit-function step).
 __device__ __forceinline__ bool noncentral_project(const CamDev& c, const double* __restrict__ dgrid,
                                                    const double* __restrict__ pgrid, d3 p, double& px,
                                                    double& py, NoncentralEval& e, d3& t1, d3& t2,
                                                    double R[2][2]) {
   constexpr double kEpsilon = 1e-12;
-  noncentral_eval(c, dgrid, pgrid, px, py, e);
-  double r0, r1;
-  noncentral_residual(e, p, r0, r1, t1, t2);
-  double lambda = -1.0;
-  for (int it = 0; it < 100; ++it) {
-    noncentral_residual_jac(e, p, t1, t2, R);
-    const double cost = r0 * r0 + r1 * r1;
-    const double H00 = R[0][0] * R[0][0] + R[1][0] * R[1][0];
-    const double H01 = R[0][0] * R[0][1] + R[1][0] * R[1][1];
-    const double H11 = R[0][1] * R[0][1] + R[1][1] * R[1][1];
-    const double b0 = r0 * R[0][0] + r1 * R[1][0];
-    const double b1 = r0 * R[0][1] + r1 * R[1][1];
-    if (lambda < 0) lambda = 0.01 * 0.5 * (H00 + H11);
-    bool accepted = false;
-    for (int k = 0; k < 10; ++k) {
-      const double H00l = H00 + lambda, H11l = H11 + lambda;
-      const double x1 = (b1 - H01 / H00l * b0) / (H11l - H01 * H01 / H00l);
-      const double x0 = (b0 - H01 * x1) / H00l;
-      const double tx = fmax(static_cast<double>(c.min_x), fmin(c.max_x + 0.999, px - x0));
-      const double ty = fmax(static_cast<double>(c.min_y), fmin(c.max_y + 0.999, py - x1));
-      NoncentralEval t;
-      noncentral_eval(c, dgrid, pgrid, tx, ty, t);
-      double tr0, tr1;
-      d3 tt1, tt2;
-      noncentral_residual(t, p, tr0, tr1, tt1, tt2);
-      const double tcost = tr0 * tr0 + tr1 * tr1;
-      if (tcost < cost) {
+  double tx = px, ty = py;
+  double lambda = -1.0, cost = 0, H00 = 0, H01 = 0, H11 = 0, b0 = 0, b1 = 0;
+  bool have_cur = false;
+  int outer = 0, attempt = 0;
+  const double lo_x = c.min_x, lo_y = c.min_y, hi_x = c.max_x + 0.999, hi_y = c.max_y + 0.999;
+  while (true) {
+    NoncentralEval t;
+    noncentral_eval(c, dgrid, pgrid, tx, ty, t);
+    double r0, r1;
+    d3 tt1, tt2;
+    noncentral_residual(t, p, r0, r1, tt1, tt2);
+    const double tcost = r0 * r0 + r1 * r1;
+    if (!have_cur || tcost < cost) {
+      px = tx;
+      py = ty;
+      e = t;
+      t1 = tt1;
+      t2 = tt2;
+      noncentral_residual_jac(t, p, tt1, tt2, R);
+      if (have_cur) {
         lambda *= 0.5;
-        px = tx;
-        py = ty;
-        e = t;
-        r0 = tr0;
-        r1 = tr1;
-        t1 = tt1;
-        t2 = tt2;
-        accepted = true;
-        break;
+        if (cost < kEpsilon) return true;
+        if (outer >= 100) return false;
       }
+      have_cur = true;
+      ++outer;
+      attempt = 0;
+      cost = tcost;
+      H00 = R[0][0] * R[0][0] + R[1][0] * R[1][0];
+      H01 = R[0][0] * R[0][1] + R[1][0] * R[1][1];
+      H11 = R[0][1] * R[0][1] + R[1][1] * R[1][1];
+      b0 = r0 * R[0][0] + r1 * R[1][0];
+      b1 = r0 * R[0][1] + r1 * R[1][1];
+      if (lambda < 0) lambda = 0.01 * 0.5 * (H00 + H11);
+    } else {
       lambda *= 2.0;
+      if (++attempt >= 10) return cost < kEpsilon;
     }
-    if (!accepted) return cost < kEpsilon;
-    if (cost < kEpsilon) {
-      noncentral_residual_jac(e, p, t1, t2, R);  // Jacobian at the final pixel for the IFT step
-      return true;
-    }
+    const double H00l = H00 + lambda, H11l = H11 + lambda;
+    const double x1 = (b1 - H01 / H00l * b0) / (H11l - H01 * H01 / H00l);
+    const double x0 = (b0 - H01 * x1) / H00l;
+    tx = fmax(lo_x, fmin(hi_x, px - x0));
+    ty = fmax(lo_y, fmin(hi_y, py - x1));
   }
-  return false;
 }
 
 // ---- central OpenCV ----------------------------------------------------------------------------

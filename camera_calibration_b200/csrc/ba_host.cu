@@ -113,11 +113,9 @@ struct b200ba_handle {
   double* d_potrf_work = nullptr;
   int potrf_lwork = 0;
   int *d_info = nullptr, *d_fail = nullptr;
-  uint32_t *d_keys = nullptr, *d_keys_sorted = nullptr, *d_vals = nullptr, *d_vals_sorted = nullptr;
-  void* d_sort_temp = nullptr;
-  size_t sort_temp_bytes_ = 0;
-  int sort_end_bit = 32;
-  uint32_t invalid_key = 0xffffffffu;
+  // Static cell-major processing order: device position -> index in the caller's (reference)
+  // observation order. Computed once at create time from the cell of the measured pixel.
+  std::vector<uint32_t> perm;
   double *d_partial = nullptr, *d_scal = nullptr;
   double* h_scal = nullptr;  // pinned [16]
   int* h_flags = nullptr;    // pinned [2]
@@ -355,22 +353,6 @@ int make_layout(b200ba_handle* h, const b200ba_options* opt) {
   h->potrf_lwork = lwork;
   if (dev_alloc(h, &h->d_potrf_work, std::max(1, lwork))) return 1;
 
-  // cell sort
-  if (dev_alloc(h, &h->d_keys, n)) return 1;
-  if (dev_alloc(h, &h->d_keys_sorted, n)) return 1;
-  if (dev_alloc(h, &h->d_vals, n)) return 1;
-  if (dev_alloc(h, &h->d_vals_sorted, n)) return 1;
-  uint64_t total_cells = 0;
-  for (int c = 0; c < h->n_cameras; ++c)
-    total_cells += static_cast<uint64_t>(std::max(1, h->cams_host[c].grid_width * h->cams_host[c].grid_height));
-  int bits = 1;
-  while ((1ull << bits) <= total_cells) ++bits;  // keys 0..total_cells-1 plus the sentinel
-  h->sort_end_bit = bits;
-  h->invalid_key = static_cast<uint32_t>((1ull << bits) - 1);
-  h->sort_temp_bytes_ = sort_temp_bytes(n, bits);
-  if (h->d_sort_temp) cudaFree(h->d_sort_temp);
-  h->d_sort_temp = nullptr;
-  CUDA_TRY(h, cudaMalloc(&h->d_sort_temp, std::max<size_t>(h->sort_temp_bytes_, 16)));
   return 0;
 }
 
@@ -413,13 +395,8 @@ int build_system(b200ba_handle* h, double huber, double* cost, double* n_valid) 
     CUDA_TRY(h, cudaMemsetAsync(h->sys.base, 0, h->sys.total * sizeof(double), h->stream));
     launch_accumulate_scatter(h->pb, h->L, h->out, h->sys, huber, h->stream);
     if (!h->L.localize_only || h->L.rig_in_state) {
-      launch_cell_keys(h->pb, h->out, h->d_keys, h->d_vals, h->invalid_key, h->stream);
-      if (h->n_obs > 0)
-        sort_pairs(h->d_sort_temp, h->sort_temp_bytes_, h->d_keys, h->d_keys_sorted, h->d_vals, h->d_vals_sorted,
-                   h->n_obs, h->sort_end_bit, h->stream);
-      launch_accumulate_cells(h->pb, h->L, h->out, h->sys, h->d_keys_sorted, h->d_vals_sorted, h->invalid_key, huber,
-                              h->stream);
-      h->timings.kernel_launches += 5;
+      launch_accumulate_cells(h->pb, h->L, h->out, h->sys, huber, h->stream);
+      h->timings.kernel_launches += 1;
     }
     h->timings.kernel_launches += 1;
     launch_cost_reduce(h->n_obs, h->out.cost, nullptr, h->out.residual, h->d_partial, h->sys.scalars, h->stream);
@@ -533,9 +510,7 @@ void free_handle_buffers(b200ba_handle* h) {
   F(h->out.residual); F(h->out.cost); F(h->out.jac); F(h->out.cell); F(h->out.has_jac);
   F(h->out_trial.residual); F(h->out_trial.cost);
   F(h->sys.base); F(h->d_W); F(h->d_S); F(h->d_Linv); F(h->d_v); F(h->d_y); F(h->d_x); F(h->d_potrf_work);
-  F(h->d_info); F(h->d_fail); F(h->d_keys); F(h->d_keys_sorted); F(h->d_vals); F(h->d_vals_sorted);
-  if (h->d_sort_temp) cudaFree(h->d_sort_temp);
-  h->d_sort_temp = nullptr;
+  F(h->d_info); F(h->d_fail);
   F(h->d_partial); F(h->d_scal);
   if (h->h_scal) cudaFreeHost(h->h_scal);
   if (h->h_flags) cudaFreeHost(h->h_flags);
@@ -673,10 +648,41 @@ int b200ba_create(const b200ba_problem* p, int device, b200ba_handle** out) {
   TRYC(dev_alloc(h, &h->d_obs_point, n));
   TRYC(dev_alloc(h, &h->d_obs_xy, n));
   if (n > 0) {
-    TRYC(cuda_ok(cudaMemcpy(h->d_obs_imageset, p->obs_imageset, n * sizeof(uint32_t), cudaMemcpyHostToDevice), "H2D"));
-    TRYC(cuda_ok(cudaMemcpy(h->d_obs_camera, p->obs_camera, n * sizeof(uint32_t), cudaMemcpyHostToDevice), "H2D"));
-    TRYC(cuda_ok(cudaMemcpy(h->d_obs_point, p->obs_point, n * sizeof(uint32_t), cudaMemcpyHostToDevice), "H2D"));
-    TRYC(cuda_ok(cudaMemcpy(h->d_obs_xy, p->obs_xy, n * sizeof(float2), cudaMemcpyHostToDevice), "H2D"));
+    // Static cell-major order: sort the observations ONCE by (camera, B-spline cell of the
+    // measured pixel). Lanes of a warp then gather the same 4x4 control points (broadcast loads
+    // instead of 32 scattered L1 wavefronts) and accumulate_cells_kernel sees long runs. The
+    // C ABI keeps the reference's residual order: inputs are permuted here, per-observation
+    // outputs are un-permuted on the way out.
+    std::vector<uint32_t> key(n);
+    for (int64_t o = 0; o < n; ++o) {
+      const uint32_t cam = p->obs_camera[o];
+      const CamDev& cd = h->pb.cams[cam];
+      uint32_t cell = 0;
+      if (cd.gw > 0) {
+        const double gx = 1.0 + cd.gmul_x * (static_cast<double>(p->obs_xy[2 * o]) - cd.min_x);
+        const double gy = 1.0 + cd.gmul_y * (static_cast<double>(p->obs_xy[2 * o + 1]) - cd.min_y);
+        const int x0 = std::min(std::max(static_cast<int>(std::floor(gx)) - 1, 0), cd.gw - 4);
+        const int y0 = std::min(std::max(static_cast<int>(std::floor(gy)) - 1, 0), cd.gh - 4);
+        cell = static_cast<uint32_t>(x0 + y0 * cd.gw);
+      }
+      key[o] = (cam << 24) | cell;
+    }
+    h->perm.resize(n);
+    for (int64_t o = 0; o < n; ++o) h->perm[o] = static_cast<uint32_t>(o);
+    std::stable_sort(h->perm.begin(), h->perm.end(), [&](uint32_t a, uint32_t b) { return key[a] < key[b]; });
+    std::vector<uint32_t> t32(n);
+    std::vector<float> txy(2 * n);
+    for (int64_t i = 0; i < n; ++i) t32[i] = p->obs_imageset[h->perm[i]];
+    TRYC(cuda_ok(cudaMemcpy(h->d_obs_imageset, t32.data(), n * sizeof(uint32_t), cudaMemcpyHostToDevice), "H2D"));
+    for (int64_t i = 0; i < n; ++i) t32[i] = p->obs_camera[h->perm[i]];
+    TRYC(cuda_ok(cudaMemcpy(h->d_obs_camera, t32.data(), n * sizeof(uint32_t), cudaMemcpyHostToDevice), "H2D"));
+    for (int64_t i = 0; i < n; ++i) t32[i] = p->obs_point[h->perm[i]];
+    TRYC(cuda_ok(cudaMemcpy(h->d_obs_point, t32.data(), n * sizeof(uint32_t), cudaMemcpyHostToDevice), "H2D"));
+    for (int64_t i = 0; i < n; ++i) {
+      txy[2 * i] = p->obs_xy[2 * h->perm[i]];
+      txy[2 * i + 1] = p->obs_xy[2 * h->perm[i] + 1];
+    }
+    TRYC(cuda_ok(cudaMemcpy(h->d_obs_xy, txy.data(), n * sizeof(float2), cudaMemcpyHostToDevice), "H2D"));
   }
   h->pb.n_obs = n;
   h->pb.obs_imageset = h->d_obs_imageset;
@@ -732,9 +738,15 @@ int b200ba_set_state(b200ba_handle* h, const b200ba_state* s) {
   for (int c = 0; c < h->n_cameras; ++c)
     CUDA_TRY(h, cudaMemcpyAsync(d.intrinsics + h->pb.cams[c].intr_off, s->intrinsics[c],
                                 sizeof(double) * intrinsics_size(h->cams_host[c]), cudaMemcpyHostToDevice, h->stream));
-  if (s->last_projection)
-    CUDA_TRY(h, cudaMemcpyAsync(h->d_last_projection, s->last_projection, 2 * sizeof(double) * h->n_obs, cudaMemcpyHostToDevice, h->stream));
-  else
+  std::vector<double> lp_perm;
+  if (s->last_projection) {
+    lp_perm.resize(2 * h->n_obs);
+    for (int64_t i = 0; i < h->n_obs; ++i) {
+      lp_perm[2 * i] = s->last_projection[2 * static_cast<int64_t>(h->perm[i])];
+      lp_perm[2 * i + 1] = s->last_projection[2 * static_cast<int64_t>(h->perm[i]) + 1];
+    }
+    CUDA_TRY(h, cudaMemcpyAsync(h->d_last_projection, lp_perm.data(), 2 * sizeof(double) * h->n_obs, cudaMemcpyHostToDevice, h->stream));
+  } else
     CUDA_TRY(h, cudaMemsetAsync(h->d_last_projection, 0, std::max<int64_t>(1, h->n_obs) * sizeof(double2), h->stream));
   CUDA_TRY(h, cudaStreamSynchronize(h->stream));
   h->have_state = true;
@@ -756,9 +768,17 @@ int b200ba_get_state(b200ba_handle* h, b200ba_state* s) {
     for (int c = 0; c < h->n_cameras; ++c)
       CUDA_TRY(h, cudaMemcpyAsync(s->intrinsics[c], d.intrinsics + h->pb.cams[c].intr_off,
                                   sizeof(double) * intrinsics_size(h->cams_host[c]), cudaMemcpyDeviceToHost, h->stream));
-  if (s->last_projection)
-    CUDA_TRY(h, cudaMemcpyAsync(s->last_projection, h->d_last_projection, 2 * sizeof(double) * h->n_obs, cudaMemcpyDeviceToHost, h->stream));
+  std::vector<double> lp_perm;
+  if (s->last_projection) {
+    lp_perm.resize(2 * h->n_obs);
+    CUDA_TRY(h, cudaMemcpyAsync(lp_perm.data(), h->d_last_projection, 2 * sizeof(double) * h->n_obs, cudaMemcpyDeviceToHost, h->stream));
+  }
   CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  if (s->last_projection)
+    for (int64_t i = 0; i < h->n_obs; ++i) {
+      s->last_projection[2 * static_cast<int64_t>(h->perm[i])] = lp_perm[2 * i];
+      s->last_projection[2 * static_cast<int64_t>(h->perm[i]) + 1] = lp_perm[2 * i + 1];
+    }
   return 0;
 }
 
@@ -900,12 +920,16 @@ int b200ba_evaluate(b200ba_handle* h, const b200ba_options* opt, int compute_jac
   if (residuals) {
     std::vector<double> tmp(2 * n);
     CUDA_TRY(h, cudaMemcpy(tmp.data(), h->out.residual, 2 * n * sizeof(double), cudaMemcpyDeviceToHost));
-    for (int64_t o = 0; o < n; ++o) {
-      residuals[2 * o] = tmp[o];
-      residuals[2 * o + 1] = tmp[n + o];
+    for (int64_t i = 0; i < n; ++i) {
+      residuals[2 * static_cast<int64_t>(h->perm[i])] = tmp[i];
+      residuals[2 * static_cast<int64_t>(h->perm[i]) + 1] = tmp[n + i];
     }
   }
-  if (costs) CUDA_TRY(h, cudaMemcpy(costs, h->out.cost, n * sizeof(double), cudaMemcpyDeviceToHost));
+  if (costs) {
+    std::vector<double> tmp(n);
+    CUDA_TRY(h, cudaMemcpy(tmp.data(), h->out.cost, n * sizeof(double), cudaMemcpyDeviceToHost));
+    for (int64_t i = 0; i < n; ++i) costs[h->perm[i]] = tmp[i];
+  }
   if (total_cost) *total_cost = h->h_scal[3];
   return 0;
 }
@@ -924,20 +948,21 @@ int b200ba_get_jacobians(b200ba_handle* h, double* j_point, double* j_pose, doub
   CUDA_TRY(h, cudaMemcpy(has.data(), h->out.has_jac, n, cudaMemcpyDeviceToHost));
   std::vector<uint32_t> cams(n);
   CUDA_TRY(h, cudaMemcpy(cams.data(), h->d_obs_camera, n * sizeof(uint32_t), cudaMemcpyDeviceToHost));
-  auto J = [&](int col, int r, int64_t o) { return jac[(2 * static_cast<size_t>(col) + r) * n + o]; };
-  for (int64_t o = 0; o < n; ++o) {
-    const bool v = has[o] != 0;
+  auto J = [&](int col, int r, int64_t i) { return jac[(2 * static_cast<size_t>(col) + r) * n + i]; };
+  for (int64_t i = 0; i < n; ++i) {
+    const int64_t o = h->perm[i];  // position i on the device holds the caller's observation o
+    const bool v = has[i] != 0;
     for (int r = 0; r < 2; ++r) {
-      if (j_point) for (int j = 0; j < 3; ++j) j_point[(o * 2 + r) * 3 + j] = v ? J(L.jc_point + j, r, o) : 0.0;
-      if (j_pose) for (int j = 0; j < 6; ++j) j_pose[(o * 2 + r) * 6 + j] = v ? J(L.jc_pose + j, r, o) : 0.0;
-      if (j_rig) for (int j = 0; j < 6; ++j) j_rig[(o * 2 + r) * 6 + j] = (v && L.rig_in_state) ? J(L.jc_rig + j, r, o) : 0.0;
+      if (j_point) for (int j = 0; j < 3; ++j) j_point[(o * 2 + r) * 3 + j] = v ? J(L.jc_point + j, r, i) : 0.0;
+      if (j_pose) for (int j = 0; j < 6; ++j) j_pose[(o * 2 + r) * 6 + j] = v ? J(L.jc_pose + j, r, i) : 0.0;
+      if (j_rig) for (int j = 0; j < 6; ++j) j_rig[(o * 2 + r) * 6 + j] = (v && L.rig_in_state) ? J(L.jc_rig + j, r, i) : 0.0;
     }
-    const CamDev& c = h->pb.cams[cams[o]];
+    const CamDev& c = h->pb.cams[cams[i]];
     for (int k = 0; k < K; ++k) {
       const bool vk = v && !L.localize_only && k < c.K;
       if (j_intr) {
-        j_intr[(o * 2 + 0) * K + k] = vk ? J(L.jc_intr + k, 0, o) : 0.0;
-        j_intr[(o * 2 + 1) * K + k] = vk ? J(L.jc_intr + k, 1, o) : 0.0;
+        j_intr[(o * 2 + 0) * K + k] = vk ? J(L.jc_intr + k, 0, i) : 0.0;
+        j_intr[(o * 2 + 1) * K + k] = vk ? J(L.jc_intr + k, 1, i) : 0.0;
       }
       if (intr_index) {
         int idx = -1;
@@ -945,10 +970,10 @@ int b200ba_get_jacobians(b200ba_handle* h, double* j_point, double* j_pose, doub
           int local;
           if (c.model_type == B200BA_MODEL_CENTRAL_GENERIC) {
             const int cp = k >> 1;
-            local = 2 * (cell[o] + (cp & 3) + (cp >> 2) * c.gw) + (k & 1);
+            local = 2 * (cell[i] + (cp & 3) + (cp >> 2) * c.gw) + (k & 1);
           } else if (c.model_type == B200BA_MODEL_NONCENTRAL_GENERIC) {
             const int cp = k / 5;
-            local = 5 * (cell[o] + (cp & 3) + (cp >> 2) * c.gw) + (k - 5 * cp);
+            local = 5 * (cell[i] + (cp & 3) + (cp >> 2) * c.gw) + (k - 5 * cp);
           } else {
             local = k;
           }

@@ -13,7 +13,7 @@
 // /root/reference/applications/camera_calibration/src/camera_calibration (APP) and
 // /root/reference/libvis/src/libvis (LV).
 
-#include <cub/cub.cuh>
+#include <cstdlib>
 
 #include "ba_device.cuh"
 #include "ba_kernels.h"
@@ -105,8 +105,8 @@ __device__ __forceinline__ void store_col(const ObsOut& out, int64_t n_obs, int6
 // Jacobians obtained analytically through the implicit function theorem at the converged
 // projection (the reference differentiates numerically: joint_optimization.cc:357-376,
 // models/central_grid.h:187-245, models/noncentral_generic.h:224-283).
-template <int MODEL, bool JAC>
-__global__ void __launch_bounds__(128)
+template <int MODEL, bool JAC, int MINB>
+__global__ void __launch_bounds__(128, MINB)
     residual_jacobian_kernel(ProblemDev pb, Layout L, StateDev st, double2* __restrict__ last_projection,
                              ObsOut out, double huber) {
   const int64_t o = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
@@ -207,21 +207,21 @@ __global__ void __launch_bounds__(128)
       double wx[4], dwx[4], wy[4], dwy[4];
       bspline_basis(fu, wx, dwx);
       bspline_basis(fv, wy, dwy);
-      const double m0u = dot3(M0, ce.u), m1u = dot3(M1, ce.u);
-      const double* tan = st.tangents + c.tan_off;
-#pragma unroll
+      // d unproj / d G_k = w_k / |s| (I - u u^T) and M u = 0 (the columns of A are orthogonal to
+      // u), so d pixel / d theta_k = -w_k / |s| * M [t1 t2]_k
+      const double* tan = st.tangents + c.tan_off + 6 * static_cast<int64_t>(cell);
+#pragma unroll 1
       for (int yy = 0; yy < 4; ++yy) {
+        const double wyv = -sel4(wy, yy) * ce.inv_n;
 #pragma unroll
         for (int xx = 0; xx < 4; ++xx) {
-          const int64_t seq = cell + xx + static_cast<int64_t>(yy) * c.gw;
-          const double wk = -wx[xx] * wy[yy] * ce.inv_n;
-          const d3 t1 = ld3(tan + 6 * seq), t2 = ld3(tan + 6 * seq + 3);
-          const double ut1 = dot3(ce.u, t1), ut2 = dot3(ce.u, t2);
+          const double wk = wx[xx] * wyv;
+          const d3 t1 = ld3(tan + 6 * xx), t2 = ld3(tan + 6 * xx + 3);
           const int k = 2 * (xx + 4 * yy);
-          store_col(out, pb.n_obs, o, jc_intr + k, wk * (dot3(M0, t1) - m0u * ut1), wk * (dot3(M1, t1) - m1u * ut1));
-          store_col(out, pb.n_obs, o, jc_intr + k + 1, wk * (dot3(M0, t2) - m0u * ut2),
-                    wk * (dot3(M1, t2) - m1u * ut2));
+          store_col(out, pb.n_obs, o, jc_intr + k, wk * dot3(M0, t1), wk * dot3(M1, t1));
+          store_col(out, pb.n_obs, o, jc_intr + k + 1, wk * dot3(M0, t2), wk * dot3(M1, t2));
         }
+        tan += 6 * static_cast<int64_t>(c.gw);
       }
     }
   } else if (model == B200BA_MODEL_NONCENTRAL_GENERIC) {
@@ -248,12 +248,13 @@ __global__ void __launch_bounds__(128)
       rd1 = ne.inv_n * (rd1 - dot3(rd1, ne.u) * ne.u);
       rd2 = ne.inv_n * (rd2 - dot3(rd2, ne.u) * ne.u);
       const double* tan = st.tangents + c.tan_off;
-#pragma unroll
+#pragma unroll 1
       for (int yy = 0; yy < 4; ++yy) {
+        const double wyv = sel4(wy, yy);
 #pragma unroll
         for (int xx = 0; xx < 4; ++xx) {
           const int64_t seq = cell + xx + static_cast<int64_t>(yy) * c.gw;
-          const double wk = wx[xx] * wy[yy];
+          const double wk = wx[xx] * wyv;
           const d3 t1 = ld3(tan + 6 * seq), t2 = ld3(tan + 6 * seq + 3);
           const d3 dk = ld3(intr + 3 * seq);
           const int k = 5 * (xx + 4 * yy);
@@ -344,6 +345,19 @@ __global__ void __launch_bounds__(128)
   }
 }
 
+// Resident blocks per SM the kernel is compiled for (register budget 65536 / (128 * MINB)).
+// 4 (128 registers, 16 warps / SM) is the measured optimum for the central model on B200;
+// B200BA_JAC_MINB=2|3|4 overrides it for tuning runs.
+static int jac_minb() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("B200BA_JAC_MINB");
+    v = e ? atoi(e) : 4;
+    if (v < 2 || v > 4) v = 4;
+  }
+  return v;
+}
+
 template <bool JAC>
 static void launch_rj(int model, const ProblemDev& pb, const Layout& L, const StateDev& st, double2* lp,
                       const ObsOut& out, double huber, cudaStream_t s) {
@@ -352,16 +366,24 @@ static void launch_rj(int model, const ProblemDev& pb, const Layout& L, const St
   if (blocks == 0) return;
   switch (model) {
     case B200BA_MODEL_CENTRAL_GENERIC:
-      residual_jacobian_kernel<B200BA_MODEL_CENTRAL_GENERIC, JAC><<<blocks, threads, 0, s>>>(pb, L, st, lp, out, huber);
+      switch (jac_minb()) {
+        case 2: residual_jacobian_kernel<B200BA_MODEL_CENTRAL_GENERIC, JAC, 2><<<blocks, threads, 0, s>>>(pb, L, st, lp, out, huber); break;
+        case 3: residual_jacobian_kernel<B200BA_MODEL_CENTRAL_GENERIC, JAC, 3><<<blocks, threads, 0, s>>>(pb, L, st, lp, out, huber); break;
+        default: residual_jacobian_kernel<B200BA_MODEL_CENTRAL_GENERIC, JAC, 4><<<blocks, threads, 0, s>>>(pb, L, st, lp, out, huber);
+      }
       break;
     case B200BA_MODEL_NONCENTRAL_GENERIC:
-      residual_jacobian_kernel<B200BA_MODEL_NONCENTRAL_GENERIC, JAC><<<blocks, threads, 0, s>>>(pb, L, st, lp, out, huber);
+      switch (jac_minb()) {
+        case 2: residual_jacobian_kernel<B200BA_MODEL_NONCENTRAL_GENERIC, JAC, 2><<<blocks, threads, 0, s>>>(pb, L, st, lp, out, huber); break;
+        case 3: residual_jacobian_kernel<B200BA_MODEL_NONCENTRAL_GENERIC, JAC, 3><<<blocks, threads, 0, s>>>(pb, L, st, lp, out, huber); break;
+        default: residual_jacobian_kernel<B200BA_MODEL_NONCENTRAL_GENERIC, JAC, 4><<<blocks, threads, 0, s>>>(pb, L, st, lp, out, huber);
+      }
       break;
     case B200BA_MODEL_CENTRAL_OPENCV:
-      residual_jacobian_kernel<B200BA_MODEL_CENTRAL_OPENCV, JAC><<<blocks, threads, 0, s>>>(pb, L, st, lp, out, huber);
+      residual_jacobian_kernel<B200BA_MODEL_CENTRAL_OPENCV, JAC, 4><<<blocks, threads, 0, s>>>(pb, L, st, lp, out, huber);
       break;
     default:
-      residual_jacobian_kernel<-1, JAC><<<blocks, threads, 0, s>>>(pb, L, st, lp, out, huber);
+      residual_jacobian_kernel<-1, JAC, 3><<<blocks, threads, 0, s>>>(pb, L, st, lp, out, huber);
   }
 }
 
@@ -547,55 +569,27 @@ void launch_accumulate_scatter(const ProblemDev& pb, const Layout& L, const ObsO
   accumulate_scatter_kernel<<<blocks, threads, 0, s>>>(pb, L, out, sys, huber);
 }
 
-// Sort key of an observation for the cell-grouped pass: camera-major, then B-spline cell.
-__global__ void cell_keys_kernel(ProblemDev pb, ObsOut out, uint32_t* keys, uint32_t* vals, uint32_t invalid_key) {
-  const int64_t o = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
-  if (o >= pb.n_obs) return;
-  uint32_t key = invalid_key;
-  if (out.has_jac[o]) {
-    const int cam = static_cast<int>(pb.obs_camera[o]);
-    uint32_t base = 0;
-    for (int c = 0; c < cam; ++c) base += static_cast<uint32_t>(max(1, pb.cams[c].gw * pb.cams[c].gh));
-    key = base + static_cast<uint32_t>(max(0, out.cell[o]));
-  }
-  keys[o] = key;
-  vals[o] = static_cast<uint32_t>(o);
-}
-
-void launch_cell_keys(const ProblemDev& pb, const ObsOut& out, uint32_t* keys, uint32_t* vals, uint32_t invalid_key,
-                      cudaStream_t s) {
-  const int threads = 256;
-  const unsigned blocks = static_cast<unsigned>((pb.n_obs + threads - 1) / threads);
-  if (blocks == 0) return;
-  cell_keys_kernel<<<blocks, threads, 0, s>>>(pb, out, keys, vals, invalid_key);
-}
-
-size_t sort_temp_bytes(int64_t n, int end_bit) {
-  size_t bytes = 0;
-  cub::DeviceRadixSort::SortPairs(nullptr, bytes, static_cast<uint32_t*>(nullptr), static_cast<uint32_t*>(nullptr),
-                                  static_cast<uint32_t*>(nullptr), static_cast<uint32_t*>(nullptr),
-                                  static_cast<int>(n), 0, end_bit);
-  return bytes;
-}
-void sort_pairs(void* temp, size_t temp_bytes, const uint32_t* keys_in, uint32_t* keys_out, const uint32_t* vals_in,
-                uint32_t* vals_out, int64_t n, int end_bit, cudaStream_t s) {
-  cub::DeviceRadixSort::SortPairs(temp, temp_bytes, keys_in, keys_out, vals_in, vals_out, static_cast<int>(n), 0,
-                                  end_bit, s);
-}
-
 // (rig U intrinsics) x (rig U intrinsics) and the matching b entries, grouped by (camera,
 // cell): every observation of a cell touches the same 4x4 control points, so the block sums
-// the rank-2 updates of a run of equal keys in registers and issues ONE set of FP64 atomics
+// the rank-2 updates of a run of equal cells in registers and issues ONE set of FP64 atomics
 // per run (neighbouring cells overlap in control points, hence atomics rather than stores).
-// A block owns kCellChunk consecutive observations of the key-sorted order.
+// Observations are stored in a static cell-major order (sorted once, at b200ba_create, by the
+// cell of the MEASURED pixel), so runs are long; an observation whose projection currently
+// falls into a neighbouring cell merely starts a short run of its own -- no per-iteration sort.
+// A block owns kCellChunk consecutive observations.
 constexpr int kCellChunk = 128;
 constexpr int kCellTile = 32;
 constexpr int kCellThreads = 256;
+constexpr uint32_t kInvalidKey = 0xffffffffu;
+
+__device__ __forceinline__ uint32_t cell_key(const ProblemDev& pb, const ObsOut& out, int64_t pos) {
+  if (!out.has_jac[pos]) return kInvalidKey;
+  return (pb.obs_camera[pos] << 24) | static_cast<uint32_t>(out.cell[pos]);  // <= 8 cameras, < 2^24 cells
+}
 
 template <int MAXPAIRS>
 __global__ void __launch_bounds__(kCellThreads)
-    accumulate_cells_kernel(ProblemDev pb, Layout L, ObsOut out, SystemDev sys, const uint32_t* __restrict__ keys,
-                            const uint32_t* __restrict__ order, uint32_t invalid_key, double huber) {
+    accumulate_cells_kernel(ProblemDev pb, Layout L, ObsOut out, SystemDev sys, double huber) {
   extern __shared__ double smem[];
   const int64_t n = pb.n_obs;
   const int64_t begin = static_cast<int64_t>(blockIdx.x) * kCellChunk;
@@ -606,7 +600,6 @@ __global__ void __launch_bounds__(kCellThreads)
   double* sJy = sJx + kCellTile * Emax;       // [kCellTile][Emax]
   double* sR = sJy + kCellTile * Emax;        // [kCellTile][2]     sqrt(w) * r
   __shared__ uint32_t sKey[kCellTile];
-  __shared__ uint32_t sObs[kCellTile];
 
   double acc[MAXPAIRS];
   double accb = 0;
@@ -614,21 +607,14 @@ __global__ void __launch_bounds__(kCellThreads)
 
   int64_t pos = begin;
   while (pos < end) {
-    const uint32_t key = keys[pos];
-    if (key == invalid_key) break;  // invalid observations sort last
-    // decode camera and cell of this run
-    int cam = 0;
-    uint32_t rem = key;
-    for (int cc = 0; cc < L.n_cameras; ++cc) {
-      const uint32_t G = static_cast<uint32_t>(max(1, pb.cams[cc].gw * pb.cams[cc].gh));
-      if (rem < G) {
-        cam = cc;
-        break;
-      }
-      rem -= G;
+    const uint32_t key = cell_key(pb, out, pos);
+    if (key == kInvalidKey) {  // no Jacobian for this observation (uniform across the block)
+      ++pos;
+      continue;
     }
+    const int cam = static_cast<int>(key >> 24);
+    const int cell = static_cast<int>(key & 0xffffffu);
     const CamDev& c = pb.cams[cam];
-    const int cell = static_cast<int>(rem);
     const int E = rigE + c.K;
     const int npairs = E * (E + 1) / 2;
     // pair -> (i, j), i <= j, row-major over the upper triangle
@@ -638,8 +624,7 @@ __global__ void __launch_bounds__(kCellThreads)
       const int p = threadIdx.x + q * kCellThreads;
       int i = 0, j = 0;
       if (p < npairs) {
-        // row i starts at offset i*E - i(i-1)/2
-        int lo = 0, hi = E - 1;
+        int lo = 0, hi = E - 1;  // row i starts at offset i*E - i(i-1)/2
         while (lo < hi) {
           const int mid = (lo + hi + 1) >> 1;
           if (mid * E - mid * (mid - 1) / 2 <= p) lo = mid; else hi = mid - 1;
@@ -656,18 +641,15 @@ __global__ void __launch_bounds__(kCellThreads)
     while (!run_done && pos < end) {
       const int tile_n = static_cast<int>(min(static_cast<int64_t>(kCellTile), end - pos));
       __syncthreads();
-      if (threadIdx.x < tile_n) {
-        sKey[threadIdx.x] = keys[pos + threadIdx.x];
-        sObs[threadIdx.x] = order[pos + threadIdx.x];
-      }
+      if (threadIdx.x < tile_n) sKey[threadIdx.x] = cell_key(pb, out, pos + threadIdx.x);
       __syncthreads();
       int run_n = 0;
       while (run_n < tile_n && sKey[run_n] == key) ++run_n;
       if (run_n < tile_n) run_done = true;
-      // stage sqrt(w) * J of the run's observations
+      // stage sqrt(w) * J of the run's observations (contiguous positions: coalesced per column)
       for (int idx = threadIdx.x; idx < run_n * E; idx += kCellThreads) {
-        const int t = idx / E, e = idx - t * E;
-        const int64_t o = sObs[t];
+        const int e = idx / run_n, t = idx - e * run_n;
+        const int64_t o = pos + t;
         const double rx = out.residual[o], ry = out.residual[n + o];
         const double sw = sqrt(huber_weight_sq(huber, rx * rx + ry * ry));
         const int col = (e < rigE) ? (L.jc_rig + e) : (L.jc_intr + (e - rigE));
@@ -713,8 +695,7 @@ __global__ void __launch_bounds__(kCellThreads)
 }
 
 void launch_accumulate_cells(const ProblemDev& pb, const Layout& L, const ObsOut& out, const SystemDev& sys,
-                             const uint32_t* keys, const uint32_t* order, uint32_t invalid_key, double huber,
-                             cudaStream_t s) {
+                             double huber, cudaStream_t s) {
   if (pb.n_obs == 0) return;
   const int rigE = L.rig_in_state ? 6 : 0;
   const int Emax = rigE + L.Kmax;
@@ -727,8 +708,7 @@ void launch_accumulate_cells(const ProblemDev& pb, const Layout& L, const ObsOut
   do {                                                                                                       \
     cudaFuncSetAttribute(accumulate_cells_kernel<MP>, cudaFuncAttributeMaxDynamicSharedMemorySize,           \
                          static_cast<int>(smem));                                                            \
-    accumulate_cells_kernel<MP><<<blocks, kCellThreads, smem, s>>>(pb, L, out, sys, keys, order, invalid_key, \
-                                                                   huber);                                   \
+    accumulate_cells_kernel<MP><<<blocks, kCellThreads, smem, s>>>(pb, L, out, sys, huber);                  \
   } while (0)
   if (per_thread <= 1)
     B200BA_LAUNCH_CELLS(1);

@@ -12,14 +12,8 @@ void launch_residual_jacobian(int uniform_model, bool jac, const ProblemDev& pb,
                               cudaStream_t s);
 void launch_accumulate_scatter(const ProblemDev& pb, const Layout& L, const ObsOut& out, const SystemDev& sys,
                                double huber, cudaStream_t s);
-void launch_cell_keys(const ProblemDev& pb, const ObsOut& out, uint32_t* keys, uint32_t* vals, uint32_t invalid_key,
-                      cudaStream_t s);
-size_t sort_temp_bytes(int64_t n, int end_bit);
-void sort_pairs(void* temp, size_t temp_bytes, const uint32_t* keys_in, uint32_t* keys_out, const uint32_t* vals_in,
-                uint32_t* vals_out, int64_t n, int end_bit, cudaStream_t s);
 void launch_accumulate_cells(const ProblemDev& pb, const Layout& L, const ObsOut& out, const SystemDev& sys,
-                             const uint32_t* keys, const uint32_t* order, uint32_t invalid_key, double huber,
-                             cudaStream_t s);
+                             double huber, cudaStream_t s);
 void launch_schur_blocks(int n_points, const double* Dblk, const double* bp, double lambda, double* Linv, double* v,
                          int* fail, cudaStream_t s);
 void launch_schur_scale_rows(int n_points, int nd, const double* B, const double* Linv, double* W, cudaStream_t s);
