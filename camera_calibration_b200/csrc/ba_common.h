@@ -77,6 +77,7 @@ struct ObsOut {
   double* jac;         // [2 * n_jcols][n_obs] SoA: row-x of column c at (2c) * n_obs, row-y at (2c+1) * n_obs
   int32_t* cell;       // [n_obs] top-left control point x0 + y0 * gw of the 4x4 support (generic models)
   uint8_t* has_jac;    // [n_obs]
+  uint16_t* evals;     // [n_obs] spline evaluations spent by the projection LM (diagnostics; may be NULL)
 };
 
 // The normal equations on the device (all FP64). Everything that takes part in the

@@ -126,7 +126,7 @@ __device__ __forceinline__ void central_eval(const CamDev& c, const double* __re
 // here every evaluation yields both, so the evaluation of an accepted trial IS the next
 // iteration's current evaluation. Control flow and results are those of the reference.
 __device__ __forceinline__ bool central_project(const CamDev& c, const double* __restrict__ grid, d3 dir,
-                                                double& px, double& py, CentralEval& e) {
+                                                double& px, double& py, CentralEval& e, int& n_eval) {
   constexpr double kEpsilon = 1e-12;
   double tx = px, ty = py;
   double lambda = -1.0, cost = 0, H00 = 0, H01 = 0, H11 = 0, b0 = 0, b1 = 0;
@@ -136,6 +136,7 @@ __device__ __forceinline__ bool central_project(const CamDev& c, const double* _
   while (true) {
     CentralEval t;
     central_eval(c, grid, tx, ty, t);
+    ++n_eval;
     const d3 r = t.u - dir;
     const double tcost = dot3(r, r);
     if (!have_cur || tcost < cost) {
@@ -258,7 +259,7 @@ __device__ __forceinline__ void noncentral_residual_jac(const NoncentralEval& e,
 __device__ __forceinline__ bool noncentral_project(const CamDev& c, const double* __restrict__ dgrid,
                                                    const double* __restrict__ pgrid, d3 p, double& px,
                                                    double& py, NoncentralEval& e, d3& t1, d3& t2,
-                                                   double R[2][2]) {
+                                                   double R[2][2], int& n_eval) {
   constexpr double kEpsilon = 1e-12;
   double tx = px, ty = py;
   double lambda = -1.0, cost = 0, H00 = 0, H01 = 0, H11 = 0, b0 = 0, b1 = 0;
@@ -268,6 +269,7 @@ __device__ __forceinline__ bool noncentral_project(const CamDev& c, const double
   while (true) {
     NoncentralEval t;
     noncentral_eval(c, dgrid, pgrid, tx, ty, t);
+    ++n_eval;
     double r0, r1;
     d3 tt1, tt2;
     noncentral_residual(t, p, r0, r1, tt1, tt2);

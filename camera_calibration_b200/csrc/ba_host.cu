@@ -316,6 +316,8 @@ int make_layout(b200ba_handle* h, const b200ba_options* opt) {
   if (dev_alloc(h, &h->out.jac, 2 * static_cast<size_t>(L.n_jcols) * n)) return 1;
   if (dev_alloc(h, &h->out.cell, n)) return 1;
   if (dev_alloc(h, &h->out.has_jac, n)) return 1;
+  if (dev_alloc(h, &h->out.evals, n)) return 1;
+  h->out_trial.evals = nullptr;
   if (dev_alloc(h, &h->out_trial.residual, 2 * n)) return 1;
   if (dev_alloc(h, &h->out_trial.cost, n)) return 1;
   h->out_trial.jac = nullptr;
@@ -507,7 +509,7 @@ void free_handle_buffers(b200ba_handle* h) {
     F(h->st[i].image_tr_global); F(h->st[i].tangents);
   }
   F(h->d_last_projection);
-  F(h->out.residual); F(h->out.cost); F(h->out.jac); F(h->out.cell); F(h->out.has_jac);
+  F(h->out.residual); F(h->out.cost); F(h->out.jac); F(h->out.cell); F(h->out.has_jac); F(h->out.evals);
   F(h->out_trial.residual); F(h->out_trial.cost);
   F(h->sys.base); F(h->d_W); F(h->d_S); F(h->d_Linv); F(h->d_v); F(h->d_y); F(h->d_x); F(h->d_potrf_work);
   F(h->d_info); F(h->d_fail);
@@ -1020,6 +1022,16 @@ int b200ba_build_system(b200ba_handle* h, const b200ba_options* opt, int32_t n, 
     for (int k = i; k < L.nd; ++k) H[static_cast<size_t>(L.nbd + i) * n + L.nbd + k] = C[static_cast<size_t>(i) * L.nd + k];
   for (int i = 0; i < L.nbd; ++i) b[i] = bp[i];
   for (int i = 0; i < L.nd; ++i) b[L.nbd + i] = bd[i];
+  return 0;
+}
+
+// Diagnostics: spline evaluations spent per observation by the last pass that wrote Jacobians
+// (caller's observation order). Not part of the reference interface.
+B200BA_API int b200ba_debug_eval_counts(b200ba_handle* h, uint16_t* counts) {
+  if (!h || !counts || !h->have_layout) return 1;
+  std::vector<uint16_t> tmp(h->n_obs);
+  CUDA_TRY(h, cudaMemcpy(tmp.data(), h->out.evals, h->n_obs * sizeof(uint16_t), cudaMemcpyDeviceToHost));
+  for (int64_t i = 0; i < h->n_obs; ++i) counts[h->perm[i]] = tmp[i];
   return 0;
 }
 

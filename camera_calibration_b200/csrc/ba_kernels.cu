@@ -137,6 +137,7 @@ __global__ void __launch_bounds__(128, MINB)
 
   const double* intr = st.intrinsics + c.intr_off;
   bool ok = false;
+  int n_eval = 0;
   CentralEval ce;
   NoncentralEval ne;
   d3 nt1, nt2;
@@ -144,24 +145,25 @@ __global__ void __launch_bounds__(128, MINB)
   if (model == B200BA_MODEL_CENTRAL_GENERIC) {
     const double ilen = rsqrt(dot3(lp, lp));
     const d3 dir = ilen * lp;
-    ok = central_project(c, intr, dir, px, py, ce);
+    ok = central_project(c, intr, dir, px, py, ce, n_eval);
     if (!ok) {
       px = c.center_x;
       py = c.center_y;
-      ok = central_project(c, intr, dir, px, py, ce);
+      ok = central_project(c, intr, dir, px, py, ce, n_eval);
     }
   } else if (model == B200BA_MODEL_NONCENTRAL_GENERIC) {
     const double* pgrid = intr + 3 * static_cast<int64_t>(c.gw) * c.gh;
-    ok = noncentral_project(c, intr, pgrid, lp, px, py, ne, nt1, nt2, nR);
+    ok = noncentral_project(c, intr, pgrid, lp, px, py, ne, nt1, nt2, nR, n_eval);
     if (!ok) {
       px = c.center_x;
       py = c.center_y;
-      ok = noncentral_project(c, intr, pgrid, lp, px, py, ne, nt1, nt2, nR);
+      ok = noncentral_project(c, intr, pgrid, lp, px, py, ne, nt1, nt2, nR, n_eval);
     }
   } else {
     ok = opencv_project(c, intr, lp, px, py);  // initial estimate ignored (central_opencv.h:61-67)
   }
 
+  if (out.evals) out.evals[o] = static_cast<uint16_t>(min(n_eval, 65535));
   if (!ok) {
     out.cost[o] = -1.0;  // AddInvalidResidual (LV/lm_optimizer_update_accumulator.h:158-160)
     out.residual[o] = nan("");
@@ -1032,12 +1034,14 @@ __global__ void project_points_kernel(CamDev c, const double* __restrict__ intr,
   bool r = false;
   if (c.model_type == B200BA_MODEL_CENTRAL_GENERIC) {
     CentralEval e;
-    if (in_area(c, x, y)) r = central_project(c, intr, rsqrt(dot3(p, p)) * p, x, y, e);
+    int ne = 0;
+    if (in_area(c, x, y)) r = central_project(c, intr, rsqrt(dot3(p, p)) * p, x, y, e, ne);
   } else if (c.model_type == B200BA_MODEL_NONCENTRAL_GENERIC) {
     NoncentralEval e;
     d3 t1, t2;
     double R[2][2];
-    if (in_area(c, x, y)) r = noncentral_project(c, intr, intr + 3 * static_cast<int64_t>(c.gw) * c.gh, p, x, y, e, t1, t2, R);
+    int ne = 0;
+    if (in_area(c, x, y)) r = noncentral_project(c, intr, intr + 3 * static_cast<int64_t>(c.gw) * c.gh, p, x, y, e, t1, t2, R, ne);
   } else {
     r = opencv_project(c, intr, p, x, y);
   }

@@ -429,6 +429,10 @@ def make_problem(config: int = 2, *, seed: Optional[int] = None, n_imagesets: Op
             xy, ok = per_cam[c]
             idx = np.nonzero(ok)[0]
             noisy = xy[idx] + noise_px * rng.standard_normal((len(idx), 2))
+            # a detected feature always lies inside the calibrated rectangle (the reference derives
+            # the rectangle from the features, calibration.cc:615-658): drop noisy out-of-rect pixels
+            keep = in_area(cams[c], noisy[:, 0].astype(np.float32), noisy[:, 1].astype(np.float32))
+            idx, noisy = idx[keep], noisy[keep]
             obs_is.append(np.full(len(idx), i, dtype=np.uint32))
             obs_cam.append(np.full(len(idx), c, dtype=np.uint32))
             obs_pt.append(idx.astype(np.uint32))

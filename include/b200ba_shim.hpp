@@ -7,7 +7,7 @@
 // containers here are minimal look-alikes (same member names and meaning). In the reference tree
 // the same 60 lines of flattening are written against the real classes -- INTEGRATION.md shows it.
 //
-// Header-only; link with -lb200ba. No oracle, no CPU fallback: errors are returned, not hidden.
+// Header-only; link with -lb200ba. No CPU fallback: errors are returned, not hidden.
 #pragma once
 
 #include <cmath>
