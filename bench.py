@@ -81,11 +81,41 @@ class ClockSampler:
 
 
 def make_workload(args):
+    """Seeded synthetic problem; cached in /tmp so that several bench invocations on one box (and
+    the ranks of one torchrun) do not regenerate it -- generation is deterministic."""
+    import pickle
     from camera_calibration_b200 import synthetic
     kw = {}
     if args.imagesets:
         kw["n_imagesets"] = args.imagesets
+    cache = f"/tmp/b200ba_workload_c{args.config}_i{args.imagesets}_v2.pkl"
+    if os.path.exists(cache):
+        try:
+            d = pickle.load(open(cache, "rb"))
+            from camera_calibration_b200.cabi import Camera, FlatProblem, FlatState
+            cams = []
+            for f in d["cams"]:
+                c = Camera()
+                for k, v in f.items():
+                    setattr(c, k, v)
+                cams.append(c)
+            pb = FlatProblem(cams, d["n_imagesets"], d["n_points"], d["oi"], d["oc"], d["op"], d["oxy"])
+            mk = lambda t: FlatState(t[0], t[1], t[2], t[3], t[4])
+            return synthetic.SyntheticProblem(d["name"], pb, mk(d["init"]), mk(d["gt"]), d["seed"], d["info"])
+        except Exception:
+            pass
     sp = synthetic.make_problem(args.config, **kw)
+    try:
+        p = sp.problem
+        st = lambda s: (s.points, s.rig_tr_global, s.camera_tr_rig, s.intrinsics, s.last_projection)
+        d = dict(cams=[{k: getattr(c, k) for k, _ in c._fields_} for c in p.cameras], n_imagesets=p.n_imagesets,
+                 n_points=p.n_points, oi=p.obs_imageset, oc=p.obs_camera, op=p.obs_point, oxy=p.obs_xy,
+                 init=st(sp.init_state), gt=st(sp.gt_state), seed=sp.seed, info=sp.info, name=sp.name)
+        tmp = cache + f".{os.getpid()}"
+        pickle.dump(d, open(tmp, "wb"))
+        os.replace(tmp, cache)
+    except Exception:
+        pass
     return sp
 
 

@@ -125,8 +125,13 @@ __device__ __forceinline__ void central_eval(const CamDev& c, const double* __re
 // evaluates "value + Jacobian at the current pixel" and "value at the trial pixel" separately;
 // here every evaluation yields both, so the evaluation of an accepted trial IS the next
 // iteration's current evaluation. Control flow and results are those of the reference.
-__device__ __forceinline__ bool central_project(const CamDev& c, const double* __restrict__ grid, d3 dir,
-                                                double& px, double& py, CentralEval& e, int& n_eval) {
+// Return value: kProjFail / kProjOk as the reference's bool; kProjUnfinished when the evaluation
+// budget max_evals ran out first (the caller then defers the observation to the straggler pass,
+// which redoes it with an unlimited budget -- results are those of an uninterrupted run).
+constexpr int kProjFail = 0, kProjOk = 1, kProjUnfinished = 2;
+__device__ __forceinline__ int central_project(const CamDev& c, const double* __restrict__ grid, d3 dir,
+                                               double& px, double& py, CentralEval& e, int& n_eval,
+                                               int max_evals) {
   constexpr double kEpsilon = 1e-12;
   double tx = px, ty = py;
   double lambda = -1.0, cost = 0, H00 = 0, H01 = 0, H11 = 0, b0 = 0, b1 = 0;
@@ -134,6 +139,7 @@ __device__ __forceinline__ bool central_project(const CamDev& c, const double* _
   int outer = 0, attempt = 0;
   const double lo_x = c.min_x, lo_y = c.min_y, hi_x = c.max_x + 0.999, hi_y = c.max_y + 0.999;
   while (true) {
+    if (n_eval >= max_evals) return kProjUnfinished;
     CentralEval t;
     central_eval(c, grid, tx, ty, t);
     ++n_eval;
@@ -146,8 +152,8 @@ __device__ __forceinline__ bool central_project(const CamDev& c, const double* _
       e = t;
       if (have_cur) {
         lambda *= 0.5;
-        if (cost < kEpsilon) return true;  // cost measured BEFORE the step
-        if (outer >= 100) return false;
+        if (cost < kEpsilon) return kProjOk;  // cost measured BEFORE the step
+        if (outer >= 100) return kProjFail;
       }
       have_cur = true;
       ++outer;
@@ -161,7 +167,7 @@ __device__ __forceinline__ bool central_project(const CamDev& c, const double* _
       if (lambda < 0) lambda = 0.01 * 0.5 * (H00 + H11);
     } else {
       lambda *= 2.0;
-      if (++attempt >= 10) return cost < kEpsilon;
+      if (++attempt >= 10) return (cost < kEpsilon) ? kProjOk : kProjFail;
     }
     const double H00l = H00 + lambda, H11l = H11 + lambda;
     const double x1 = (b1 - H01 / H00l * b0) / (H11l - H01 * H01 / H00l);
@@ -256,10 +262,10 @@ __device__ __forceinline__ void noncentral_residual_jac(const NoncentralEval& e,
 // NoncentralGenericModel::ProjectWithInitialEstimate (noncentral_generic.cc:156-264); same
 // single-evaluation-site formulation as central_project. On success R is the 2x2 residual
 // Jacobian and (t1, t2) the tangent frame at the final pixel (inputs of the implicit-function step).
-__device__ __forceinline__ bool noncentral_project(const CamDev& c, const double* __restrict__ dgrid,
-                                                   const double* __restrict__ pgrid, d3 p, double& px,
-                                                   double& py, NoncentralEval& e, d3& t1, d3& t2,
-                                                   double R[2][2], int& n_eval) {
+__device__ __forceinline__ int noncentral_project(const CamDev& c, const double* __restrict__ dgrid,
+                                                  const double* __restrict__ pgrid, d3 p, double& px,
+                                                  double& py, NoncentralEval& e, d3& t1, d3& t2,
+                                                  double R[2][2], int& n_eval, int max_evals) {
   constexpr double kEpsilon = 1e-12;
   double tx = px, ty = py;
   double lambda = -1.0, cost = 0, H00 = 0, H01 = 0, H11 = 0, b0 = 0, b1 = 0;
@@ -267,6 +273,7 @@ __device__ __forceinline__ bool noncentral_project(const CamDev& c, const double
   int outer = 0, attempt = 0;
   const double lo_x = c.min_x, lo_y = c.min_y, hi_x = c.max_x + 0.999, hi_y = c.max_y + 0.999;
   while (true) {
+    if (n_eval >= max_evals) return kProjUnfinished;
     NoncentralEval t;
     noncentral_eval(c, dgrid, pgrid, tx, ty, t);
     ++n_eval;
@@ -283,8 +290,8 @@ __device__ __forceinline__ bool noncentral_project(const CamDev& c, const double
       noncentral_residual_jac(t, p, tt1, tt2, R);
       if (have_cur) {
         lambda *= 0.5;
-        if (cost < kEpsilon) return true;
-        if (outer >= 100) return false;
+        if (cost < kEpsilon) return kProjOk;
+        if (outer >= 100) return kProjFail;
       }
       have_cur = true;
       ++outer;
@@ -298,7 +305,7 @@ __device__ __forceinline__ bool noncentral_project(const CamDev& c, const double
       if (lambda < 0) lambda = 0.01 * 0.5 * (H00 + H11);
     } else {
       lambda *= 2.0;
-      if (++attempt >= 10) return cost < kEpsilon;
+      if (++attempt >= 10) return (cost < kEpsilon) ? kProjOk : kProjFail;
     }
     const double H00l = H00 + lambda, H11l = H11 + lambda;
     const double x1 = (b1 - H01 / H00l * b0) / (H11l - H01 * H01 / H00l);

@@ -116,6 +116,8 @@ struct b200ba_handle {
   // Static cell-major processing order: device position -> index in the caller's (reference)
   // observation order. Computed once at create time from the cell of the measured pixel.
   std::vector<uint32_t> perm;
+  uint32_t* d_straggler_list = nullptr;  // observations deferred by the main pass of the Jacobian kernel
+  int* d_straggler_count = nullptr;
   double *d_partial = nullptr, *d_scal = nullptr;
   double* h_scal = nullptr;  // pinned [16]
   int* h_flags = nullptr;    // pinned [2]
@@ -382,8 +384,8 @@ int evaluate_state(b200ba_handle* h, int which, bool jac, const ObsOut& out, dou
   {
     ScopedPhase ph(h, phase);
     launch_residual_jacobian(h->uniform_model, jac, h->pb, h->L, h->st[which], h->d_last_projection, out, huber,
-                             h->stream);
-    h->timings.kernel_launches += (h->n_obs > 0);
+                             h->d_straggler_list, h->d_straggler_count, h->stream);
+    h->timings.kernel_launches += 2 * (h->n_obs > 0);
   }
   CUDA_TRY(h, cudaGetLastError());
   return 0;
@@ -512,7 +514,7 @@ void free_handle_buffers(b200ba_handle* h) {
   F(h->out.residual); F(h->out.cost); F(h->out.jac); F(h->out.cell); F(h->out.has_jac); F(h->out.evals);
   F(h->out_trial.residual); F(h->out_trial.cost);
   F(h->sys.base); F(h->d_W); F(h->d_S); F(h->d_Linv); F(h->d_v); F(h->d_y); F(h->d_x); F(h->d_potrf_work);
-  F(h->d_info); F(h->d_fail);
+  F(h->d_info); F(h->d_fail); F(h->d_straggler_list); F(h->d_straggler_count);
   F(h->d_partial); F(h->d_scal);
   if (h->h_scal) cudaFreeHost(h->h_scal);
   if (h->h_flags) cudaFreeHost(h->h_flags);
@@ -701,6 +703,8 @@ int b200ba_create(const b200ba_problem* p, int device, b200ba_handle** out) {
   }
   TRYC(dev_alloc(h, &h->d_last_projection, n));
   TRYC(cuda_ok(cudaMemset(h->d_last_projection, 0, std::max<int64_t>(1, n) * sizeof(double2)), "memset"));
+  TRYC(dev_alloc(h, &h->d_straggler_list, n));
+  TRYC(dev_alloc(h, &h->d_straggler_count, 1));
   TRYC(dev_alloc(h, &h->d_info, 2));
   TRYC(dev_alloc(h, &h->d_fail, 1));
   TRYC(dev_alloc(h, &h->d_partial, cost_reduce_partial_size()));
@@ -1024,6 +1028,10 @@ int b200ba_build_system(b200ba_handle* h, const b200ba_options* opt, int32_t n, 
   for (int i = 0; i < L.nd; ++i) b[L.nbd + i] = bd[i];
   return 0;
 }
+
+// Diagnostics / tests: evaluation budget of the main Jacobian pass (default 16); 1 forces every
+// observation of a generic camera through the straggler pass.
+B200BA_API void b200ba_debug_set_eval_budget(int budget) { set_main_eval_budget(budget); }
 
 // Diagnostics: spline evaluations spent per observation by the last pass that wrote Jacobians
 // (caller's observation order). Not part of the reference interface.

@@ -13,6 +13,7 @@
 // /root/reference/applications/camera_calibration/src/camera_calibration (APP) and
 // /root/reference/libvis/src/libvis (LV).
 
+#include <algorithm>
 #include <cstdlib>
 
 #include "ba_device.cuh"
@@ -105,12 +106,26 @@ __device__ __forceinline__ void store_col(const ObsOut& out, int64_t n_obs, int6
 // Jacobians obtained analytically through the implicit function theorem at the converged
 // projection (the reference differentiates numerically: joint_optimization.cc:357-376,
 // models/central_grid.h:187-245, models/noncentral_generic.h:224-283).
-template <int MODEL, bool JAC, int MINB>
-__global__ void __launch_bounds__(128, MINB)
-    residual_jacobian_kernel(ProblemDev pb, Layout L, StateDev st, double2* __restrict__ last_projection,
-                             ObsOut out, double huber) {
-  const int64_t o = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
-  if (o >= pb.n_obs) return;
+//
+// Two passes share this code. The MAIN pass (STRAGGLER = false) gives every observation a budget
+// of kMainEvalBudget spline evaluations -- in the warm-started steady state all but a handful
+// need exactly 2 -- and appends the rare observation that needs more (a point whose projection
+// runs against the border of the calibrated area burns the reference's full 100 x 10 iteration
+// allowance twice: ~400 evaluations) to a list instead of letting one lane hold its warp, block
+// and ultimately the whole launch hostage. The STRAGGLER pass redoes the listed observations from
+// scratch with an unlimited budget, two lanes per observation: lane 0 runs the warm-started
+// attempt, lane 1 speculatively runs the reference's retry from the image centre; the result is
+// exactly what the sequential reference procedure yields.
+constexpr int kUnlimitedEvals = 1 << 30;
+static int g_main_eval_budget = 16;
+void set_main_eval_budget(int b) { g_main_eval_budget = b < 1 ? 1 : b; }
+
+template <int MODEL, bool JAC, bool STRAGGLER>
+__device__ __forceinline__ void process_observation(const ProblemDev& pb, const Layout& L, const StateDev& st,
+                                                    double2* __restrict__ last_projection, const ObsOut& out,
+                                                    double huber, uint32_t* __restrict__ straggler_list,
+                                                    int* __restrict__ straggler_count, int64_t o, int role,
+                                                    int main_budget) {
   const int iset = static_cast<int>(pb.obs_imageset[o]);
   const int cam = static_cast<int>(pb.obs_camera[o]);
   const int pidx = static_cast<int>(pb.obs_point[o]);
@@ -142,28 +157,55 @@ __global__ void __launch_bounds__(128, MINB)
   NoncentralEval ne;
   d3 nt1, nt2;
   double nR[2][2];
+  const int budget = STRAGGLER ? kUnlimitedEvals : main_budget;
+  int status = kProjFail;
+  if (STRAGGLER && role == 1) {
+    px = c.center_x;
+    py = c.center_y;
+  }
   if (model == B200BA_MODEL_CENTRAL_GENERIC) {
     const double ilen = rsqrt(dot3(lp, lp));
     const d3 dir = ilen * lp;
-    ok = central_project(c, intr, dir, px, py, ce, n_eval);
-    if (!ok) {
+    status = central_project(c, intr, dir, px, py, ce, n_eval, budget);
+    if (!STRAGGLER && status == kProjFail) {
+      // backup: re-initialise at the centre of the calibrated area (joint_optimization.cc:334-342)
       px = c.center_x;
       py = c.center_y;
-      ok = central_project(c, intr, dir, px, py, ce, n_eval);
+      status = central_project(c, intr, dir, px, py, ce, n_eval, budget);
     }
   } else if (model == B200BA_MODEL_NONCENTRAL_GENERIC) {
     const double* pgrid = intr + 3 * static_cast<int64_t>(c.gw) * c.gh;
-    ok = noncentral_project(c, intr, pgrid, lp, px, py, ne, nt1, nt2, nR, n_eval);
-    if (!ok) {
+    status = noncentral_project(c, intr, pgrid, lp, px, py, ne, nt1, nt2, nR, n_eval, budget);
+    if (!STRAGGLER && status == kProjFail) {
       px = c.center_x;
       py = c.center_y;
-      ok = noncentral_project(c, intr, pgrid, lp, px, py, ne, nt1, nt2, nR, n_eval);
+      status = noncentral_project(c, intr, pgrid, lp, px, py, ne, nt1, nt2, nR, n_eval, budget);
     }
   } else {
-    ok = opencv_project(c, intr, lp, px, py);  // initial estimate ignored (central_opencv.h:61-67)
+    status = opencv_project(c, intr, lp, px, py) ? kProjOk : kProjFail;  // estimate ignored (central_opencv.h:61-67)
   }
-
+  if (!STRAGGLER) {
+    if (status == kProjUnfinished) {
+      const int slot = atomicAdd(straggler_count, 1);
+      straggler_list[slot] = static_cast<uint32_t>(o);
+      return;  // every output of this observation is written by the straggler pass
+    }
+    ok = status == kProjOk;
+  } else {
+    // lane 0 (warm) wins if it succeeded, else lane 1 (centre); the winner writes the outputs
+    const bool mine = (role != 2) && status == kProjOk;
+    const bool other = __shfl_xor_sync(0xffffffffu, mine ? 1 : 0, 1) != 0;
+    if (role == 2) return;
+    if (role == 0) {
+      ok = mine;
+      if (!mine && other) return;  // lane 1 reports the success
+    } else {
+      if (other || !mine) return;  // lane 0 succeeded, or both failed (lane 0 reports the failure)
+      ok = true;
+    }
+  }
   if (out.evals) out.evals[o] = static_cast<uint16_t>(min(n_eval, 65535));
+
   if (!ok) {
     out.cost[o] = -1.0;  // AddInvalidResidual (LV/lm_optimizer_update_accumulator.h:158-160)
     out.residual[o] = nan("");
@@ -347,6 +389,36 @@ __global__ void __launch_bounds__(128, MINB)
   }
 }
 
+template <int MODEL, bool JAC, int MINB, bool STRAGGLER>
+__global__ void __launch_bounds__(128, MINB)
+    residual_jacobian_kernel(ProblemDev pb, Layout L, StateDev st, double2* __restrict__ last_projection,
+                             ObsOut out, double huber, uint32_t* __restrict__ straggler_list,
+                             int* __restrict__ straggler_count, int main_budget) {
+  if (!STRAGGLER) {
+    const int64_t o = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+    if (o >= pb.n_obs) return;
+    process_observation<MODEL, JAC, false>(pb, L, st, last_projection, out, huber, straggler_list, straggler_count, o, 0,
+                                           main_budget);
+  } else {
+    // two lanes per listed observation; the loop bound is warp-uniform so that the pair shuffle
+    // inside process_observation always sees whole warps
+    const int count = *straggler_count;
+    const int lane = threadIdx.x & 31;
+    const int64_t warp_id = (blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x) >> 5;
+    const int64_t stride = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 1;  // pairs per sweep
+    for (int64_t base = warp_id * 16; base < count; base += stride) {
+      int64_t pair = base + (lane >> 1);
+      int role = lane & 1;  // 0 = warm-start attempt, 1 = speculative centre attempt
+      if (pair >= count) {
+        pair = count - 1;
+        role = 2;  // muted lane: computes, never writes
+      }
+      process_observation<MODEL, JAC, true>(pb, L, st, last_projection, out, huber, straggler_list, straggler_count,
+                                            straggler_list[pair], role, main_budget);
+    }
+  }
+}
+
 // Resident blocks per SM the kernel is compiled for (register budget 65536 / (128 * MINB)).
 // 4 (128 registers, 16 warps / SM) is the measured optimum for the central model on B200;
 // B200BA_JAC_MINB=2|3|4 overrides it for tuning runs.
@@ -360,42 +432,57 @@ static int jac_minb() {
   return v;
 }
 
-template <bool JAC>
-static void launch_rj(int model, const ProblemDev& pb, const Layout& L, const StateDev& st, double2* lp,
-                      const ObsOut& out, double huber, cudaStream_t s) {
+// Straggler pass geometry: a fixed grid that loops over the device-side list (its length is not
+// known on the host without a sync); 2 lanes per listed observation.
+constexpr int kStragglerBlocks = 296;
+constexpr int kStragglerThreads = 128;
+
+template <int MODEL, bool JAC, int MINB>
+static void launch_rj_model(const ProblemDev& pb, const Layout& L, const StateDev& st, double2* lp,
+                            const ObsOut& out, double huber, uint32_t* list, int* count, cudaStream_t s) {
   const int threads = 128;
   const unsigned blocks = static_cast<unsigned>((pb.n_obs + threads - 1) / threads);
-  if (blocks == 0) return;
+  residual_jacobian_kernel<MODEL, JAC, MINB, false><<<blocks, threads, 0, s>>>(pb, L, st, lp, out, huber, list, count,
+                                                                               g_main_eval_budget);
+}
+
+template <bool JAC>
+static void launch_rj(int model, const ProblemDev& pb, const Layout& L, const StateDev& st, double2* lp,
+                      const ObsOut& out, double huber, uint32_t* list, int* count, cudaStream_t s) {
+  if (pb.n_obs == 0) return;
+  cudaMemsetAsync(count, 0, sizeof(int), s);
   switch (model) {
     case B200BA_MODEL_CENTRAL_GENERIC:
       switch (jac_minb()) {
-        case 2: residual_jacobian_kernel<B200BA_MODEL_CENTRAL_GENERIC, JAC, 2><<<blocks, threads, 0, s>>>(pb, L, st, lp, out, huber); break;
-        case 3: residual_jacobian_kernel<B200BA_MODEL_CENTRAL_GENERIC, JAC, 3><<<blocks, threads, 0, s>>>(pb, L, st, lp, out, huber); break;
-        default: residual_jacobian_kernel<B200BA_MODEL_CENTRAL_GENERIC, JAC, 4><<<blocks, threads, 0, s>>>(pb, L, st, lp, out, huber);
+        case 2: launch_rj_model<B200BA_MODEL_CENTRAL_GENERIC, JAC, 2>(pb, L, st, lp, out, huber, list, count, s); break;
+        case 3: launch_rj_model<B200BA_MODEL_CENTRAL_GENERIC, JAC, 3>(pb, L, st, lp, out, huber, list, count, s); break;
+        default: launch_rj_model<B200BA_MODEL_CENTRAL_GENERIC, JAC, 4>(pb, L, st, lp, out, huber, list, count, s);
       }
+      residual_jacobian_kernel<B200BA_MODEL_CENTRAL_GENERIC, JAC, 2, true>
+          <<<kStragglerBlocks, kStragglerThreads, 0, s>>>(pb, L, st, lp, out, huber, list, count, 0);
       break;
     case B200BA_MODEL_NONCENTRAL_GENERIC:
-      switch (jac_minb()) {
-        case 2: residual_jacobian_kernel<B200BA_MODEL_NONCENTRAL_GENERIC, JAC, 2><<<blocks, threads, 0, s>>>(pb, L, st, lp, out, huber); break;
-        case 3: residual_jacobian_kernel<B200BA_MODEL_NONCENTRAL_GENERIC, JAC, 3><<<blocks, threads, 0, s>>>(pb, L, st, lp, out, huber); break;
-        default: residual_jacobian_kernel<B200BA_MODEL_NONCENTRAL_GENERIC, JAC, 4><<<blocks, threads, 0, s>>>(pb, L, st, lp, out, huber);
-      }
+      launch_rj_model<B200BA_MODEL_NONCENTRAL_GENERIC, JAC, 3>(pb, L, st, lp, out, huber, list, count, s);
+      residual_jacobian_kernel<B200BA_MODEL_NONCENTRAL_GENERIC, JAC, 2, true>
+          <<<kStragglerBlocks, kStragglerThreads, 0, s>>>(pb, L, st, lp, out, huber, list, count, 0);
       break;
     case B200BA_MODEL_CENTRAL_OPENCV:
-      residual_jacobian_kernel<B200BA_MODEL_CENTRAL_OPENCV, JAC, 4><<<blocks, threads, 0, s>>>(pb, L, st, lp, out, huber);
+      launch_rj_model<B200BA_MODEL_CENTRAL_OPENCV, JAC, 4>(pb, L, st, lp, out, huber, list, count, s);
       break;
     default:
-      residual_jacobian_kernel<-1, JAC, 3><<<blocks, threads, 0, s>>>(pb, L, st, lp, out, huber);
+      launch_rj_model<-1, JAC, 3>(pb, L, st, lp, out, huber, list, count, s);
+      residual_jacobian_kernel<-1, JAC, 2, true><<<kStragglerBlocks, kStragglerThreads, 0, s>>>(pb, L, st, lp, out, huber,
+                                                                                             list, count, 0);
   }
 }
 
 void launch_residual_jacobian(int uniform_model, bool jac, const ProblemDev& pb, const Layout& L,
                               const StateDev& st, double2* last_projection, const ObsOut& out, double huber,
-                              cudaStream_t s) {
+                              uint32_t* straggler_list, int* straggler_count, cudaStream_t s) {
   if (jac)
-    launch_rj<true>(uniform_model, pb, L, st, last_projection, out, huber, s);
+    launch_rj<true>(uniform_model, pb, L, st, last_projection, out, huber, straggler_list, straggler_count, s);
   else
-    launch_rj<false>(uniform_model, pb, L, st, last_projection, out, huber, s);
+    launch_rj<false>(uniform_model, pb, L, st, last_projection, out, huber, straggler_list, straggler_count, s);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1035,13 +1122,13 @@ __global__ void project_points_kernel(CamDev c, const double* __restrict__ intr,
   if (c.model_type == B200BA_MODEL_CENTRAL_GENERIC) {
     CentralEval e;
     int ne = 0;
-    if (in_area(c, x, y)) r = central_project(c, intr, rsqrt(dot3(p, p)) * p, x, y, e, ne);
+    if (in_area(c, x, y)) r = central_project(c, intr, rsqrt(dot3(p, p)) * p, x, y, e, ne, kUnlimitedEvals) == kProjOk;
   } else if (c.model_type == B200BA_MODEL_NONCENTRAL_GENERIC) {
     NoncentralEval e;
     d3 t1, t2;
     double R[2][2];
     int ne = 0;
-    if (in_area(c, x, y)) r = noncentral_project(c, intr, intr + 3 * static_cast<int64_t>(c.gw) * c.gh, p, x, y, e, t1, t2, R, ne);
+    if (in_area(c, x, y)) r = noncentral_project(c, intr, intr + 3 * static_cast<int64_t>(c.gw) * c.gh, p, x, y, e, t1, t2, R, ne, kUnlimitedEvals) == kProjOk;
   } else {
     r = opencv_project(c, intr, p, x, y);
   }

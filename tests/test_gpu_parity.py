@@ -293,3 +293,32 @@ def test_multi_gpu_matches_single_gpu():
            "127.0.0.1", "--master-port", "29533", os.path.join(root, "tests", "mgpu_check.py")]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
     assert r.returncode == 0 and "MGPU_OK" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
+
+
+def test_straggler_pass_equals_main_pass(oracle_lib):
+    """With an evaluation budget of 1 every observation is deferred to the two-lane straggler pass;
+    the results must equal the oracle exactly like the normal path's do."""
+    import ctypes as C
+    lib = cabi.load_library()
+    lib.b200ba_debug_set_eval_budget.restype = None
+    lib.b200ba_debug_set_eval_budget.argtypes = [C.c_int]
+    try:
+        lib.b200ba_debug_set_eval_budget(1)
+        for cfg in (2, 3):
+            sp = _small(cfg)
+            opt = cabi.default_options(max_iteration_count=3)
+            with api.BundleAdjuster(sp.problem) as adj:
+                adj.set_state(sp.init_state)
+                g = adj.evaluate(opt, compute_jacobians=True)
+                st = sp.init_state.copy()
+                rep = adj.optimize_host(st, opt)
+            o = oracle_lib.evaluate(sp.problem, sp.init_state, opt, True)
+            assert np.array_equal(g["costs"] >= 0, o["costs"] >= 0)
+            v = o["costs"] >= 0
+            assert np.abs(g["residuals"][v] - o["residuals"][v]).max() < 1e-9
+            assert np.abs(g["j_intr"][v] - o["j_intr"][v]).max() < 1e-8 * np.abs(o["j_intr"]).max()
+            _, orep = oracle_lib.optimize(sp.problem, sp.init_state, opt)
+            assert rep.trace()[2] == orep.trace()[2]
+            assert np.allclose(rep.trace()[0], orep.trace()[0], rtol=1e-7)
+    finally:
+        lib.b200ba_debug_set_eval_budget(16)
