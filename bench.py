@@ -240,7 +240,8 @@ def run_b200(args):
     t0 = time.perf_counter()
     dev_ms = 0.0
     jac_ms, jac_n, launches = 0.0, 0, 0
-    phases = {"jacobian": 0.0, "accumulate": 0.0, "schur": 0.0, "factor": 0.0, "trial": 0.0, "update": 0.0, "allreduce": 0.0}
+    phases = {"jacobian": 0.0, "straggler": 0.0, "accumulate": 0.0, "schur": 0.0, "factor": 0.0, "trial": 0.0, "update": 0.0,
+              "allreduce": 0.0}
     costs = []
     for _ in range(K):
         opt.init_lambda = lam
@@ -251,7 +252,7 @@ def run_b200(args):
         jac_ms += t.jacobian_kernel_ms
         jac_n += t.jacobian_kernel_launches
         launches += t.kernel_launches
-        for k, v in (("jacobian", t.jacobian_kernel_ms), ("accumulate", t.accumulate_ms), ("schur", t.schur_ms),
+        for k, v in (("jacobian", t.jacobian_kernel_ms), ("straggler", t.straggler_ms), ("accumulate", t.accumulate_ms), ("schur", t.schur_ms),
                      ("factor", t.factor_ms), ("trial", t.trial_cost_ms), ("update", t.update_ms), ("allreduce", t.allreduce_ms)):
             phases[k] += v / K
         costs.append(rep.final_cost)

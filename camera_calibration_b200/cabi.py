@@ -165,6 +165,7 @@ class Timings(C.Structure):
         ("allreduce_ms", C.c_double),
         ("total_ms", C.c_double),
         ("kernel_launches", C.c_int64),
+        ("straggler_ms", C.c_double),
     ]
 
 

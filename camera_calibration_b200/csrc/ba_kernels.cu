@@ -118,6 +118,7 @@ __device__ __forceinline__ void store_col(const ObsOut& out, int64_t n_obs, int6
 // exactly what the sequential reference procedure yields.
 constexpr int kUnlimitedEvals = 1 << 30;
 static int g_main_eval_budget = 16;
+static cudaEvent_t g_main_done_event = nullptr;  // recorded between the main and the straggler pass
 void set_main_eval_budget(int b) { g_main_eval_budget = b < 1 ? 1 : b; }
 
 template <int MODEL, bool JAC, bool STRAGGLER>
@@ -444,12 +445,15 @@ static void launch_rj_model(const ProblemDev& pb, const Layout& L, const StateDe
   const unsigned blocks = static_cast<unsigned>((pb.n_obs + threads - 1) / threads);
   residual_jacobian_kernel<MODEL, JAC, MINB, false><<<blocks, threads, 0, s>>>(pb, L, st, lp, out, huber, list, count,
                                                                                g_main_eval_budget);
+  if (g_main_done_event) cudaEventRecord(g_main_done_event, s);
 }
 
 template <bool JAC>
 static void launch_rj(int model, const ProblemDev& pb, const Layout& L, const StateDev& st, double2* lp,
-                      const ObsOut& out, double huber, uint32_t* list, int* count, cudaStream_t s) {
+                      const ObsOut& out, double huber, uint32_t* list, int* count, cudaStream_t s,
+                      cudaEvent_t main_done) {
   if (pb.n_obs == 0) return;
+  g_main_done_event = main_done;
   cudaMemsetAsync(count, 0, sizeof(int), s);
   switch (model) {
     case B200BA_MODEL_CENTRAL_GENERIC:
@@ -478,11 +482,13 @@ static void launch_rj(int model, const ProblemDev& pb, const Layout& L, const St
 
 void launch_residual_jacobian(int uniform_model, bool jac, const ProblemDev& pb, const Layout& L,
                               const StateDev& st, double2* last_projection, const ObsOut& out, double huber,
-                              uint32_t* straggler_list, int* straggler_count, cudaStream_t s) {
+                              uint32_t* straggler_list, int* straggler_count, cudaStream_t s,
+                              cudaEvent_t main_done) {
   if (jac)
-    launch_rj<true>(uniform_model, pb, L, st, last_projection, out, huber, straggler_list, straggler_count, s);
+    launch_rj<true>(uniform_model, pb, L, st, last_projection, out, huber, straggler_list, straggler_count, s, main_done);
   else
-    launch_rj<false>(uniform_model, pb, L, st, last_projection, out, huber, straggler_list, straggler_count, s);
+    launch_rj<false>(uniform_model, pb, L, st, last_projection, out, huber, straggler_list, straggler_count, s, main_done);
+  g_main_done_event = nullptr;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -631,23 +637,8 @@ __global__ void __launch_bounds__(128)
       for (int b = 0; b < 6; ++b) atomicAdd(&Crow[rc + b], w * (jox[a] * jrx[b] + joy[a] * jry[b]));
     }
   }
-  // ---- intrinsics columns: B[p, intr], C[pose, intr] ------------------------------------------
-  if (!L.localize_only) {
-    const CamDev& c = pb.cams[cam];
-    const int cell = out.cell[o];
-    for (int k = 0; k < c.K; ++k) {
-      const double jx = out.jac[(2 * static_cast<int64_t>(L.jc_intr + k)) * n + o];
-      const double jy = out.jac[(2 * static_cast<int64_t>(L.jc_intr + k) + 1) * n + o];
-      const int col = L.d_intr + intr_col(c, cell, k);
-      const double wjx = w * jx, wjy = w * jy;
-#pragma unroll
-      for (int a = 0; a < 3; ++a)
-        atomicAdd(&sys.B[(3 * static_cast<int64_t>(pidx) + a) * L.nd + col], jpx[a] * wjx + jpy[a] * wjy);
-#pragma unroll
-      for (int a = 0; a < 6; ++a)
-        atomicAdd(&sys.C[static_cast<int64_t>(L.d_pose + 6 * iset + a) * L.nd + col], jox[a] * wjx + joy[a] * wjy);
-    }
-  }
+  // B[p, intrinsics] and C[pose, intrinsics] are accumulated by accumulate_cells_kernel, where a
+  // warp covers the 32 (80 / 12) intrinsics columns of ONE matrix row: sector-coalesced atomics.
 }
 
 void launch_accumulate_scatter(const ProblemDev& pb, const Layout& L, const ObsOut& out, const SystemDev& sys,
@@ -688,7 +679,11 @@ __global__ void __launch_bounds__(kCellThreads)
   double* sJx = smem;                         // [kCellTile][Emax]  sqrt(w) * J row x
   double* sJy = sJx + kCellTile * Emax;       // [kCellTile][Emax]
   double* sR = sJy + kCellTile * Emax;        // [kCellTile][2]     sqrt(w) * r
+  double* sPx = sR + 2 * kCellTile;           // [kCellTile][9]     sqrt(w) * J row x of [point 3 | pose 6]
+  double* sPy = sPx + 9 * kCellTile;          // [kCellTile][9]
   __shared__ uint32_t sKey[kCellTile];
+  __shared__ int sPoint[kCellTile];
+  __shared__ int sIset[kCellTile];
 
   double acc[MAXPAIRS];
   double accb = 0;
@@ -749,7 +744,37 @@ __global__ void __launch_bounds__(kCellThreads)
           sR[2 * t + 1] = sw * ry;
         }
       }
+      for (int idx = threadIdx.x; idx < run_n * 9; idx += kCellThreads) {
+        const int r9 = idx / run_n, t = idx - r9 * run_n;
+        const int64_t o = pos + t;
+        const double rx = out.residual[o], ry = out.residual[n + o];
+        const double sw = sqrt(huber_weight_sq(huber, rx * rx + ry * ry));
+        const int col = (r9 < 3) ? (L.jc_point + r9) : (L.jc_pose + (r9 - 3));
+        sPx[t * 9 + r9] = sw * out.jac[(2 * static_cast<int64_t>(col)) * n + o];
+        sPy[t * 9 + r9] = sw * out.jac[(2 * static_cast<int64_t>(col) + 1) * n + o];
+        if (r9 == 0) {
+          sPoint[t] = static_cast<int>(pb.obs_point[o]);
+          sIset[t] = static_cast<int>(pb.obs_imageset[o]);
+        }
+      }
       __syncthreads();
+      // [point | pose] rows x intrinsics columns of the run: B[p, intr], C[pose, intr]. Consecutive
+      // lanes take consecutive intrinsics columns of ONE matrix row, so a warp-wide FP64 RED touches
+      // a few contiguous sectors instead of 32 scattered ones.
+      if (!L.localize_only) {
+        const int K = c.K;
+        for (int idx = threadIdx.x; idx < run_n * 9 * K; idx += kCellThreads) {
+          const int kk = idx % K;
+          const int rest = idx / K;
+          const int r9 = rest % 9, t = rest / 9;
+          const double v = fma(sPx[t * 9 + r9], sJx[t * Emax + rigE + kk], sPy[t * 9 + r9] * sJy[t * Emax + rigE + kk]);
+          const int gc = L.d_intr + intr_col(c, cell, kk);
+          if (r9 < 3)
+            atomicAdd(&sys.B[(3 * static_cast<int64_t>(sPoint[t]) + r9) * L.nd + gc], v);
+          else
+            atomicAdd(&sys.C[static_cast<int64_t>(L.d_pose + 6 * sIset[t] + (r9 - 3)) * L.nd + gc], v);
+        }
+      }
 #pragma unroll
       for (int q = 0; q < MAXPAIRS; ++q) {
         if (threadIdx.x + q * kCellThreads < npairs) {
@@ -791,7 +816,7 @@ void launch_accumulate_cells(const ProblemDev& pb, const Layout& L, const ObsOut
   if (Emax == 0) return;
   const int npairs = Emax * (Emax + 1) / 2;
   const int per_thread = (npairs + kCellThreads - 1) / kCellThreads;
-  const size_t smem = (2 * static_cast<size_t>(kCellTile) * Emax + 2 * kCellTile) * sizeof(double);
+  const size_t smem = (2 * static_cast<size_t>(kCellTile) * Emax + 2 * kCellTile + 18 * kCellTile) * sizeof(double);
   const unsigned blocks = static_cast<unsigned>((pb.n_obs + kCellChunk - 1) / kCellChunk);
 #define B200BA_LAUNCH_CELLS(MP)                                                                              \
   do {                                                                                                       \

@@ -9,7 +9,8 @@ void launch_prepare_state(const ProblemDev& pb, const Layout& L, const StateDev&
 // uniform_model: the model type shared by all cameras, or -1 for a mixed rig (runtime switch)
 void launch_residual_jacobian(int uniform_model, bool jac, const ProblemDev& pb, const Layout& L,
                               const StateDev& st, double2* last_projection, const ObsOut& out, double huber,
-                              uint32_t* straggler_list, int* straggler_count, cudaStream_t s);
+                              uint32_t* straggler_list, int* straggler_count, cudaStream_t s,
+                              cudaEvent_t main_done = nullptr);
 // evaluation budget of the main pass before an observation is deferred to the straggler pass
 void set_main_eval_budget(int budget);
 void launch_accumulate_scatter(const ProblemDev& pb, const Layout& L, const ObsOut& out, const SystemDev& sys,

@@ -226,7 +226,7 @@ B200BA_API int b200ba_comm_init(b200ba_handle* h, const uint8_t id[B200BA_NCCL_U
 /* ---- instrumentation ------------------------------------------------------ */
 /* Device-side timings (CUDA events on the handle's stream) of the last b200ba_optimize. */
 typedef struct b200ba_timings {
-  double jacobian_kernel_ms; /* sum over launches of the residual+Jacobian kernel */
+  double jacobian_kernel_ms; /* sum over launches of the MAIN pass of the residual+Jacobian kernel */
   int32_t jacobian_kernel_launches;
   double accumulate_ms;      /* JtJ / Jtr accumulation kernels */
   double schur_ms;           /* D^-1, D^-1 B, B^T D^-1 B contraction */
@@ -236,6 +236,8 @@ typedef struct b200ba_timings {
   double allreduce_ms;
   double total_ms;
   int64_t kernel_launches;   /* kernels of this library launched */
+  double straggler_ms;       /* straggler passes of the residual/Jacobian kernel (observations whose
+                                projection needs more than the main pass's evaluation budget) */
 } b200ba_timings;
 B200BA_API int b200ba_get_timings(const b200ba_handle* h, b200ba_timings* t);
 
