@@ -81,6 +81,8 @@ enum Phase { PH_JAC = 0, PH_ACC, PH_SCHUR, PH_FACTOR, PH_TRIAL, PH_UPDATE, PH_AL
 struct b200ba_handle {
   int device = 0;
   cudaStream_t stream = nullptr;
+  cudaStream_t side_stream = nullptr;  // straggler pass of the Jacobian kernel, overlapped with accumulation
+  cudaEvent_t straggler_done = nullptr;
   cublasHandle_t cublas = nullptr;
   cusolverDnHandle_t cusolver = nullptr;
   std::string error;
@@ -380,19 +382,29 @@ int all_reduce(b200ba_handle* h, double* buf, size_t count) {
 }
 
 // One residual pass on state `which` into `out`; jac selects Compute<true>/<false>.
-int evaluate_state(b200ba_handle* h, int which, bool jac, const ObsOut& out, double huber, int phase) {
+// overlap_stragglers: launch the straggler pass on the side stream and return without joining
+// (the caller joins with join_stragglers() after independent work).
+int evaluate_state(b200ba_handle* h, int which, bool jac, const ObsOut& out, double huber, int phase,
+                   bool overlap_stragglers = false) {
   launch_prepare_state(h->pb, h->L, h->st[which], h->n_control_total, h->stream);
   h->timings.kernel_launches += 1;
   {
-    // [a .. mid]: main pass (what `roofline` is quoted on); [mid .. b]: straggler pass
-    cudaEvent_t a = get_event(h), mid = get_event(h), b = get_event(h);
+    // [a .. mid]: main pass (what `roofline` is quoted on)
+    cudaEvent_t a = get_event(h), mid = get_event(h);
     cudaEventRecord(a, h->stream);
     launch_residual_jacobian(h->uniform_model, jac, h->pb, h->L, h->st[which], h->d_last_projection, out, huber,
                              h->d_straggler_list, h->d_straggler_count, h->stream, mid);
     if (h->n_obs == 0) cudaEventRecord(mid, h->stream);
-    cudaEventRecord(b, h->stream);
     h->pending.push_back({phase, a, mid, true});
-    h->pending.push_back({PH_STRAGGLER, mid, b, false});
+    cudaStream_t ss = overlap_stragglers ? h->side_stream : h->stream;
+    if (overlap_stragglers) CUDA_TRY(h, cudaStreamWaitEvent(h->side_stream, mid, 0));
+    cudaEvent_t s0 = get_event(h), s1 = get_event(h);
+    cudaEventRecord(s0, ss);
+    launch_straggler_pass(h->uniform_model, jac, h->pb, h->L, h->st[which], h->d_last_projection, out, huber,
+                          h->d_straggler_list, h->d_straggler_count, ss);
+    cudaEventRecord(s1, ss);
+    h->pending.push_back({PH_STRAGGLER, s0, s1, true});
+    h->straggler_done = s1;  // stays valid until the next resolve_timings()
     h->timings.kernel_launches += 2 * (h->n_obs > 0);
   }
   CUDA_TRY(h, cudaGetLastError());
@@ -401,7 +413,9 @@ int evaluate_state(b200ba_handle* h, int which, bool jac, const ObsOut& out, dou
 
 // Hot loop 1: H, b at the current state (LV/lm_optimizer.h:706-716).
 int build_system(b200ba_handle* h, double huber, double* cost, double* n_valid) {
-  if (evaluate_state(h, h->cur, true, h->out, huber, PH_JAC)) return 1;
+  // The straggler pass (a handful of observations burning the reference's full iteration
+  // allowance) runs on the side stream underneath the accumulation of everything else.
+  if (evaluate_state(h, h->cur, true, h->out, huber, PH_JAC, /*overlap_stragglers=*/true)) return 1;
   {
     ScopedPhase ph(h, PH_ACC);
     CUDA_TRY(h, cudaMemsetAsync(h->sys.base, 0, h->sys.total * sizeof(double), h->stream));
@@ -410,7 +424,10 @@ int build_system(b200ba_handle* h, double huber, double* cost, double* n_valid) 
       launch_accumulate_cells(h->pb, h->L, h->out, h->sys, huber, h->stream);
       h->timings.kernel_launches += 1;
     }
-    h->timings.kernel_launches += 1;
+    // join, then fold in the stragglers that succeeded after all
+    CUDA_TRY(h, cudaStreamWaitEvent(h->stream, h->straggler_done, 0));
+    launch_accumulate_list(h->pb, h->L, h->out, h->sys, huber, h->d_straggler_list, h->d_straggler_count, h->stream);
+    h->timings.kernel_launches += 2;
     launch_cost_reduce(h->n_obs, h->out.cost, nullptr, h->out.residual, h->d_partial, h->sys.scalars, h->stream);
     // trace(H) of this rank's partial system, for the lambda initialisation (lm_optimizer.h:766-781)
     launch_trace(h->L.n_points, h->sys.Dblk, h->L.nd, h->sys.C, h->sys.scalars + 8, h->stream);
@@ -604,6 +621,7 @@ int b200ba_create(const b200ba_problem* p, int device, b200ba_handle** out) {
     if (h->cublas) cublasDestroy(h->cublas);
     if (h->cusolver) cusolverDnDestroy(h->cusolver);
     if (h->stream) cudaStreamDestroy(h->stream);
+    if (h->side_stream) cudaStreamDestroy(h->side_stream);
     delete h;
     return rc;
   };
@@ -622,6 +640,7 @@ int b200ba_create(const b200ba_problem* p, int device, b200ba_handle** out) {
   };
   TRYC(cuda_ok(cudaSetDevice(device), "cudaSetDevice"));
   TRYC(cuda_ok(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking), "cudaStreamCreate"));
+  TRYC(cuda_ok(cudaStreamCreateWithFlags(&h->side_stream, cudaStreamNonBlocking), "cudaStreamCreate"));
   if (cublasCreate(&h->cublas) != CUBLAS_STATUS_SUCCESS) {
     h->error = "cublasCreate failed";
     return fail(1);
@@ -735,6 +754,7 @@ void b200ba_destroy(b200ba_handle* h) {
   if (h->cublas) cublasDestroy(h->cublas);
   if (h->cusolver) cusolverDnDestroy(h->cusolver);
   if (h->stream) cudaStreamDestroy(h->stream);
+  if (h->side_stream) cudaStreamDestroy(h->side_stream);
   delete h;
 }
 
@@ -965,7 +985,7 @@ int b200ba_get_jacobians(b200ba_handle* h, double* j_point, double* j_pose, doub
   auto J = [&](int col, int r, int64_t i) { return jac[(2 * static_cast<size_t>(col) + r) * n + i]; };
   for (int64_t i = 0; i < n; ++i) {
     const int64_t o = h->perm[i];  // position i on the device holds the caller's observation o
-    const bool v = has[i] != 0;
+    const bool v = has[i] == 1 || has[i] == 3;  // valid, or a late success of the straggler pass
     for (int r = 0; r < 2; ++r) {
       if (j_point) for (int j = 0; j < 3; ++j) j_point[(o * 2 + r) * 3 + j] = v ? J(L.jc_point + j, r, i) : 0.0;
       if (j_pose) for (int j = 0; j < 6; ++j) j_pose[(o * 2 + r) * 6 + j] = v ? J(L.jc_pose + j, r, i) : 0.0;

@@ -21,6 +21,8 @@
 
 namespace b200ba {
 
+__device__ __forceinline__ int intr_col(const CamDev& c, int cell, int k);
+
 // ------------------------------------------------------------------------------------------
 // prepare_state: composed poses + tangent frames
 // ------------------------------------------------------------------------------------------
@@ -117,6 +119,8 @@ __device__ __forceinline__ void store_col(const ObsOut& out, int64_t n_obs, int6
 // attempt, lane 1 speculatively runs the reference's retry from the image centre; the result is
 // exactly what the sequential reference procedure yields.
 constexpr int kUnlimitedEvals = 1 << 30;
+// ObsOut::has_jac states
+constexpr uint8_t kJacNone = 0, kJacValid = 1, kJacPending = 2, kJacLate = 3;
 static int g_main_eval_budget = 16;
 static cudaEvent_t g_main_done_event = nullptr;  // recorded between the main and the straggler pass
 void set_main_eval_budget(int b) { g_main_eval_budget = b < 1 ? 1 : b; }
@@ -189,7 +193,8 @@ __device__ __forceinline__ void process_observation(const ProblemDev& pb, const 
     if (status == kProjUnfinished) {
       const int slot = atomicAdd(straggler_count, 1);
       straggler_list[slot] = static_cast<uint32_t>(o);
-      return;  // every output of this observation is written by the straggler pass
+      if (JAC) out.has_jac[o] = kJacPending;
+      return;  // every other output of this observation is written by the straggler pass
     }
     ok = status == kProjOk;
   } else {
@@ -332,7 +337,9 @@ __device__ __forceinline__ void process_observation(const ProblemDev& pb, const 
     }
   }
   out.cell[o] = cell;
-  out.has_jac[o] = 1;
+  // a late (straggler-pass) success is flagged separately: the main accumulation kernels may be
+  // running concurrently and must not pick it up; accumulate_list_kernel folds it in afterwards
+  out.has_jac[o] = STRAGGLER ? kJacLate : kJacValid;
 
   // ---- chain rule to pose / rig / point (joint_optimization.cc:378-438) ----------------------
   // For the left update q <- (1, delta) q: d(R(q) v)/d delta = -2 [R v]_x.
@@ -462,19 +469,34 @@ static void launch_rj(int model, const ProblemDev& pb, const Layout& L, const St
         case 3: launch_rj_model<B200BA_MODEL_CENTRAL_GENERIC, JAC, 3>(pb, L, st, lp, out, huber, list, count, s); break;
         default: launch_rj_model<B200BA_MODEL_CENTRAL_GENERIC, JAC, 4>(pb, L, st, lp, out, huber, list, count, s);
       }
-      residual_jacobian_kernel<B200BA_MODEL_CENTRAL_GENERIC, JAC, 2, true>
-          <<<kStragglerBlocks, kStragglerThreads, 0, s>>>(pb, L, st, lp, out, huber, list, count, 0);
       break;
     case B200BA_MODEL_NONCENTRAL_GENERIC:
       launch_rj_model<B200BA_MODEL_NONCENTRAL_GENERIC, JAC, 3>(pb, L, st, lp, out, huber, list, count, s);
-      residual_jacobian_kernel<B200BA_MODEL_NONCENTRAL_GENERIC, JAC, 2, true>
-          <<<kStragglerBlocks, kStragglerThreads, 0, s>>>(pb, L, st, lp, out, huber, list, count, 0);
       break;
     case B200BA_MODEL_CENTRAL_OPENCV:
       launch_rj_model<B200BA_MODEL_CENTRAL_OPENCV, JAC, 4>(pb, L, st, lp, out, huber, list, count, s);
       break;
     default:
       launch_rj_model<-1, JAC, 3>(pb, L, st, lp, out, huber, list, count, s);
+  }
+}
+
+template <bool JAC>
+static void launch_stragglers(int model, const ProblemDev& pb, const Layout& L, const StateDev& st, double2* lp,
+                              const ObsOut& out, double huber, uint32_t* list, int* count, cudaStream_t s) {
+  if (pb.n_obs == 0) return;
+  switch (model) {
+    case B200BA_MODEL_CENTRAL_GENERIC:
+      residual_jacobian_kernel<B200BA_MODEL_CENTRAL_GENERIC, JAC, 2, true>
+          <<<kStragglerBlocks, kStragglerThreads, 0, s>>>(pb, L, st, lp, out, huber, list, count, 0);
+      break;
+    case B200BA_MODEL_NONCENTRAL_GENERIC:
+      residual_jacobian_kernel<B200BA_MODEL_NONCENTRAL_GENERIC, JAC, 2, true>
+          <<<kStragglerBlocks, kStragglerThreads, 0, s>>>(pb, L, st, lp, out, huber, list, count, 0);
+      break;
+    case B200BA_MODEL_CENTRAL_OPENCV:
+      break;  // closed-form projection: the main pass never defers
+    default:
       residual_jacobian_kernel<-1, JAC, 2, true><<<kStragglerBlocks, kStragglerThreads, 0, s>>>(pb, L, st, lp, out, huber,
                                                                                              list, count, 0);
   }
@@ -489,6 +511,85 @@ void launch_residual_jacobian(int uniform_model, bool jac, const ProblemDev& pb,
   else
     launch_rj<false>(uniform_model, pb, L, st, last_projection, out, huber, straggler_list, straggler_count, s, main_done);
   g_main_done_event = nullptr;
+}
+
+void launch_straggler_pass(int uniform_model, bool jac, const ProblemDev& pb, const Layout& L, const StateDev& st,
+                           double2* last_projection, const ObsOut& out, double huber, uint32_t* straggler_list,
+                           int* straggler_count, cudaStream_t s) {
+  if (jac)
+    launch_stragglers<true>(uniform_model, pb, L, st, last_projection, out, huber, straggler_list, straggler_count, s);
+  else
+    launch_stragglers<false>(uniform_model, pb, L, st, last_projection, out, huber, straggler_list, straggler_count, s);
+}
+
+// Folds the late successes of the straggler pass into the normal equations: one warp per listed
+// observation walks the upper triangle of its column set [point 3 | pose 6 | rig 6 | intrinsics K]
+// with FP64 atomics (LV/lm_optimizer_jtj_accumulator_base.h:287-412). The list is short in the
+// steady state; generality over speed.
+__global__ void accumulate_list_kernel(ProblemDev pb, Layout L, ObsOut out, SystemDev sys, double huber,
+                                       const uint32_t* __restrict__ list, const int* __restrict__ count) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x) >> 5;
+  const int64_t n_warps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
+  const int64_t n = pb.n_obs;
+  for (int64_t li = warp; li < *count; li += n_warps) {
+    const int64_t o = list[li];
+    if (out.has_jac[o] != kJacLate) continue;
+    const int cam = static_cast<int>(pb.obs_camera[o]);
+    const int iset = static_cast<int>(pb.obs_imageset[o]);
+    const int pidx = static_cast<int>(pb.obs_point[o]);
+    const CamDev& c = pb.cams[cam];
+    const int cell = out.cell[o];
+    const double rx = out.residual[o], ry = out.residual[n + o];
+    const double w = huber_weight_sq(huber, rx * rx + ry * ry);
+    const int K = L.localize_only ? 0 : c.K;
+    const int nc = 9 + (L.rig_in_state ? 6 : 0) + K;
+    // column e of this observation: Jacobian storage column and global unknown index
+    auto jcol = [&](int e) -> int {
+      if (e < 9) return e;  // point 0-2, pose 3-8
+      if (L.rig_in_state && e < 15) return L.jc_rig + (e - 9);
+      return L.jc_intr + (e - (L.rig_in_state ? 15 : 9));
+    };
+    auto gidx = [&](int e) -> int {  // index in [points | dense]
+      if (e < 3) return 3 * pidx + e;
+      if (e < 9) return L.nbd + L.d_pose + 6 * iset + (e - 3);
+      if (L.rig_in_state && e < 15) return L.nbd + L.d_rig + 6 * cam + (e - 9);
+      return L.nbd + L.d_intr + intr_col(c, cell, e - (L.rig_in_state ? 15 : 9));
+    };
+    for (int p = lane; p < nc * nc; p += 32) {
+      const int i = p / nc, j = p - i * nc;
+      if (j < i) continue;
+      const int ci = jcol(i), cj = jcol(j);
+      const double v = w * (out.jac[(2 * static_cast<int64_t>(ci)) * n + o] * out.jac[(2 * static_cast<int64_t>(cj)) * n + o] +
+                            out.jac[(2 * static_cast<int64_t>(ci) + 1) * n + o] * out.jac[(2 * static_cast<int64_t>(cj) + 1) * n + o]);
+      const int gi = gidx(i), gj = gidx(j);
+      if (gj < L.nbd) {  // point x point: 3x3 upper block
+        const int a = gi - 3 * pidx, b = gj - 3 * pidx;
+        const int e = (a == 0) ? b : (a == 1 ? 2 + b : 5);
+        atomicAdd(&sys.Dblk[6 * static_cast<int64_t>(pidx) + e], v);
+      } else if (gi < L.nbd) {
+        atomicAdd(&sys.B[static_cast<int64_t>(gi) * L.nd + (gj - L.nbd)], v);
+      } else {
+        atomicAdd(&sys.C[static_cast<int64_t>(gi - L.nbd) * L.nd + (gj - L.nbd)], v);
+      }
+    }
+    for (int i = lane; i < nc; i += 32) {
+      const int ci = jcol(i);
+      const double v = w * (out.jac[(2 * static_cast<int64_t>(ci)) * n + o] * rx + out.jac[(2 * static_cast<int64_t>(ci) + 1) * n + o] * ry);
+      const int gi = gidx(i);
+      if (gi < L.nbd)
+        atomicAdd(&sys.bp[gi], v);
+      else
+        atomicAdd(&sys.bd[gi - L.nbd], v);
+    }
+    __syncwarp();
+    if (lane == 0) out.has_jac[o] = kJacValid;
+  }
+}
+void launch_accumulate_list(const ProblemDev& pb, const Layout& L, const ObsOut& out, const SystemDev& sys,
+                            double huber, const uint32_t* list, const int* count, cudaStream_t s) {
+  if (pb.n_obs == 0) return;
+  accumulate_list_kernel<<<296, 128, 0, s>>>(pb, L, out, sys, huber, list, count);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -524,7 +625,7 @@ __global__ void __launch_bounds__(128)
     accumulate_scatter_kernel(ProblemDev pb, Layout L, ObsOut out, SystemDev sys, double huber) {
   const int64_t o = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
   const int64_t n = pb.n_obs;
-  const bool active = (o < n) && out.has_jac[o];
+  const bool active = (o < n) && out.has_jac[o] == kJacValid;
   int iset = -1;
   double w = 0, rx = 0, ry = 0;
   double jpx[3], jpy[3], jox[6], joy[6];
@@ -663,7 +764,7 @@ constexpr int kCellThreads = 256;
 constexpr uint32_t kInvalidKey = 0xffffffffu;
 
 __device__ __forceinline__ uint32_t cell_key(const ProblemDev& pb, const ObsOut& out, int64_t pos) {
-  if (!out.has_jac[pos]) return kInvalidKey;
+  if (out.has_jac[pos] != kJacValid) return kInvalidKey;
   return (pb.obs_camera[pos] << 24) | static_cast<uint32_t>(out.cell[pos]);  // <= 8 cameras, < 2^24 cells
 }
 

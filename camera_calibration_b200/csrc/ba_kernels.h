@@ -11,6 +11,11 @@ void launch_residual_jacobian(int uniform_model, bool jac, const ProblemDev& pb,
                               const StateDev& st, double2* last_projection, const ObsOut& out, double huber,
                               uint32_t* straggler_list, int* straggler_count, cudaStream_t s,
                               cudaEvent_t main_done = nullptr);
+void launch_straggler_pass(int uniform_model, bool jac, const ProblemDev& pb, const Layout& L, const StateDev& st,
+                           double2* last_projection, const ObsOut& out, double huber, uint32_t* straggler_list,
+                           int* straggler_count, cudaStream_t s);
+void launch_accumulate_list(const ProblemDev& pb, const Layout& L, const ObsOut& out, const SystemDev& sys,
+                            double huber, const uint32_t* list, const int* count, cudaStream_t s);
 // evaluation budget of the main pass before an observation is deferred to the straggler pass
 void set_main_eval_budget(int budget);
 void launch_accumulate_scatter(const ProblemDev& pb, const Layout& L, const ObsOut& out, const SystemDev& sys,
