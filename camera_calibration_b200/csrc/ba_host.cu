@@ -118,6 +118,8 @@ struct b200ba_handle {
   // Static cell-major processing order: device position -> index in the caller's (reference)
   // observation order. Computed once at create time from the cell of the measured pixel.
   std::vector<uint32_t> perm;
+  uint32_t* d_perm = nullptr;
+  double2* d_lp_stage = nullptr;  // last_projection in the caller's order (H2D / D2H staging)
   uint32_t* d_straggler_list = nullptr;  // observations deferred by the main pass of the Jacobian kernel
   int* d_straggler_count = nullptr;
   double *d_partial = nullptr, *d_scal = nullptr;
@@ -539,7 +541,7 @@ void free_handle_buffers(b200ba_handle* h) {
   F(h->out.residual); F(h->out.cost); F(h->out.jac); F(h->out.cell); F(h->out.has_jac); F(h->out.evals);
   F(h->out_trial.residual); F(h->out_trial.cost);
   F(h->sys.base); F(h->d_W); F(h->d_S); F(h->d_Linv); F(h->d_v); F(h->d_y); F(h->d_x); F(h->d_potrf_work);
-  F(h->d_info); F(h->d_fail); F(h->d_straggler_list); F(h->d_straggler_count);
+  F(h->d_info); F(h->d_fail); F(h->d_straggler_list); F(h->d_straggler_count); F(h->d_perm); F(h->d_lp_stage);
   F(h->d_partial); F(h->d_scal);
   if (h->h_scal) cudaFreeHost(h->h_scal);
   if (h->h_flags) cudaFreeHost(h->h_flags);
@@ -714,7 +716,10 @@ int b200ba_create(const b200ba_problem* p, int device, b200ba_handle** out) {
       txy[2 * i + 1] = p->obs_xy[2 * h->perm[i] + 1];
     }
     TRYC(cuda_ok(cudaMemcpy(h->d_obs_xy, txy.data(), n * sizeof(float2), cudaMemcpyHostToDevice), "H2D"));
+    TRYC(dev_alloc(h, &h->d_perm, n));
+    TRYC(cuda_ok(cudaMemcpy(h->d_perm, h->perm.data(), n * sizeof(uint32_t), cudaMemcpyHostToDevice), "H2D"));
   }
+  TRYC(dev_alloc(h, &h->d_lp_stage, n));
   h->pb.n_obs = n;
   h->pb.obs_imageset = h->d_obs_imageset;
   h->pb.obs_camera = h->d_obs_camera;
@@ -772,14 +777,10 @@ int b200ba_set_state(b200ba_handle* h, const b200ba_state* s) {
   for (int c = 0; c < h->n_cameras; ++c)
     CUDA_TRY(h, cudaMemcpyAsync(d.intrinsics + h->pb.cams[c].intr_off, s->intrinsics[c],
                                 sizeof(double) * intrinsics_size(h->cams_host[c]), cudaMemcpyHostToDevice, h->stream));
-  std::vector<double> lp_perm;
   if (s->last_projection) {
-    lp_perm.resize(2 * h->n_obs);
-    for (int64_t i = 0; i < h->n_obs; ++i) {
-      lp_perm[2 * i] = s->last_projection[2 * static_cast<int64_t>(h->perm[i])];
-      lp_perm[2 * i + 1] = s->last_projection[2 * static_cast<int64_t>(h->perm[i]) + 1];
-    }
-    CUDA_TRY(h, cudaMemcpyAsync(h->d_last_projection, lp_perm.data(), 2 * sizeof(double) * h->n_obs, cudaMemcpyHostToDevice, h->stream));
+    // caller's order -> device staging -> cell-major order (gather on the device)
+    CUDA_TRY(h, cudaMemcpyAsync(h->d_lp_stage, s->last_projection, 2 * sizeof(double) * h->n_obs, cudaMemcpyHostToDevice, h->stream));
+    launch_permute_double2(h->n_obs, h->d_perm, h->d_lp_stage, h->d_last_projection, /*scatter=*/false, h->stream);
   } else
     CUDA_TRY(h, cudaMemsetAsync(h->d_last_projection, 0, std::max<int64_t>(1, h->n_obs) * sizeof(double2), h->stream));
   CUDA_TRY(h, cudaStreamSynchronize(h->stream));
@@ -802,17 +803,11 @@ int b200ba_get_state(b200ba_handle* h, b200ba_state* s) {
     for (int c = 0; c < h->n_cameras; ++c)
       CUDA_TRY(h, cudaMemcpyAsync(s->intrinsics[c], d.intrinsics + h->pb.cams[c].intr_off,
                                   sizeof(double) * intrinsics_size(h->cams_host[c]), cudaMemcpyDeviceToHost, h->stream));
-  std::vector<double> lp_perm;
   if (s->last_projection) {
-    lp_perm.resize(2 * h->n_obs);
-    CUDA_TRY(h, cudaMemcpyAsync(lp_perm.data(), h->d_last_projection, 2 * sizeof(double) * h->n_obs, cudaMemcpyDeviceToHost, h->stream));
+    launch_permute_double2(h->n_obs, h->d_perm, h->d_last_projection, h->d_lp_stage, /*scatter=*/true, h->stream);
+    CUDA_TRY(h, cudaMemcpyAsync(s->last_projection, h->d_lp_stage, 2 * sizeof(double) * h->n_obs, cudaMemcpyDeviceToHost, h->stream));
   }
   CUDA_TRY(h, cudaStreamSynchronize(h->stream));
-  if (s->last_projection)
-    for (int64_t i = 0; i < h->n_obs; ++i) {
-      s->last_projection[2 * static_cast<int64_t>(h->perm[i])] = lp_perm[2 * i];
-      s->last_projection[2 * static_cast<int64_t>(h->perm[i]) + 1] = lp_perm[2 * i + 1];
-    }
   return 0;
 }
 

@@ -1365,6 +1365,23 @@ void launch_generic_block_inverse(int bs, int nb, int nd, const double* D, const
   generic_block_inverse_kernel<<<nb, 128, 0, s>>>(bs, nb, nd, D, B, b1, DinvB, Dinvb);
 }
 
+// dst[i] = src[perm[i]] (gather) or dst[perm[i]] = src[i] (scatter) for double2 payloads: moves
+// last_projection between the caller's observation order and the device's cell-major order.
+__global__ void permute_double2_kernel(int64_t n, const uint32_t* __restrict__ perm, const double2* __restrict__ src,
+                                       double2* __restrict__ dst, int scatter) {
+  const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (i >= n) return;
+  if (scatter)
+    dst[perm[i]] = src[i];
+  else
+    dst[i] = src[perm[i]];
+}
+void launch_permute_double2(int64_t n, const uint32_t* perm, const double2* src, double2* dst, bool scatter,
+                            cudaStream_t s) {
+  if (n == 0) return;
+  permute_double2_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, s>>>(n, perm, src, dst, scatter ? 1 : 0);
+}
+
 // mirror the valid (row <= col) triangle of a row-major square matrix into the other one
 __global__ void symmetrize_kernel(int n, double* M) {
   const int j = blockIdx.x * blockDim.x + threadIdx.x;

@@ -40,5 +40,7 @@ void launch_unproject_pixels(const CamDev& c, const double* intr, int64_t n, con
 void launch_generic_block_inverse(int bs, int nb, int nd, const double* D, const double* B, const double* b1,
                                   double* DinvB, double* Dinvb, cudaStream_t s);
 void launch_symmetrize(int n, double* M, cudaStream_t s);
+void launch_permute_double2(int64_t n, const uint32_t* perm, const double2* src, double2* dst, bool scatter,
+                            cudaStream_t s);
 
 }  // namespace b200ba
