@@ -32,22 +32,28 @@ struct CamDev {
   int upd_count;      // update_parameter_count()
 };
 
-// Variable layout of JointOptimizationState (joint_optimization.cc:97-170) and of the
-// block / dense split of H (lm_optimizer.h:657-685) for eliminate_points = true.
+// Variable layout of JointOptimizationState (joint_optimization.cc:49-59,97-170) and of the
+// block-diagonal / dense split of H (lm_optimizer.h:657-685):
+//   eliminate_points:  [points 3P | rig_tr_global 6N | camera_tr_rig 6C (iff C > 1) | intrinsics]
+//                      block part = points (3x3 blocks)
+//   otherwise:         [rig_tr_global 6N | camera_tr_rig 6C (iff C > 1) | points 3P | intrinsics]
+//                      block part = imageset poses (6x6 blocks)
+// g_* are offsets in that global ordering; a dense index is (global - nbd).
 struct Layout {
   int n_points, n_imagesets, n_cameras;
   int rig_in_state;     // n_cameras > 1
   int localize_only;
+  int eliminate_points;
   int dof;              // all unknowns
-  int nbd;              // 3 * n_points (block-diagonal part)
+  int bs;               // Schur block size: 3 (points) or 6 (poses)
+  int nblocks;          // number of blocks: P or N
+  int dsz;              // packed upper-triangle size of a block: bs (bs + 1) / 2
+  int nbd;              // bs * nblocks (block-diagonal part)
   int nd;               // dense part
-  // offsets inside the dense part
-  int d_pose;           // 0
-  int d_rig;            // 6 * n_imagesets
-  int d_intr;           // 6 * n_imagesets + (rig ? 6 * n_cameras : 0)
+  int g_point, g_pose, g_rig, g_intr;  // global offsets of the variable groups
   int n_jcols;          // Jacobian columns stored per observation: 3 + 6 + (rig ? 6 : 0) + Kmax
   int Kmax;             // max IntrinsicsJacobianSize over cameras (0 when localize_only)
-  int jc_point, jc_pose, jc_rig, jc_intr;  // first column of each part
+  int jc_point, jc_pose, jc_rig, jc_intr;  // first storage column of each part
 };
 
 struct ProblemDev {
@@ -85,9 +91,9 @@ struct ObsOut {
 struct SystemDev {
   double* base;     // the single allocation
   int64_t total;    // doubles
-  double* Dblk;     // [n_points][6]   upper 3x3: 00 01 02 11 12 22
-  double* bp;       // [3 * n_points]
-  double* B;        // [3 * n_points][nd]   row-major
+  double* Dblk;     // [nblocks][dsz]  packed upper triangle of each bs x bs block, row-major
+  double* bp;       // [nbd]
+  double* B;        // [nbd][nd]   row-major
   double* C;        // [nd][nd] row-major, row <= col valid (== column-major lower)
   double* bd;       // [nd]
   double* scalars;  // [8]: cost, n_valid, ...

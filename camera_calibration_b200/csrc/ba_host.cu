@@ -277,21 +277,19 @@ void resolve_timings(b200ba_handle* h) {
 
 // ---- layout / buffers ----------------------------------------------------------------------
 int make_layout(b200ba_handle* h, const b200ba_options* opt) {
-  if (!opt->eliminate_points) {
-    h->error = "eliminate_points=false (6x6 pose-block elimination, SURVEY.md 8f-3) is not implemented on the GPU path";
-    return 2;
-  }
   if (opt->regularization_weight != 0) {
     // the reference logs an error and ignores it (joint_optimization.cc:299-305)
     h->error = "regularization_weight must be 0 (disabled in the reference)";
     return 2;
   }
   Layout L{};
+  memset(&L, 0, sizeof(L));
   L.n_points = h->n_points;
   L.n_imagesets = h->n_imagesets;
   L.n_cameras = h->n_cameras;
   L.rig_in_state = h->n_cameras > 1;
   L.localize_only = opt->localize_only ? 1 : 0;
+  L.eliminate_points = opt->eliminate_points ? 1 : 0;
   int n_intr = 0, kmax = 0;
   for (int c = 0; c < h->n_cameras; ++c) {
     n_intr += update_parameter_count(h->cams_host[c]);
@@ -301,12 +299,27 @@ int make_layout(b200ba_handle* h, const b200ba_options* opt) {
     n_intr = 0;
     kmax = 0;
   }
-  L.nbd = 3 * h->n_points;
-  L.d_pose = 0;
-  L.d_rig = 6 * h->n_imagesets;
-  L.d_intr = L.d_rig + (L.rig_in_state ? 6 * h->n_cameras : 0);
-  L.nd = L.d_intr + n_intr;
-  L.dof = L.nbd + L.nd;
+  const int rig_dof = L.rig_in_state ? 6 * h->n_cameras : 0;
+  // JointOptimizationState offsets (joint_optimization.cc:142-170)
+  if (L.eliminate_points) {
+    L.bs = 3;
+    L.nblocks = h->n_points;
+    L.g_point = 0;
+    L.g_pose = 3 * h->n_points;
+    L.g_rig = L.g_pose + 6 * h->n_imagesets;
+    L.g_intr = L.g_rig + rig_dof;
+  } else {
+    L.bs = 6;
+    L.nblocks = h->n_imagesets;
+    L.g_pose = 0;
+    L.g_rig = 6 * h->n_imagesets;
+    L.g_point = L.g_rig + rig_dof;
+    L.g_intr = L.g_point + 3 * h->n_points;
+  }
+  L.dsz = L.bs * (L.bs + 1) / 2;
+  L.nbd = L.bs * L.nblocks;
+  L.dof = 3 * h->n_points + 6 * h->n_imagesets + rig_dof + n_intr;
+  L.nd = L.dof - L.nbd;
   L.Kmax = kmax;
   L.jc_point = 0;
   L.jc_pose = 3;
@@ -338,7 +351,7 @@ int make_layout(b200ba_handle* h, const b200ba_options* opt) {
   // with several ranks each rank folds its partial C into its partial Schur complement, and the
   // all-reduce of S makes it global (see solve_system).
   const int64_t oD = 0;
-  const int64_t obp = oD + align32(6LL * L.n_points);
+  const int64_t obp = oD + align32(static_cast<int64_t>(L.dsz) * L.nblocks);
   const int64_t oB = obp + align32(L.nbd);
   const int64_t obd = oB + align32(static_cast<int64_t>(L.nbd) * L.nd);
   const int64_t osc = obd + align32(L.nd);
@@ -354,7 +367,7 @@ int make_layout(b200ba_handle* h, const b200ba_options* opt) {
   s.scalars = s.base + osc;
   if (dev_alloc(h, &h->d_W, static_cast<size_t>(L.nbd) * L.nd)) return 1;
   if (dev_alloc(h, &h->d_S, static_cast<size_t>(L.nd) * L.nd + L.nd)) return 1;  // + partial rhs tail
-  if (dev_alloc(h, &h->d_Linv, 6 * static_cast<size_t>(L.n_points))) return 1;
+  if (dev_alloc(h, &h->d_Linv, static_cast<size_t>(L.dsz) * L.nblocks)) return 1;
   if (dev_alloc(h, &h->d_v, L.nbd)) return 1;
   if (dev_alloc(h, &h->d_y, L.nbd)) return 1;
   if (dev_alloc(h, &h->d_x, L.dof)) return 1;
@@ -432,7 +445,7 @@ int build_system(b200ba_handle* h, double huber, double* cost, double* n_valid) 
     h->timings.kernel_launches += 2;
     launch_cost_reduce(h->n_obs, h->out.cost, nullptr, h->out.residual, h->d_partial, h->sys.scalars, h->stream);
     // trace(H) of this rank's partial system, for the lambda initialisation (lm_optimizer.h:766-781)
-    launch_trace(h->L.n_points, h->sys.Dblk, h->L.nd, h->sys.C, h->sys.scalars + 8, h->stream);
+    launch_trace(h->L.nblocks, h->L.bs, h->sys.Dblk, h->L.nd, h->sys.C, h->sys.scalars + 8, h->stream);
     h->timings.kernel_launches += 3;
   }
   CUDA_TRY(h, cudaGetLastError());
@@ -454,27 +467,27 @@ int solve_system(b200ba_handle* h, double lambda, int* spd) {
   // Point range of this rank for the contraction: S = sum_r (C_r - W_r^T W_r) + lambda I, where
   // C_r is the rank's partial dense block and W_r the rows of W = L^-1 B of its points (B, D are
   // global after the per-build all-reduce). With one rank this is the plain S = C + lambda I - W^T W.
-  const int p0 = static_cast<int>(static_cast<int64_t>(L.n_points) * h->rank / h->n_ranks);
-  const int p1 = static_cast<int>(static_cast<int64_t>(L.n_points) * (h->rank + 1) / h->n_ranks);
-  const int k_rows = 3 * (p1 - p0);
+  const int p0 = static_cast<int>(static_cast<int64_t>(L.nblocks) * h->rank / h->n_ranks);
+  const int p1 = static_cast<int>(static_cast<int64_t>(L.nblocks) * (h->rank + 1) / h->n_ranks);
+  const int k_rows = L.bs * (p1 - p0);
   double* rhs_tail = h->d_S + static_cast<size_t>(L.nd) * L.nd;
   {
     ScopedPhase ph(h, PH_SCHUR);
     CUDA_TRY(h, cudaMemsetAsync(h->d_fail, 0, sizeof(int), h->stream));
-    launch_schur_blocks(L.n_points, h->sys.Dblk, h->sys.bp, lambda, h->d_Linv, h->d_v, h->d_fail, h->stream);
-    launch_schur_scale_rows(L.n_points, L.nd, h->sys.B, h->d_Linv, h->d_W, h->stream);
+    launch_schur_blocks(L.bs, L.nblocks, h->sys.Dblk, h->sys.bp, lambda, h->d_Linv, h->d_v, h->d_fail, h->stream);
+    launch_schur_scale_rows(L.bs, L.nblocks, L.nd, h->sys.B, h->d_Linv, h->d_W, h->stream);
     CUDA_TRY(h, cudaMemcpyAsync(h->d_S, h->sys.C, static_cast<size_t>(L.nd) * L.nd * sizeof(double),
                                 cudaMemcpyDeviceToDevice, h->stream));
     CUDA_TRY(h, cudaMemsetAsync(rhs_tail, 0, L.nd * sizeof(double), h->stream));
     h->timings.kernel_launches += 2;
     if (k_rows > 0 && L.nd > 0) {
       const double zero = 0.0;
-      const double* Wr = h->d_W + static_cast<size_t>(3 * p0) * L.nd;
+      const double* Wr = h->d_W + static_cast<size_t>(L.bs) * p0 * L.nd;
       // row-major W [nbd x nd] is the column-major nd x nbd matrix W^T: S -= W_r^T W_r (lower)
       CUBLAS_TRY(h, cublasDsyrk(h->cublas, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_N, L.nd, k_rows, &minus_one, Wr, L.nd,
                                 &one, h->d_S, L.nd));
       // partial reduced right-hand side: -W_r^T v_r
-      CUBLAS_TRY(h, cublasDgemv(h->cublas, CUBLAS_OP_N, L.nd, k_rows, &minus_one, Wr, L.nd, h->d_v + 3 * p0, 1, &zero,
+      CUBLAS_TRY(h, cublasDgemv(h->cublas, CUBLAS_OP_N, L.nd, k_rows, &minus_one, Wr, L.nd, h->d_v + L.bs * p0, 1, &zero,
                                 rhs_tail, 1));
     }
   }
@@ -503,7 +516,7 @@ int solve_system(b200ba_handle* h, double lambda, int* spd) {
     if (L.nbd > 0 && L.nd > 0)
       CUBLAS_TRY(h, cublasDgemv(h->cublas, CUBLAS_OP_T, L.nd, L.nbd, &minus_one, h->d_W, L.nd, h->d_x + L.nbd, 1, &one,
                                 h->d_y, 1));
-    launch_schur_backsub(L.n_points, h->d_Linv, h->d_y, h->d_x, h->stream);
+    launch_schur_backsub(L.bs, L.nblocks, h->d_Linv, h->d_y, h->d_x, h->stream);
     h->timings.kernel_launches += 1;
   }
   CUDA_TRY(h, cudaMemcpyAsync(h->h_flags, h->d_info, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
@@ -1006,7 +1019,7 @@ int b200ba_get_jacobians(b200ba_handle* h, double* j_point, double* j_pose, doub
           } else {
             local = k;
           }
-          idx = L.nbd + L.d_intr + c.upd_off + local;
+          idx = L.g_intr + c.upd_off + local;
         }
         intr_index[o * K + k] = idx;
       }
@@ -1025,7 +1038,7 @@ int b200ba_build_system(b200ba_handle* h, const b200ba_options* opt, int32_t n, 
   double c = 0, nv = 0;
   if (build_system(h, opt->huber_parameter, &c, &nv)) return 1;
   if (cost) *cost = c;
-  std::vector<double> D(6 * static_cast<size_t>(L.n_points)), bp(L.nbd), B(static_cast<size_t>(L.nbd) * L.nd),
+  std::vector<double> D(static_cast<size_t>(L.dsz) * L.nblocks), bp(L.nbd), B(static_cast<size_t>(L.nbd) * L.nd),
       C(static_cast<size_t>(L.nd) * L.nd), bd(L.nd);
   CUDA_TRY(h, cudaMemcpy(D.data(), h->sys.Dblk, D.size() * sizeof(double), cudaMemcpyDeviceToHost));
   CUDA_TRY(h, cudaMemcpy(bp.data(), h->sys.bp, bp.size() * sizeof(double), cudaMemcpyDeviceToHost));
@@ -1033,15 +1046,12 @@ int b200ba_build_system(b200ba_handle* h, const b200ba_options* opt, int32_t n, 
   CUDA_TRY(h, cudaMemcpy(C.data(), h->sys.C, C.size() * sizeof(double), cudaMemcpyDeviceToHost));
   CUDA_TRY(h, cudaMemcpy(bd.data(), h->sys.bd, bd.size() * sizeof(double), cudaMemcpyDeviceToHost));
   std::fill(H, H + static_cast<size_t>(n) * n, 0.0);
-  for (int p = 0; p < L.n_points; ++p) {
-    const double* d = &D[6 * static_cast<size_t>(p)];
-    const int o = 3 * p;
-    H[static_cast<size_t>(o) * n + o] = d[0];
-    H[static_cast<size_t>(o) * n + o + 1] = d[1];
-    H[static_cast<size_t>(o) * n + o + 2] = d[2];
-    H[static_cast<size_t>(o + 1) * n + o + 1] = d[3];
-    H[static_cast<size_t>(o + 1) * n + o + 2] = d[4];
-    H[static_cast<size_t>(o + 2) * n + o + 2] = d[5];
+  for (int p = 0; p < L.nblocks; ++p) {
+    const double* d = &D[static_cast<size_t>(L.dsz) * p];
+    const int o = L.bs * p;
+    for (int a2 = 0; a2 < L.bs; ++a2)
+      for (int b2 = a2; b2 < L.bs; ++b2)
+        H[static_cast<size_t>(o + a2) * n + o + b2] = d[a2 * L.bs - (a2 * (a2 - 1)) / 2 + (b2 - a2)];
   }
   for (int i = 0; i < L.nbd; ++i)
     for (int k = 0; k < L.nd; ++k) H[static_cast<size_t>(i) * n + L.nbd + k] = B[static_cast<size_t>(i) * L.nd + k];

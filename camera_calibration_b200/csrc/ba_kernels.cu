@@ -23,6 +23,32 @@ namespace b200ba {
 
 __device__ __forceinline__ int intr_col(const CamDev& c, int cell, int k);
 
+// H(gi, gj) += v with gi, gj in the reference's global variable ordering; only the upper triangle
+// is stored (lm_optimizer_update_accumulator.h:179,212,223): the pair is ordered first, then
+// routed to the block-diagonal, off-diagonal or dense part (GetPartOfHAndB, :478-505).
+__device__ __forceinline__ void add_H(const Layout& L, const SystemDev& sys, int gi, int gj, double v) {
+  if (gi > gj) {
+    const int t = gi;
+    gi = gj;
+    gj = t;
+  }
+  if (gj < L.nbd) {
+    const int blk = gi / L.bs;
+    const int a = gi - blk * L.bs, b = gj - blk * L.bs;  // same block by construction
+    atomicAdd(&sys.Dblk[static_cast<int64_t>(blk) * L.dsz + a * L.bs - (a * (a - 1)) / 2 + (b - a)], v);
+  } else if (gi < L.nbd) {
+    atomicAdd(&sys.B[static_cast<int64_t>(gi) * L.nd + (gj - L.nbd)], v);
+  } else {
+    atomicAdd(&sys.C[static_cast<int64_t>(gi - L.nbd) * L.nd + (gj - L.nbd)], v);
+  }
+}
+__device__ __forceinline__ void add_b(const Layout& L, const SystemDev& sys, int gi, double v) {
+  if (gi < L.nbd)
+    atomicAdd(&sys.bp[gi], v);
+  else
+    atomicAdd(&sys.bd[gi - L.nbd], v);
+}
+
 // ------------------------------------------------------------------------------------------
 // prepare_state: composed poses + tangent frames
 // ------------------------------------------------------------------------------------------
@@ -550,11 +576,11 @@ __global__ void accumulate_list_kernel(ProblemDev pb, Layout L, ObsOut out, Syst
       if (L.rig_in_state && e < 15) return L.jc_rig + (e - 9);
       return L.jc_intr + (e - (L.rig_in_state ? 15 : 9));
     };
-    auto gidx = [&](int e) -> int {  // index in [points | dense]
-      if (e < 3) return 3 * pidx + e;
-      if (e < 9) return L.nbd + L.d_pose + 6 * iset + (e - 3);
-      if (L.rig_in_state && e < 15) return L.nbd + L.d_rig + 6 * cam + (e - 9);
-      return L.nbd + L.d_intr + intr_col(c, cell, e - (L.rig_in_state ? 15 : 9));
+    auto gidx = [&](int e) -> int {  // global index in the reference ordering
+      if (e < 3) return L.g_point + 3 * pidx + e;
+      if (e < 9) return L.g_pose + 6 * iset + (e - 3);
+      if (L.rig_in_state && e < 15) return L.g_rig + 6 * cam + (e - 9);
+      return L.g_intr + intr_col(c, cell, e - (L.rig_in_state ? 15 : 9));
     };
     for (int p = lane; p < nc * nc; p += 32) {
       const int i = p / nc, j = p - i * nc;
@@ -562,25 +588,12 @@ __global__ void accumulate_list_kernel(ProblemDev pb, Layout L, ObsOut out, Syst
       const int ci = jcol(i), cj = jcol(j);
       const double v = w * (out.jac[(2 * static_cast<int64_t>(ci)) * n + o] * out.jac[(2 * static_cast<int64_t>(cj)) * n + o] +
                             out.jac[(2 * static_cast<int64_t>(ci) + 1) * n + o] * out.jac[(2 * static_cast<int64_t>(cj) + 1) * n + o]);
-      const int gi = gidx(i), gj = gidx(j);
-      if (gj < L.nbd) {  // point x point: 3x3 upper block
-        const int a = gi - 3 * pidx, b = gj - 3 * pidx;
-        const int e = (a == 0) ? b : (a == 1 ? 2 + b : 5);
-        atomicAdd(&sys.Dblk[6 * static_cast<int64_t>(pidx) + e], v);
-      } else if (gi < L.nbd) {
-        atomicAdd(&sys.B[static_cast<int64_t>(gi) * L.nd + (gj - L.nbd)], v);
-      } else {
-        atomicAdd(&sys.C[static_cast<int64_t>(gi - L.nbd) * L.nd + (gj - L.nbd)], v);
-      }
+      add_H(L, sys, gidx(i), gidx(j), v);
     }
     for (int i = lane; i < nc; i += 32) {
       const int ci = jcol(i);
       const double v = w * (out.jac[(2 * static_cast<int64_t>(ci)) * n + o] * rx + out.jac[(2 * static_cast<int64_t>(ci) + 1) * n + o] * ry);
-      const int gi = gidx(i);
-      if (gi < L.nbd)
-        atomicAdd(&sys.bp[gi], v);
-      else
-        atomicAdd(&sys.bd[gi - L.nbd], v);
+      add_b(L, sys, gidx(i), v);
     }
     __syncwarp();
     if (lane == 0) out.has_jac[o] = kJacValid;
@@ -614,132 +627,64 @@ __device__ __forceinline__ double warp_sum(double v) {
   return v;
 }
 
-// H += (w J)^T J, b += (w J)^T r for the parts that group by point and by imageset
-// (LV/lm_optimizer_jtj_accumulator_base.h:287-412, LV/lm_optimizer_update_accumulator.h:180-360):
-//   D_p (3x3), b_p, B[p, pose], B[p, rig], B[p, intrinsics]   -- FP64 atomics, no hot addresses
-//   C[pose, pose], b_pose                                     -- warp-shuffle reduction when the
-//                                                                warp lies inside one imageset
-//   C[pose, rig], C[pose, intrinsics]                          -- FP64 atomics
-// The (rig U intrinsics)^2 block is left to accumulate_cells_kernel.
+// H += (w J)^T J, b += (w J)^T r (LV/lm_optimizer_jtj_accumulator_base.h:287-412,
+// LV/lm_optimizer_update_accumulator.h:180-360) for the small per-observation blocks:
+//   point x point (3x3), pose x pose (6x6), point x pose (3x6), {point, pose} x rig, and the
+//   matching b entries -- 54 (+ 54 with a rig) FP64 atomics per observation.
+// Which of them land in the block-diagonal, off-diagonal or dense part depends on the
+// elimination order and is decided by add_H(). Everything involving intrinsics columns, and
+// rig x rig, is left to accumulate_cells_kernel.
 __global__ void __launch_bounds__(128)
     accumulate_scatter_kernel(ProblemDev pb, Layout L, ObsOut out, SystemDev sys, double huber) {
   const int64_t o = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
   const int64_t n = pb.n_obs;
-  const bool active = (o < n) && out.has_jac[o] == kJacValid;
-  int iset = -1;
-  double w = 0, rx = 0, ry = 0;
+  if (o >= n || out.has_jac[o] != kJacValid) return;
+  const int iset = static_cast<int>(pb.obs_imageset[o]);
+  const int cam = static_cast<int>(pb.obs_camera[o]);
+  const int pidx = static_cast<int>(pb.obs_point[o]);
+  const double rx = out.residual[o], ry = out.residual[n + o];
+  const double w = huber_weight_sq(huber, rx * rx + ry * ry);
   double jpx[3], jpy[3], jox[6], joy[6];
-  int pidx = 0, cam = 0;
-  if (active) {
-    iset = static_cast<int>(pb.obs_imageset[o]);
-    cam = static_cast<int>(pb.obs_camera[o]);
-    pidx = static_cast<int>(pb.obs_point[o]);
-    rx = out.residual[o];
-    ry = out.residual[n + o];
-    w = huber_weight_sq(huber, rx * rx + ry * ry);
-#pragma unroll
-    for (int a = 0; a < 3; ++a) {
-      jpx[a] = out.jac[(2 * static_cast<int64_t>(L.jc_point + a)) * n + o];
-      jpy[a] = out.jac[(2 * static_cast<int64_t>(L.jc_point + a) + 1) * n + o];
-    }
-#pragma unroll
-    for (int a = 0; a < 6; ++a) {
-      jox[a] = out.jac[(2 * static_cast<int64_t>(L.jc_pose + a)) * n + o];
-      joy[a] = out.jac[(2 * static_cast<int64_t>(L.jc_pose + a) + 1) * n + o];
-    }
-  } else {
-#pragma unroll
-    for (int a = 0; a < 3; ++a) jpx[a] = jpy[a] = 0;
-#pragma unroll
-    for (int a = 0; a < 6; ++a) jox[a] = joy[a] = 0;
-  }
-
-  // ---- pose x pose and b_pose: segmented warp reduction --------------------------------------
-  {
-    const int lane = threadIdx.x & 31;
-    // a warp whose lanes are all inactive has nothing to add
-    const bool any_active = __any_sync(0xffffffffu, active);
-    if (any_active) {
-      // the representative imageset is that of the first active lane
-      const unsigned act = __ballot_sync(0xffffffffu, active);
-      const int first = __ffs(act) - 1;
-      const int iset_f = __shfl_sync(0xffffffffu, iset, first);
-      const bool uni = __all_sync(0xffffffffu, !active || iset == iset_f);
-      double* Cpose = sys.C;
-      if (uni) {
-#pragma unroll
-        for (int a = 0; a < 6; ++a) {
-#pragma unroll
-          for (int b = a; b < 6; ++b) {
-            const double v = warp_sum(w * (jox[a] * jox[b] + joy[a] * joy[b]));
-            if (lane == 0) {
-              const int64_t row = L.d_pose + 6 * iset_f + a;
-              atomicAdd(&Cpose[row * L.nd + (L.d_pose + 6 * iset_f + b)], v);
-            }
-          }
-          const double vb = warp_sum(w * (jox[a] * rx + joy[a] * ry));
-          if (lane == 0) atomicAdd(&sys.bd[L.d_pose + 6 * iset_f + a], vb);
-        }
-      } else if (active) {
-#pragma unroll
-        for (int a = 0; a < 6; ++a) {
-          const int64_t row = L.d_pose + 6 * iset + a;
-#pragma unroll
-          for (int b = a; b < 6; ++b)
-            atomicAdd(&Cpose[row * L.nd + (L.d_pose + 6 * iset + b)], w * (jox[a] * jox[b] + joy[a] * joy[b]));
-          atomicAdd(&sys.bd[row], w * (jox[a] * rx + joy[a] * ry));
-        }
-      }
-    }
-  }
-  if (!active) return;
-
-  // ---- point block D_p, b_p -----------------------------------------------------------------
-  {
-    double* D = sys.Dblk + 6 * static_cast<int64_t>(pidx);
-    int e = 0;
-#pragma unroll
-    for (int a = 0; a < 3; ++a) {
-#pragma unroll
-      for (int b = a; b < 3; ++b) {
-        atomicAdd(&D[e], w * (jpx[a] * jpx[b] + jpy[a] * jpy[b]));
-        ++e;
-      }
-      atomicAdd(&sys.bp[3 * static_cast<int64_t>(pidx) + a], w * (jpx[a] * rx + jpy[a] * ry));
-    }
-  }
-  // ---- B[p, pose] ---------------------------------------------------------------------------
 #pragma unroll
   for (int a = 0; a < 3; ++a) {
-    double* Brow = sys.B + (3 * static_cast<int64_t>(pidx) + a) * L.nd;
+    jpx[a] = out.jac[(2 * static_cast<int64_t>(L.jc_point + a)) * n + o];
+    jpy[a] = out.jac[(2 * static_cast<int64_t>(L.jc_point + a) + 1) * n + o];
+  }
+#pragma unroll
+  for (int a = 0; a < 6; ++a) {
+    jox[a] = out.jac[(2 * static_cast<int64_t>(L.jc_pose + a)) * n + o];
+    joy[a] = out.jac[(2 * static_cast<int64_t>(L.jc_pose + a) + 1) * n + o];
+  }
+  const int gp = L.g_point + 3 * pidx, go = L.g_pose + 6 * iset;
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
     const double wx_ = w * jpx[a], wy_ = w * jpy[a];
 #pragma unroll
-    for (int b = 0; b < 6; ++b) atomicAdd(&Brow[L.d_pose + 6 * iset + b], wx_ * jox[b] + wy_ * joy[b]);
+    for (int b = a; b < 3; ++b) add_H(L, sys, gp + a, gp + b, wx_ * jpx[b] + wy_ * jpy[b]);
+#pragma unroll
+    for (int b = 0; b < 6; ++b) add_H(L, sys, gp + a, go + b, wx_ * jox[b] + wy_ * joy[b]);
+    add_b(L, sys, gp + a, wx_ * rx + wy_ * ry);
   }
-  // ---- rig columns: B[p, rig], C[pose, rig] ---------------------------------------------------
+#pragma unroll
+  for (int a = 0; a < 6; ++a) {
+    const double wx_ = w * jox[a], wy_ = w * joy[a];
+#pragma unroll
+    for (int b = a; b < 6; ++b) add_H(L, sys, go + a, go + b, wx_ * jox[b] + wy_ * joy[b]);
+    add_b(L, sys, go + a, wx_ * rx + wy_ * ry);
+  }
   if (L.rig_in_state) {
-    double jrx[6], jry[6];
+    const int gr = L.g_rig + 6 * cam;
+#pragma unroll 1
+    for (int b = 0; b < 6; ++b) {
+      const double jrx = out.jac[(2 * static_cast<int64_t>(L.jc_rig + b)) * n + o];
+      const double jry = out.jac[(2 * static_cast<int64_t>(L.jc_rig + b) + 1) * n + o];
+      const double wx_ = w * jrx, wy_ = w * jry;
 #pragma unroll
-    for (int a = 0; a < 6; ++a) {
-      jrx[a] = out.jac[(2 * static_cast<int64_t>(L.jc_rig + a)) * n + o];
-      jry[a] = out.jac[(2 * static_cast<int64_t>(L.jc_rig + a) + 1) * n + o];
-    }
-    const int rc = L.d_rig + 6 * cam;
+      for (int a = 0; a < 3; ++a) add_H(L, sys, gp + a, gr + b, wx_ * jpx[a] + wy_ * jpy[a]);
 #pragma unroll
-    for (int a = 0; a < 3; ++a) {
-      double* Brow = sys.B + (3 * static_cast<int64_t>(pidx) + a) * L.nd;
-#pragma unroll
-      for (int b = 0; b < 6; ++b) atomicAdd(&Brow[rc + b], w * (jpx[a] * jrx[b] + jpy[a] * jry[b]));
-    }
-#pragma unroll
-    for (int a = 0; a < 6; ++a) {
-      double* Crow = sys.C + static_cast<int64_t>(L.d_pose + 6 * iset + a) * L.nd;
-#pragma unroll
-      for (int b = 0; b < 6; ++b) atomicAdd(&Crow[rc + b], w * (jox[a] * jrx[b] + joy[a] * jry[b]));
+      for (int a = 0; a < 6; ++a) add_H(L, sys, go + a, gr + b, wx_ * jox[a] + wy_ * joy[a]);
     }
   }
-  // B[p, intrinsics] and C[pose, intrinsics] are accumulated by accumulate_cells_kernel, where a
-  // warp covers the 32 (80 / 12) intrinsics columns of ONE matrix row: sector-coalesced atomics.
 }
 
 void launch_accumulate_scatter(const ProblemDev& pb, const Layout& L, const ObsOut& out, const SystemDev& sys,
@@ -869,11 +814,9 @@ __global__ void __launch_bounds__(kCellThreads)
           const int rest = idx / K;
           const int r9 = rest % 9, t = rest / 9;
           const double v = fma(sPx[t * 9 + r9], sJx[t * Emax + rigE + kk], sPy[t * 9 + r9] * sJy[t * Emax + rigE + kk]);
-          const int gc = L.d_intr + intr_col(c, cell, kk);
-          if (r9 < 3)
-            atomicAdd(&sys.B[(3 * static_cast<int64_t>(sPoint[t]) + r9) * L.nd + gc], v);
-          else
-            atomicAdd(&sys.C[static_cast<int64_t>(L.d_pose + 6 * sIset[t] + (r9 - 3)) * L.nd + gc], v);
+          const int gc = L.g_intr + intr_col(c, cell, kk);
+          const int gr = (r9 < 3) ? (L.g_point + 3 * sPoint[t] + r9) : (L.g_pose + 6 * sIset[t] + (r9 - 3));
+          add_H(L, sys, gr, gc, v);
         }
       }
 #pragma unroll
@@ -895,17 +838,14 @@ __global__ void __launch_bounds__(kCellThreads)
       pos += run_n;
     }
     // flush the run
-    auto gcol = [&](int e) -> int {
-      return (e < rigE) ? (L.d_rig + 6 * cam + e) : (L.d_intr + intr_col(c, cell, e - rigE));
+    auto gcol = [&](int e) -> int {  // rig and intrinsics are dense variables in both elimination orders
+      return (e < rigE) ? (L.g_rig + 6 * cam + e) : (L.g_intr + intr_col(c, cell, e - rigE));
     };
 #pragma unroll
     for (int q = 0; q < MAXPAIRS; ++q) {
-      if (threadIdx.x + q * kCellThreads < npairs) {
-        const int gi = gcol(pi[q]), gj = gcol(pj[q]);
-        atomicAdd(&sys.C[static_cast<int64_t>(gi) * L.nd + gj], acc[q]);
-      }
+      if (threadIdx.x + q * kCellThreads < npairs) add_H(L, sys, gcol(pi[q]), gcol(pj[q]), acc[q]);
     }
-    if (threadIdx.x < E) atomicAdd(&sys.bd[gcol(threadIdx.x)], accb);
+    if (threadIdx.x < E) add_b(L, sys, gcol(threadIdx.x), accb);
   }
 }
 
@@ -941,82 +881,134 @@ void launch_accumulate_cells(const ProblemDev& pb, const Layout& L, const ObsOut
 // ------------------------------------------------------------------------------------------
 // Schur complement helpers (LV/lm_optimizer.h:1246-1369)
 // ------------------------------------------------------------------------------------------
-// Per point: L = chol(D_p + lambda I) (lower), Linv = L^-1 (6 doubles), v = Linv b_p.
-// A non-positive pivot raises *fail (the caller rejects the attempt like a NaN update).
-__global__ void schur_blocks_kernel(int n_points, const double* __restrict__ Dblk, const double* __restrict__ bp,
+// Per block: L = chol(D_i + lambda I) (lower), Linv = L^-1 (packed lower, row-major), v = Linv b_i.
+// D_i is stored as its packed upper triangle. A non-positive pivot raises *fail (the caller
+// rejects the attempt like the reference rejects a NaN update).
+template <int BS>
+__global__ void schur_blocks_kernel(int n_blocks, const double* __restrict__ Dblk, const double* __restrict__ bp,
                                     double lambda, double* __restrict__ Linv, double* __restrict__ v, int* fail) {
+  constexpr int DSZ = BS * (BS + 1) / 2;
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= n_points) return;
-  const double* D = Dblk + 6 * static_cast<int64_t>(p);
-  const double a00 = D[0] + lambda, a01 = D[1], a02 = D[2], a11 = D[3] + lambda, a12 = D[4], a22 = D[5] + lambda;
-  const double l00s = a00;
-  if (!(l00s > 0)) *fail = 1;
-  const double l00 = sqrt(l00s);
-  const double l10 = a01 / l00, l20 = a02 / l00;
-  const double l11s = a11 - l10 * l10;
-  if (!(l11s > 0)) *fail = 1;
-  const double l11 = sqrt(l11s);
-  const double l21 = (a12 - l20 * l10) / l11;
-  const double l22s = a22 - l20 * l20 - l21 * l21;
-  if (!(l22s > 0)) *fail = 1;
-  const double l22 = sqrt(l22s);
-  // inverse of the lower-triangular factor
-  const double i00 = 1.0 / l00, i11 = 1.0 / l11, i22 = 1.0 / l22;
-  const double i10 = -l10 * i00 * i11;
-  const double i21 = -l21 * i11 * i22;
-  const double i20 = -(l20 * i00 + l21 * i10) * i22;
-  double* Li = Linv + 6 * static_cast<int64_t>(p);
-  Li[0] = i00;
-  Li[1] = i10;
-  Li[2] = i11;
-  Li[3] = i20;
-  Li[4] = i21;
-  Li[5] = i22;
-  const double b0 = bp[3 * p], b1 = bp[3 * p + 1], b2 = bp[3 * p + 2];
-  v[3 * p] = i00 * b0;
-  v[3 * p + 1] = i10 * b0 + i11 * b1;
-  v[3 * p + 2] = i20 * b0 + i21 * b1 + i22 * b2;
+  if (p >= n_blocks) return;
+  const double* D = Dblk + static_cast<int64_t>(DSZ) * p;
+  double A[BS][BS], Lm[BS][BS], Li[BS][BS];
+#pragma unroll
+  for (int a = 0; a < BS; ++a)
+#pragma unroll
+    for (int b = a; b < BS; ++b) {
+      const double d = D[a * BS - (a * (a - 1)) / 2 + (b - a)] + (a == b ? lambda : 0.0);
+      A[a][b] = d;
+      A[b][a] = d;
+    }
+  bool bad = false;
+#pragma unroll
+  for (int j = 0; j < BS; ++j) {
+    double s = A[j][j];
+#pragma unroll
+    for (int k2 = 0; k2 < j; ++k2) s -= Lm[j][k2] * Lm[j][k2];
+    if (!(s > 0)) bad = true;
+    const double ljj = sqrt(s);
+    Lm[j][j] = ljj;
+#pragma unroll
+    for (int i = j + 1; i < BS; ++i) {
+      double t = A[i][j];
+#pragma unroll
+      for (int k2 = 0; k2 < j; ++k2) t -= Lm[i][k2] * Lm[j][k2];
+      Lm[i][j] = t / ljj;
+    }
+  }
+  if (bad) *fail = 1;
+  // inverse of the lower-triangular factor by forward substitution, column by column
+#pragma unroll
+  for (int c2 = 0; c2 < BS; ++c2) {
+#pragma unroll
+    for (int i = 0; i < BS; ++i) {
+      if (i < c2) {
+        Li[i][c2] = 0;
+      } else {
+        double t = (i == c2) ? 1.0 : 0.0;
+#pragma unroll
+        for (int k2 = c2; k2 < i; ++k2) t -= Lm[i][k2] * Li[k2][c2];
+        Li[i][c2] = t / Lm[i][i];
+      }
+    }
+  }
+  double* out = Linv + static_cast<int64_t>(DSZ) * p;
+#pragma unroll
+  for (int i = 0; i < BS; ++i)
+#pragma unroll
+    for (int j = 0; j <= i; ++j) out[(i * (i + 1)) / 2 + j] = Li[i][j];
+#pragma unroll
+  for (int i = 0; i < BS; ++i) {
+    double t = 0;
+#pragma unroll
+    for (int j = 0; j <= i; ++j) t += Li[i][j] * bp[BS * p + j];
+    v[BS * p + i] = t;
+  }
 }
-void launch_schur_blocks(int n_points, const double* Dblk, const double* bp, double lambda, double* Linv, double* v,
-                         int* fail, cudaStream_t s) {
-  if (n_points == 0) return;
-  schur_blocks_kernel<<<(n_points + 127) / 128, 128, 0, s>>>(n_points, Dblk, bp, lambda, Linv, v, fail);
+void launch_schur_blocks(int bs, int n_blocks, const double* Dblk, const double* bp, double lambda, double* Linv,
+                         double* v, int* fail, cudaStream_t s) {
+  if (n_blocks == 0) return;
+  if (bs == 3)
+    schur_blocks_kernel<3><<<(n_blocks + 127) / 128, 128, 0, s>>>(n_blocks, Dblk, bp, lambda, Linv, v, fail);
+  else
+    schur_blocks_kernel<6><<<(n_blocks + 127) / 128, 128, 0, s>>>(n_blocks, Dblk, bp, lambda, Linv, v, fail);
 }
 
-// W = L^-1 B, three rows per point. With D^-1 = L^-T L^-1 the contraction B^T D^-1 B
+// W = L^-1 B, BS rows per block. With D^-1 = L^-T L^-1 the contraction B^T D^-1 B
 // (LV/lm_optimizer.h:1294-1311,1328) becomes the symmetric rank-k update W^T W.
+template <int BS>
 __global__ void schur_scale_rows_kernel(int nd, const double* __restrict__ B, const double* __restrict__ Linv,
                                         double* __restrict__ W) {
+  constexpr int DSZ = BS * (BS + 1) / 2;
   const int p = blockIdx.y;
   const int col = blockIdx.x * blockDim.x + threadIdx.x;
   if (col >= nd) return;
-  const double* Li = Linv + 6 * static_cast<int64_t>(p);
-  const int64_t r0 = 3 * static_cast<int64_t>(p) * nd + col;
-  const double b0 = B[r0], b1 = B[r0 + nd], b2 = B[r0 + 2 * static_cast<int64_t>(nd)];
-  W[r0] = Li[0] * b0;
-  W[r0 + nd] = fma(Li[1], b0, Li[2] * b1);
-  W[r0 + 2 * static_cast<int64_t>(nd)] = fma(Li[3], b0, fma(Li[4], b1, Li[5] * b2));
+  const double* Li = Linv + static_cast<int64_t>(DSZ) * p;
+  const int64_t r0 = static_cast<int64_t>(BS) * p * nd + col;
+  double b[BS];
+#pragma unroll
+  for (int i = 0; i < BS; ++i) b[i] = B[r0 + static_cast<int64_t>(i) * nd];
+#pragma unroll
+  for (int i = 0; i < BS; ++i) {
+    double t = 0;
+#pragma unroll
+    for (int j = 0; j <= i; ++j) t = fma(Li[(i * (i + 1)) / 2 + j], b[j], t);
+    W[r0 + static_cast<int64_t>(i) * nd] = t;
+  }
 }
-void launch_schur_scale_rows(int n_points, int nd, const double* B, const double* Linv, double* W, cudaStream_t s) {
-  if (n_points == 0 || nd == 0) return;
-  dim3 grid((nd + 255) / 256, n_points);
-  schur_scale_rows_kernel<<<grid, 256, 0, s>>>(nd, B, Linv, W);
+void launch_schur_scale_rows(int bs, int n_blocks, int nd, const double* B, const double* Linv, double* W,
+                             cudaStream_t s) {
+  if (n_blocks == 0 || nd == 0) return;
+  dim3 grid((nd + 255) / 256, n_blocks);
+  if (bs == 3)
+    schur_scale_rows_kernel<3><<<grid, 256, 0, s>>>(nd, B, Linv, W);
+  else
+    schur_scale_rows_kernel<6><<<grid, 256, 0, s>>>(nd, B, Linv, W);
 }
 
-// x_p = L^-T y_p, y = v - W x_d (back-substitution, LV/lm_optimizer.h:1366-1367)
-__global__ void schur_backsub_kernel(int n_points, const double* __restrict__ Linv, const double* __restrict__ y,
+// x_b = L^-T y_b, y = v - W x_d (back-substitution, LV/lm_optimizer.h:1366-1367)
+template <int BS>
+__global__ void schur_backsub_kernel(int n_blocks, const double* __restrict__ Linv, const double* __restrict__ y,
                                      double* __restrict__ xp) {
+  constexpr int DSZ = BS * (BS + 1) / 2;
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= n_points) return;
-  const double* Li = Linv + 6 * static_cast<int64_t>(p);
-  const double y0 = y[3 * p], y1 = y[3 * p + 1], y2 = y[3 * p + 2];
-  xp[3 * p] = Li[0] * y0 + Li[1] * y1 + Li[3] * y2;
-  xp[3 * p + 1] = Li[2] * y1 + Li[4] * y2;
-  xp[3 * p + 2] = Li[5] * y2;
+  if (p >= n_blocks) return;
+  const double* Li = Linv + static_cast<int64_t>(DSZ) * p;
+#pragma unroll
+  for (int j = 0; j < BS; ++j) {
+    double t = 0;
+#pragma unroll
+    for (int i = j; i < BS; ++i) t += Li[(i * (i + 1)) / 2 + j] * y[BS * p + i];
+    xp[BS * p + j] = t;
+  }
 }
-void launch_schur_backsub(int n_points, const double* Linv, const double* y, double* xp, cudaStream_t s) {
-  if (n_points == 0) return;
-  schur_backsub_kernel<<<(n_points + 127) / 128, 128, 0, s>>>(n_points, Linv, y, xp);
+void launch_schur_backsub(int bs, int n_blocks, const double* Linv, const double* y, double* xp, cudaStream_t s) {
+  if (n_blocks == 0) return;
+  if (bs == 3)
+    schur_backsub_kernel<3><<<(n_blocks + 127) / 128, 128, 0, s>>>(n_blocks, Linv, y, xp);
+  else
+    schur_backsub_kernel<6><<<(n_blocks + 127) / 128, 128, 0, s>>>(n_blocks, Linv, y, xp);
 }
 
 // S(i, i) = C(i, i) + lambda (LV/lm_optimizer.h:839-852: the damping is ADDED to the diagonal)
@@ -1029,15 +1021,16 @@ void launch_add_diagonal(int n, double* M, int64_t ld, double lambda, cudaStream
   add_diagonal_kernel<<<(n + 255) / 256, 256, 0, s>>>(n, M, ld, lambda);
 }
 
-// trace of H = sum diag(D_p) + sum diag(C) for the lambda initialisation
+// trace of H = sum of the block diagonals + sum diag(C) for the lambda initialisation
 // (LV/lm_optimizer.h:766-781); single block, deterministic order.
-__global__ void trace_kernel(int n_points, const double* __restrict__ Dblk, int nd, const double* __restrict__ C,
-                             double* out) {
+__global__ void trace_kernel(int n_blocks, int bs, const double* __restrict__ Dblk, int nd,
+                             const double* __restrict__ C, double* out) {
   __shared__ double sh[256];
+  const int dsz = bs * (bs + 1) / 2;
   double a = 0;
-  for (int p = threadIdx.x; p < n_points; p += blockDim.x) {
-    const double* D = Dblk + 6 * static_cast<int64_t>(p);
-    a += D[0] + D[3] + D[5];
+  for (int p = threadIdx.x; p < n_blocks; p += blockDim.x) {
+    const double* D = Dblk + static_cast<int64_t>(dsz) * p;
+    for (int i = 0; i < bs; ++i) a += D[i * bs - (i * (i - 1)) / 2];
   }
   for (int i = threadIdx.x; i < nd; i += blockDim.x) a += C[static_cast<int64_t>(i) * nd + i];
   sh[threadIdx.x] = a;
@@ -1048,8 +1041,8 @@ __global__ void trace_kernel(int n_points, const double* __restrict__ Dblk, int 
   }
   if (threadIdx.x == 0) *out = sh[0];
 }
-void launch_trace(int n_points, const double* Dblk, int nd, const double* C, double* out, cudaStream_t s) {
-  trace_kernel<<<1, 256, 0, s>>>(n_points, Dblk, nd, C, out);
+void launch_trace(int n_blocks, int bs, const double* Dblk, int nd, const double* C, double* out, cudaStream_t s) {
+  trace_kernel<<<1, 256, 0, s>>>(n_blocks, bs, Dblk, nd, C, out);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1086,20 +1079,20 @@ __global__ void update_state_kernel(ProblemDev pb, Layout L, StateDev src, State
   // segment 0: point coordinates
   const int64_t n_pc = 3 * static_cast<int64_t>(L.n_points);
   if (tid < n_pc) {
-    dst.points[tid] = src.points[tid] - x[tid];
+    dst.points[tid] = src.points[tid] - x[L.g_point + tid];
     return;
   }
   int64_t k = tid - n_pc;
   // segment 1: imageset poses
   if (k < L.n_imagesets) {
-    retract_pose(src.rig_tr_global + 7 * k, dst.rig_tr_global + 7 * k, x + L.nbd + L.d_pose + 6 * k);
+    retract_pose(src.rig_tr_global + 7 * k, dst.rig_tr_global + 7 * k, x + L.g_pose + 6 * k);
     return;
   }
   k -= L.n_imagesets;
   // segment 2: camera_tr_rig (variables only when there is more than one camera)
   if (k < L.n_cameras) {
     if (L.rig_in_state) {
-      retract_pose(src.camera_tr_rig + 7 * k, dst.camera_tr_rig + 7 * k, x + L.nbd + L.d_rig + 6 * k);
+      retract_pose(src.camera_tr_rig + 7 * k, dst.camera_tr_rig + 7 * k, x + L.g_rig + 6 * k);
     } else {
       for (int i = 0; i < 7; ++i) dst.camera_tr_rig[7 * k + i] = src.camera_tr_rig[7 * k + i];
     }
@@ -1135,7 +1128,7 @@ __global__ void update_state_kernel(ProblemDev pb, Layout L, StateDev src, State
     }
     d3 t1, t2;
     compute_tangents(dir, t1, t2);
-    const double* dl = x + L.nbd + L.d_intr + c.upd_off + c.dof_per_point * local;
+    const double* dl = x + L.g_intr + c.upd_off + c.dof_per_point * local;
     const d3 nd_ = (dir + (-dl[0]) * t1) + (-dl[1]) * t2;
     const double nn = sqrt(dot3(nd_, nd_));
     go[0] = nd_.x / nn;
@@ -1166,7 +1159,7 @@ __global__ void update_state_kernel(ProblemDev pb, Layout L, StateDev src, State
       local -= np;
     }
     const CamDev& c = pb.cams[cam];
-    const double d = L.localize_only ? 0.0 : x[L.nbd + L.d_intr + c.upd_off + local];
+    const double d = L.localize_only ? 0.0 : x[L.g_intr + c.upd_off + local];
     dst.intrinsics[c.intr_off + local] = src.intrinsics[c.intr_off + local] - d;
   }
 }

@@ -22,12 +22,13 @@ void launch_accumulate_scatter(const ProblemDev& pb, const Layout& L, const ObsO
                                double huber, cudaStream_t s);
 void launch_accumulate_cells(const ProblemDev& pb, const Layout& L, const ObsOut& out, const SystemDev& sys,
                              double huber, cudaStream_t s);
-void launch_schur_blocks(int n_points, const double* Dblk, const double* bp, double lambda, double* Linv, double* v,
-                         int* fail, cudaStream_t s);
-void launch_schur_scale_rows(int n_points, int nd, const double* B, const double* Linv, double* W, cudaStream_t s);
-void launch_schur_backsub(int n_points, const double* Linv, const double* y, double* xp, cudaStream_t s);
+void launch_schur_blocks(int bs, int n_blocks, const double* Dblk, const double* bp, double lambda, double* Linv,
+                         double* v, int* fail, cudaStream_t s);
+void launch_schur_scale_rows(int bs, int n_blocks, int nd, const double* B, const double* Linv, double* W,
+                             cudaStream_t s);
+void launch_schur_backsub(int bs, int n_blocks, const double* Linv, const double* y, double* xp, cudaStream_t s);
 void launch_add_diagonal(int n, double* M, int64_t ld, double lambda, cudaStream_t s);
-void launch_trace(int n_points, const double* Dblk, int nd, const double* C, double* out, cudaStream_t s);
+void launch_trace(int n_blocks, int bs, const double* Dblk, int nd, const double* C, double* out, cudaStream_t s);
 void launch_update_state(const ProblemDev& pb, const Layout& L, const StateDev& src, const StateDev& dst,
                          const double* x, int64_t n_control_total, int64_t n_param_total, cudaStream_t s);
 void launch_cost_reduce(int64_t n, const double* trial, const double* base, const double* residual, double* partial,

@@ -133,10 +133,10 @@ def test_residuals_and_jacobians_match_oracle(oracle_lib, cfg):
         assert np.abs(a - b).max() < 1e-8 * scale, (cfg, k, np.abs(a - b).max(), scale)
 
 
-@pytest.mark.parametrize("cfg", [1, 2, 3, 4])
-def test_normal_equations_match_oracle(oracle_lib, cfg):
+@pytest.mark.parametrize("cfg,eliminate_points", [(1, 1), (2, 1), (3, 1), (4, 1), (2, 0), (3, 0), (4, 0), (1, 0)])
+def test_normal_equations_match_oracle(oracle_lib, cfg, eliminate_points):
     sp = _small(cfg)
-    opt = cabi.default_options()
+    opt = cabi.default_options(eliminate_points=eliminate_points)
     with api.BundleAdjuster(sp.problem) as adj:
         adj.set_state(sp.init_state)
         Hg, bg, cg = adj.build_system(opt)
@@ -150,11 +150,14 @@ def test_normal_equations_match_oracle(oracle_lib, cfg):
     assert np.array_equal(Hg != 0, Ho != 0) or np.abs(Hg[(Hg != 0) != (Ho != 0)]).max() < 1e-12 * np.abs(Ho).max()
 
 
-@pytest.mark.parametrize("cfg,iters", [(1, 8), (2, 8), (3, 6), (4, 6)])
-def test_lm_trajectory_matches_oracle(oracle_lib, cfg, iters):
-    """Same accept / reject sequence, same cost after every iteration, same final state."""
+@pytest.mark.parametrize("cfg,iters,eliminate_points", [(1, 8, 1), (2, 8, 1), (3, 6, 1), (4, 6, 1), (2, 6, 0), (4, 5, 0),
+                                                         (3, 4, 0)])
+def test_lm_trajectory_matches_oracle(oracle_lib, cfg, iters, eliminate_points):
+    """Same accept / reject sequence, same cost after every iteration, same final state -- for the
+    point-elimination order (3x3 blocks, what north_star names) and the pose-elimination order
+    (6x6 blocks, what the product's Calibrate() runs, calibration.cc:227-237)."""
     sp = _small(cfg)
-    opt = cabi.default_options(max_iteration_count=iters)
+    opt = cabi.default_options(max_iteration_count=iters, eliminate_points=eliminate_points)
     st = sp.init_state.copy()
     with api.BundleAdjuster(sp.problem) as adj:
         rep = adj.optimize_host(st, opt)
@@ -196,6 +199,20 @@ def test_reference_ba_test_threshold_gpu():
     cost = np.inf
     for i in range(20):
         cost, lam, performed = api.OptimizeJointly(ds, state, 1, lam, 1e-4, 0, False, True, api.SchurMode.Dense,
+                                                   print_progress=False)
+        if not performed:
+            break
+    assert cost <= 1e-6
+
+
+def test_reference_ba_test_threshold_gpu_product_default():
+    """The reference's own call: eliminate_points=false (test/util.h:452-469)."""
+    problem, st, _ = helpers.reference_ba_test_problem(num_cameras=1, n_points=150, n_poses=100)
+    ds, state = api.dataset_from_flat(problem, st)
+    lam = -1.0
+    cost = np.inf
+    for i in range(20):
+        cost, lam, performed = api.OptimizeJointly(ds, state, 1, lam, 1e-4, 0, False, False, api.SchurMode.Dense,
                                                    print_progress=False)
         if not performed:
             break
