@@ -848,9 +848,16 @@ int b200ba_optimize(b200ba_handle* h, const b200ba_options* opt, b200ba_report* 
   const double huber = opt->huber_parameter;
   double lambda = 0, init_lambda = opt->init_lambda;
   double final_cost = -1;
+  // n_valid / sum |r|^2 of the CURRENT state, taken from the passes the LM loop makes anyway (the
+  // base pass of a build, or the trial pass of an accepted step) -- no extra pass for statistics
+  double stat_valid = 0, stat_sumsq = 0;
+  bool have_stats = false;
   for (int iteration = 0; iteration < opt->max_iteration_count; ++iteration) {
     double cost = 0, n_valid = 0;
     if (build_system(h, huber, &cost, &n_valid)) return 1;
+    stat_valid = h->h_scal[4];
+    stat_sumsq = h->h_scal[5];
+    have_stats = true;
     double last_cost = cost;
     if (iteration == 0) report->initial_cost = cost;
     if (cost == 0) {  // "Cost is zero, stopping." (lm_optimizer.h:755-760)
@@ -896,6 +903,8 @@ int b200ba_optimize(b200ba_handle* h, const b200ba_options* opt, b200ba_report* 
       // CostIsSmallerThan (lm_optimizer.h:993-1011)
       if (count > 0 && left < right) {
         h->cur = trial;
+        stat_valid = h->h_scal[4];
+        stat_sumsq = h->h_scal[5];
         lambda = 0.5f * lambda;
         applied_update = true;
         report->num_iterations_performed += 1;
@@ -921,12 +930,17 @@ int b200ba_optimize(b200ba_handle* h, const b200ba_options* opt, b200ba_report* 
     if (last_cost == 0) break;
   }
   report->final_cost = final_cost;
-  // statistics at the final state: residual-only pass from the warm start
-  if (evaluate_state(h, h->cur, false, h->out_trial, huber, PH_TRIAL)) return 1;
-  launch_cost_reduce(h->n_obs, h->out_trial.cost, nullptr, h->out_trial.residual, h->d_partial, h->d_scal, h->stream);
-  h->timings.kernel_launches += 2;
-  if (all_reduce(h, h->d_scal, 6)) return 1;
-  CUDA_TRY(h, cudaMemcpyAsync(h->h_scal, h->d_scal, 6 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  if (!have_stats) {
+    // max_iteration_count == 0: statistics of the unchanged state need one residual-only pass
+    if (evaluate_state(h, h->cur, false, h->out_trial, huber, PH_TRIAL)) return 1;
+    launch_cost_reduce(h->n_obs, h->out_trial.cost, nullptr, h->out_trial.residual, h->d_partial, h->d_scal, h->stream);
+    h->timings.kernel_launches += 2;
+    if (all_reduce(h, h->d_scal, 6)) return 1;
+    CUDA_TRY(h, cudaMemcpyAsync(h->h_scal, h->d_scal, 6 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    if (sync_stream(h)) return 1;
+    stat_valid = h->h_scal[4];
+    stat_sumsq = h->h_scal[5];
+  }
   cudaEventRecord(ev_total_b, h->stream);
   if (sync_stream(h)) return 1;
   {
@@ -936,10 +950,10 @@ int b200ba_optimize(b200ba_handle* h, const b200ba_options* opt, b200ba_report* 
     h->event_pool.push_back(ev_total_a);
     h->event_pool.push_back(ev_total_b);
   }
-  report->n_valid = static_cast<int64_t>(h->h_scal[4]);
+  report->n_valid = static_cast<int64_t>(stat_valid);
   // with several ranks n_valid is global (all-reduced) while n_obs is this rank's shard
   report->n_invalid = (h->n_ranks > 1) ? -1 : (h->n_obs - report->n_valid);
-  report->rmse = report->n_valid > 0 ? std::sqrt(h->h_scal[5] / h->h_scal[4]) : 0.0;
+  report->rmse = report->n_valid > 0 ? std::sqrt(stat_sumsq / stat_valid) : 0.0;
   report->cost_and_jacobian_evaluation_time = 1e-3 * (h->timings.jacobian_kernel_ms + h->timings.accumulate_ms + h->timings.trial_cost_ms);
   report->solve_time = 1e-3 * (h->timings.schur_ms + h->timings.factor_ms);
   return 0;

@@ -68,8 +68,12 @@ def full(tag, rep, cmd):
                 if w in idx:
                     f.write(f"| `{w}` | {r[idx[w]]} | {units[idx[w]]} |\n")
             f.write("\n")
-            if 'residual_jacobian' in name and ('true' in name or ', 1>' in name):
-                latest = r
+            if 'residual_jacobian_kernel<' in name:
+                # template arguments <MODEL, JAC, MINB, STRAGGLER>: the main pass with Jacobians
+                args = [a.strip().replace('(int)', '').replace('(bool)', '') for a in
+                        name.split('residual_jacobian_kernel<')[1].split('>')[0].split(',')]
+                if len(args) >= 4 and args[1] in ('1', 'true') and args[3] in ('0', 'false'):
+                    latest = r
     if latest is not None:
         tr = to_bytes(latest[idx['dram__bytes_read.sum']], units[idx['dram__bytes_read.sum']]) + \
             to_bytes(latest[idx['dram__bytes_write.sum']], units[idx['dram__bytes_write.sum']])

@@ -339,3 +339,28 @@ def test_straggler_pass_equals_main_pass(oracle_lib):
             assert np.allclose(rep.trace()[0], orep.trace()[0], rtol=1e-7)
     finally:
         lib.b200ba_debug_set_eval_budget(16)
+
+
+@pytest.mark.parametrize("cfg", [3, 4])
+def test_full_size_other_configs(cfg):
+    """BASELINE configs 3 (non-central, ~1 M observations, 10 000 intrinsics) and 4 (2-camera rig,
+    ~1.9 M observations, 20 172 unknown intrinsics + rig) at full size: ground-truth cost at the
+    noise level, LM iterations accepted with decreasing cost, valid counts consistent."""
+    sp = synthetic.make_problem(cfg)
+    opt = cabi.default_options(max_iteration_count=2)
+    with api.BundleAdjuster(sp.problem) as adj:
+        adj.set_state(sp.gt_state)
+        e0 = adj.evaluate(opt)
+        valid = e0["costs"] >= 0
+        assert valid.mean() > 0.9999
+        rmse_gt = np.sqrt((e0["residuals"][valid] ** 2).sum() / valid.sum())
+        assert abs(rmse_gt - 0.05 * np.sqrt(2)) < 3e-3
+        st = sp.init_state.copy()
+        rep = adj.optimize_host(st, opt)
+        assert rep.num_iterations_performed == 2
+        c = rep.trace()[0]
+        assert c[0] < rep.initial_cost and c[1] < c[0]
+        assert 0 <= rep.n_invalid <= 50 and rep.n_valid + rep.n_invalid == sp.n_obs
+        t = adj.timings()
+        print(f"config {cfg}: n_obs {sp.n_obs} total {t.total_ms:.1f} ms jac {t.jacobian_kernel_ms:.3f} acc {t.accumulate_ms:.2f} "
+              f"schur {t.schur_ms:.1f} factor {t.factor_ms:.1f} trial {t.trial_cost_ms:.2f} straggler {t.straggler_ms:.2f}")
