@@ -468,7 +468,7 @@ static int jac_minb() {
 
 // Straggler pass geometry: a fixed grid that loops over the device-side list (its length is not
 // known on the host without a sync); 2 lanes per listed observation.
-constexpr int kStragglerBlocks = 296;
+constexpr int kStragglerBlocks = 1184;  // 8 per SM: the cold first pass (every projection starts at last_projection = 0) defers many observations
 constexpr int kStragglerThreads = 128;
 
 template <int MODEL, bool JAC, int MINB>
