@@ -352,3 +352,84 @@ def LoadBAState(base_path: str, dataset: Optional[Dataset] = None) -> Optional[B
     if dataset is not None:
         st.ComputeFeatureIdToPointsIndex(dataset)
     return st
+
+
+# ---------------------------------------------------------------------------------------
+# COLMAP text model (the --bundle_adjustment entry point)
+# ---------------------------------------------------------------------------------------
+def ReadColmapImages(images_txt_path: str, read_observations: bool = True):
+    """libvis/src/libvis/external_io/colmap_model.cc:96-142: two lines per image,
+    ``IMAGE_ID QW QX QY QZ TX TY TZ CAMERA_ID NAME`` then ``X Y POINT3D_ID ...``; values are
+    parsed into FLOAT (SE3f / Vector2f) like the reference. Returns {image_id: dict} or None."""
+    try:
+        lines = open(images_txt_path).read().split("\n")
+    except OSError:
+        return None
+    images = {}
+    i = 0
+    while i < len(lines):
+        line = lines[i]
+        i += 1
+        if len(line) == 0 or line[0] == "#":
+            continue
+        f = line.split()
+        q = np.array([f[1], f[2], f[3], f[4]], dtype=np.float32)
+        t = np.array([f[5], f[6], f[7]], dtype=np.float32)
+        obs_line = lines[i] if i < len(lines) else ""
+        i += 1
+        xy = np.zeros((0, 2), np.float32)
+        ids = np.zeros(0, np.int64)
+        if read_observations:
+            v = obs_line.split()
+            n = len(v) // 3
+            arr = np.array(v[:3 * n], dtype=np.float64).reshape(n, 3)
+            xy = arr[:, :2].astype(np.float32)
+            ids = arr[:, 2].astype(np.int64)
+        images[int(f[0])] = dict(image_id=int(f[0]), q=q, t=t, camera_id=int(f[8]), file_path=f[9] if len(f) > 9 else "",
+                                 xy=xy, point3d_id=ids)
+    return images
+
+
+def ReadColmapPoints3D(points3d_txt_path: str):
+    """colmap_model.cc:265-299: ``ID X Y Z R G B ERROR track...`` (positions float, tracks ignored)."""
+    try:
+        lines = open(points3d_txt_path).read().split("\n")
+    except OSError:
+        return None
+    pts = {}
+    for line in lines:
+        if len(line) == 0 or line[0] == "#":
+            continue
+        f = line.split()
+        pts[int(f[0])] = np.array(f[1:4], dtype=np.float32)
+    return pts
+
+
+def LoadColmapProblem(model: CameraModel, model_input_directory: str):
+    """tools/bundle_adjustment.cc:110-184: COLMAP text model -> (Dataset, BAState); images and
+    points are ordered by increasing id; observations without a 3D point (id -1) are dropped; the
+    single rig pose is the identity."""
+    images = ReadColmapImages(os.path.join(model_input_directory, "images.txt"), True)
+    points = ReadColmapPoints3D(os.path.join(model_input_directory, "points3D.txt"))
+    if images is None or points is None:
+        return None
+    ds = Dataset(1)
+    ds.SetImageSize(0, (model.width(), model.height()))
+    st = BAState()
+    st.intrinsics = [model]
+    st.camera_tr_rig = np.array([[1.0, 0, 0, 0, 0, 0, 0]])
+    ordered = [images[k] for k in sorted(images)]
+    st.image_used = [True] * len(ordered)
+    st.rig_tr_global = np.zeros((len(ordered), 7))
+    for i, im in enumerate(ordered):
+        q = im["q"].astype(np.float64)
+        st.rig_tr_global[i] = np.concatenate([q / np.linalg.norm(q), im["t"].astype(np.float64)])
+        s = ds.NewImageset()
+        s.SetFilename(im["file_path"])
+        keep = im["point3d_id"] >= 0
+        s.SetFeaturesOfCamera(0, im["xy"][keep], im["point3d_id"][keep].astype(np.int32))
+    ids = sorted(points)
+    st.points = np.array([points[k] for k in ids], dtype=np.float64).reshape(-1, 3)
+    st.feature_id_to_points_index = {k: i for i, k in enumerate(ids)}
+    st.ComputeFeatureIdToPointsIndex(ds)
+    return ds, st

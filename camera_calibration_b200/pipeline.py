@@ -1,0 +1,142 @@
+"""The callers either side of the hot path: the product's outer bundle-adjustment
+loop ``RunBundleAdjustment`` (applications/camera_calibration/src/camera_calibration/calibration.cc:187-304)
+with its per-iteration checkpoint and ``ChooseNiceCameraOrientation``
+(models/central_generic.cc:570-621). Host logic only; every numerical step (un-projection, the LM
+iteration) runs in ``libb200ba.so``.
+"""
+from __future__ import annotations
+
+import math
+from typing import Callable, List, Optional
+
+import numpy as np
+
+from . import api, synthetic
+from .api import BAState, CameraModel, CentralGenericModel, Dataset, SchurMode
+
+
+def _from_two_vectors(a: np.ndarray, b: np.ndarray) -> np.ndarray:
+    """Eigen::Quaterniond::FromTwoVectors(a, b) as a rotation matrix (rotates a onto b)."""
+    v0 = a / np.linalg.norm(a)
+    v1 = b / np.linalg.norm(b)
+    c = float(v1 @ v0)
+    if c < -1.0 + 1e-12:  # opposite vectors: any perpendicular axis (Eigen uses an SVD here)
+        axis = np.cross(v0, [1.0, 0, 0])
+        if np.linalg.norm(axis) < 1e-6:
+            axis = np.cross(v0, [0, 1.0, 0])
+        axis /= np.linalg.norm(axis)
+        q = np.array([0.0, *axis])
+    else:
+        axis = np.cross(v0, v1)
+        s = math.sqrt((1.0 + c) * 2.0)
+        q = np.array([0.5 * s, *(axis / s)])
+    return synthetic.quat_to_rot(q)
+
+
+def _rot_to_quat(R: np.ndarray) -> np.ndarray:
+    """Rotation matrix -> unit quaternion (w, x, y, z)."""
+    t = np.trace(R)
+    if t > 0:
+        s = math.sqrt(t + 1.0) * 2
+        q = np.array([0.25 * s, (R[2, 1] - R[1, 2]) / s, (R[0, 2] - R[2, 0]) / s, (R[1, 0] - R[0, 1]) / s])
+    else:
+        i = int(np.argmax(np.diag(R)))
+        j, k = (i + 1) % 3, (i + 2) % 3
+        s = math.sqrt(R[i, i] - R[j, j] - R[k, k] + 1.0) * 2
+        q = np.zeros(4)
+        q[0] = (R[k, j] - R[j, k]) / s
+        q[1 + i] = 0.25 * s
+        q[1 + j] = (R[j, i] + R[i, j]) / s
+        q[1 + k] = (R[k, i] + R[i, k]) / s
+    return q / np.linalg.norm(q)
+
+
+def ChooseNiceCameraOrientation(model: CameraModel) -> np.ndarray:
+    """Rotates the model such that +z looks forward at the image centre and +x points right;
+    returns the applied rotation (to be left-multiplied onto camera_tr_rig). Only the central
+    generic model implements it in the reference (central_generic.cc:570-621); the base class and
+    the non-central model return the identity (camera_model.h:120-122, noncentral_generic.h:128-132)."""
+    if not isinstance(model, CentralGenericModel):
+        return np.eye(3)
+    w, h = model.width(), model.height()
+    ok, forward, _ = model.Unproject(0.5 * w, 0.5 * h)
+    if not ok:
+        forward = np.array([0.0, 0, 1.0])
+    forward_rotation = _from_two_vectors(forward, np.array([0.0, 0, 1.0]))
+    right_min_x, right_max_x = min(w - 1, w // 2 + 11), w - 1
+    right_min_y, right_max_y = max(0, h // 2 - 10), min(h - 1, h // 2 + 10)
+    xs, ys = np.meshgrid(np.arange(right_min_x, right_max_x + 1), np.arange(right_min_y, right_max_y + 1))
+    px = np.stack([xs.ravel() + 0.5, ys.ravel() + 0.5], -1)
+    right_rotation = np.eye(3)
+    if len(px):
+        d, _, okm = model.UnprojectMany(px)
+        if okm.any():
+            frr = forward_rotation @ d[okm].mean(axis=0)
+            angle = math.atan2(-frr[1], frr[0])
+            c, s = math.cos(angle), math.sin(angle)
+            right_rotation = np.array([[c, -s, 0], [s, c, 0], [0, 0, 1.0]])
+    rotation = right_rotation @ forward_rotation
+    model.m_grid = model.m_grid @ rotation.T  # Rotate(): every direction d -> rotation * d
+    return rotation
+
+
+def RunBundleAdjustment(use_cuda: bool, schur_mode: SchurMode, max_iteration_count: int,
+                        cost_reduction_threshold: float, dataset: Dataset, state: BAState,
+                        regularization_weight: float, localize_only: bool,
+                        state_output_path: Optional[str] = None, eliminate_points: bool = False,
+                        on_iteration: Optional[Callable[[int, float], None]] = None) -> List[float]:
+    """calibration.cc:187-304: single LM iterations until the cost stops falling by more than
+    ``cost_reduction_threshold``; the state directory is rewritten after every iteration (the
+    reference's checkpoint / resume mechanism) and the cameras are re-oriented. Returns the cost
+    after each iteration. ``eliminate_points`` defaults to the product's choice (False)."""
+    numerical_diff_delta = 1e-4  # calibration.cc:201
+    lam = -1.0
+    last_cost = math.inf
+    costs: List[float] = []
+    for iteration in range(max_iteration_count):
+        if use_cuda:
+            report, lam = api.CudaOptimizeJointly(dataset, state, 1, 50, lam, numerical_diff_delta,
+                                                  regularization_weight, print_progress=False)
+            cost = report.final_cost
+        else:
+            cost, lam, _ = api.OptimizeJointly(dataset, state, 1, lam, numerical_diff_delta, regularization_weight,
+                                               localize_only, eliminate_points, schur_mode, print_progress=False)
+        costs.append(cost)
+        if state_output_path:
+            from . import io
+            io.SaveBAState(state_output_path, state)
+        if not localize_only:
+            for c in range(state.num_cameras()):
+                rotation = ChooseNiceCameraOrientation(state.intrinsics[c])
+                rt = np.concatenate([_rot_to_quat(rotation), np.zeros(3)])
+                state.camera_tr_rig[c] = synthetic.pose_mul(rt, state.camera_tr_rig[c])
+        if on_iteration:
+            on_iteration(iteration, cost)
+        if cost >= last_cost - cost_reduction_threshold:
+            break
+        last_cost = cost
+    return costs
+
+
+def BundleAdjustment(state_directory: str, model_input_directory: str, model_output_directory: str,
+                     max_iteration_count: int = 30) -> int:
+    """The ``--bundle_adjustment`` tool (tools/bundle_adjustment.cc:50-220): load
+    ``intrinsics0.yaml``, read a COLMAP text model, run <= 30 single LM iterations with
+    ``localize_only=true, eliminate_points=true`` and write the state directory + ``cost.txt``
+    (14 significant digits) after every iteration. Returns EXIT_SUCCESS / EXIT_FAILURE."""
+    import os
+    from . import io
+    model = io.LoadCameraModel(os.path.join(state_directory, "intrinsics0.yaml"))
+    if model is None:
+        return 1
+    loaded = io.LoadColmapProblem(model, model_input_directory)
+    if loaded is None:
+        return 1
+    dataset, state = loaded
+    lam = -1.0
+    for _ in range(max_iteration_count):
+        cost, lam, _ = api.OptimizeJointly(dataset, state, 1, lam, 1e-4, 0, True, True, SchurMode.Dense, print_progress=False)
+        io.SaveBAState(model_output_directory, state)
+        with open(os.path.join(model_output_directory, "cost.txt"), "w") as f:
+            f.write(f"{cost:.14g}\n")
+    return 0
