@@ -717,19 +717,24 @@ template <int MAXPAIRS>
 __global__ void __launch_bounds__(kCellThreads)
     accumulate_cells_kernel(ProblemDev pb, Layout L, ObsOut out, SystemDev sys, double huber) {
   extern __shared__ double smem[];
+  static_assert(kCellTile == 32, "one lane per observation of a tile");
   const int64_t n = pb.n_obs;
   const int64_t begin = static_cast<int64_t>(blockIdx.x) * kCellChunk;
   const int64_t end = min(n, begin + kCellChunk);
   const int rigE = L.rig_in_state ? 6 : 0;
-  const int Emax = rigE + L.Kmax;  // smem row length
-  double* sJx = smem;                         // [kCellTile][Emax]  sqrt(w) * J row x
-  double* sJy = sJx + kCellTile * Emax;       // [kCellTile][Emax]
-  double* sR = sJy + kCellTile * Emax;        // [kCellTile][2]     sqrt(w) * r
-  double* sPx = sR + 2 * kCellTile;           // [kCellTile][9]     sqrt(w) * J row x of [point 3 | pose 6]
-  double* sPy = sPx + 9 * kCellTile;          // [kCellTile][9]
+  const int Emax = rigE + L.Kmax;
+  const int S = Emax | 1;                  // odd row stride: lane-per-observation stores are conflict-free
+  double* sJx = smem;                      // [32][S]  sqrt(w) * J row x of [rig | intrinsics]
+  double* sJy = sJx + kCellTile * S;       // [32][S]
+  double* sR = sJy + kCellTile * S;        // [32][2]  sqrt(w) * r
+  double* sPx = sR + 2 * kCellTile;        // [32][9]  sqrt(w) * J row x of [point 3 | pose 6]
+  double* sPy = sPx + 9 * kCellTile;       // [32][9]
   __shared__ uint32_t sKey[kCellTile];
   __shared__ int sPoint[kCellTile];
   __shared__ int sIset[kCellTile];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr int kWarps = kCellThreads / 32;
+  constexpr int kSlots = (kMaxK + 31) / 32;  // intrinsics columns per lane
 
   double acc[MAXPAIRS];
   double accb = 0;
@@ -745,7 +750,8 @@ __global__ void __launch_bounds__(kCellThreads)
     const int cam = static_cast<int>(key >> 24);
     const int cell = static_cast<int>(key & 0xffffffu);
     const CamDev& c = pb.cams[cam];
-    const int E = rigE + c.K;
+    const int K = L.localize_only ? 0 : c.K;
+    const int E = rigE + K;
     const int npairs = E * (E + 1) / 2;
     // pair -> (i, j), i <= j, row-major over the upper triangle
 #pragma unroll
@@ -766,7 +772,14 @@ __global__ void __launch_bounds__(kCellThreads)
       pj[q] = j;
     }
     accb = 0;
-    // walk the run in tiles
+    // dense column (offset inside a row of B / C) of the intrinsics entries this lane covers
+    int gck[kSlots];
+#pragma unroll
+    for (int s = 0; s < kSlots; ++s) {
+      const int kk = lane + 32 * s;
+      gck[s] = (kk < K) ? (L.g_intr + intr_col(c, cell, kk) - L.nbd) : -1;
+    }
+    // walk the run in tiles of 32 observations (lane <-> observation while staging)
     bool run_done = false;
     while (!run_done && pos < end) {
       const int tile_n = static_cast<int>(min(static_cast<int64_t>(kCellTile), end - pos));
@@ -776,63 +789,66 @@ __global__ void __launch_bounds__(kCellThreads)
       int run_n = 0;
       while (run_n < tile_n && sKey[run_n] == key) ++run_n;
       if (run_n < tile_n) run_done = true;
-      // stage sqrt(w) * J of the run's observations (contiguous positions: coalesced per column)
-      for (int idx = threadIdx.x; idx < run_n * E; idx += kCellThreads) {
-        const int e = idx / run_n, t = idx - e * run_n;
-        const int64_t o = pos + t;
+      // stage sqrt(w) * J: warp <-> column, lane <-> observation (coalesced column reads)
+      if (lane < run_n) {
+        const int64_t o = pos + lane;
         const double rx = out.residual[o], ry = out.residual[n + o];
         const double sw = sqrt(huber_weight_sq(huber, rx * rx + ry * ry));
-        const int col = (e < rigE) ? (L.jc_rig + e) : (L.jc_intr + (e - rigE));
-        sJx[t * Emax + e] = sw * out.jac[(2 * static_cast<int64_t>(col)) * n + o];
-        sJy[t * Emax + e] = sw * out.jac[(2 * static_cast<int64_t>(col) + 1) * n + o];
-        if (e == 0) {
-          sR[2 * t] = sw * rx;
-          sR[2 * t + 1] = sw * ry;
+        for (int e = warp; e < E; e += kWarps) {
+          const int col = (e < rigE) ? (L.jc_rig + e) : (L.jc_intr + (e - rigE));
+          sJx[lane * S + e] = sw * out.jac[(2 * static_cast<int64_t>(col)) * n + o];
+          sJy[lane * S + e] = sw * out.jac[(2 * static_cast<int64_t>(col) + 1) * n + o];
         }
-      }
-      for (int idx = threadIdx.x; idx < run_n * 9; idx += kCellThreads) {
-        const int r9 = idx / run_n, t = idx - r9 * run_n;
-        const int64_t o = pos + t;
-        const double rx = out.residual[o], ry = out.residual[n + o];
-        const double sw = sqrt(huber_weight_sq(huber, rx * rx + ry * ry));
-        const int col = (r9 < 3) ? (L.jc_point + r9) : (L.jc_pose + (r9 - 3));
-        sPx[t * 9 + r9] = sw * out.jac[(2 * static_cast<int64_t>(col)) * n + o];
-        sPy[t * 9 + r9] = sw * out.jac[(2 * static_cast<int64_t>(col) + 1) * n + o];
-        if (r9 == 0) {
-          sPoint[t] = static_cast<int>(pb.obs_point[o]);
-          sIset[t] = static_cast<int>(pb.obs_imageset[o]);
+        for (int r9 = warp; r9 < 9; r9 += kWarps) {
+          const int col = (r9 < 3) ? (L.jc_point + r9) : (L.jc_pose + (r9 - 3));
+          sPx[lane * 9 + r9] = sw * out.jac[(2 * static_cast<int64_t>(col)) * n + o];
+          sPy[lane * 9 + r9] = sw * out.jac[(2 * static_cast<int64_t>(col) + 1) * n + o];
+        }
+        if (warp == 0) {
+          sR[2 * lane] = sw * rx;
+          sR[2 * lane + 1] = sw * ry;
+          sPoint[lane] = static_cast<int>(pb.obs_point[o]);
+          sIset[lane] = static_cast<int>(pb.obs_imageset[o]);
         }
       }
       __syncthreads();
-      // [point | pose] rows x intrinsics columns of the run: B[p, intr], C[pose, intr]. Consecutive
-      // lanes take consecutive intrinsics columns of ONE matrix row, so a warp-wide FP64 RED touches
-      // a few contiguous sectors instead of 32 scattered ones.
-      if (!L.localize_only) {
-        const int K = c.K;
-        for (int idx = threadIdx.x; idx < run_n * 9 * K; idx += kCellThreads) {
-          const int kk = idx % K;
-          const int rest = idx / K;
-          const int r9 = rest % 9, t = rest / 9;
-          const double v = fma(sPx[t * 9 + r9], sJx[t * Emax + rigE + kk], sPy[t * 9 + r9] * sJy[t * Emax + rigE + kk]);
-          const int gc = L.g_intr + intr_col(c, cell, kk);
-          const int gr = (r9 < 3) ? (L.g_point + 3 * sPoint[t] + r9) : (L.g_pose + 6 * sIset[t] + (r9 - 3));
-          add_H(L, sys, gr, gc, v);
+      // [point | pose] rows x intrinsics columns of the run. A warp takes one (observation, row)
+      // pair at a time and its lanes the consecutive intrinsics columns of that ONE matrix row:
+      // the warp-wide FP64 RED touches a few contiguous sectors instead of 32 scattered ones.
+      if (K > 0) {
+        for (int q = warp; q < run_n * 9; q += kWarps) {
+          const int t = q / 9, r9 = q - 9 * t;
+          const double px = sPx[t * 9 + r9], py = sPy[t * 9 + r9];
+          const int grow = (r9 < 3) ? (L.g_point + 3 * sPoint[t] + r9) : (L.g_pose + 6 * sIset[t] + (r9 - 3));
+          // intrinsics columns are dense and come last in both orderings: row < column always
+          double* rowp = (grow < L.nbd) ? (sys.B + static_cast<int64_t>(grow) * L.nd)
+                                        : (sys.C + static_cast<int64_t>(grow - L.nbd) * L.nd);
+          const double* jx = sJx + t * S + rigE;
+          const double* jy = sJy + t * S + rigE;
+#pragma unroll
+          for (int s = 0; s < kSlots; ++s) {
+            const int kk = lane + 32 * s;
+            if (kk < K) atomicAdd(rowp + gck[s], fma(px, jx[kk], py * jy[kk]));
+          }
         }
       }
+      // (rig U intrinsics)^2 and b: register accumulation over the run
 #pragma unroll
       for (int q = 0; q < MAXPAIRS; ++q) {
         if (threadIdx.x + q * kCellThreads < npairs) {
           double a = acc[q];
-          const int i = pi[q], j = pj[q];
-          for (int t = 0; t < run_n; ++t)
-            a = fma(sJx[t * Emax + i], sJx[t * Emax + j], fma(sJy[t * Emax + i], sJy[t * Emax + j], a));
+          const double* xi = sJx + pi[q];
+          const double* xj = sJx + pj[q];
+          const double* yi = sJy + pi[q];
+          const double* yj = sJy + pj[q];
+          for (int t = 0; t < run_n; ++t) a = fma(xi[t * S], xj[t * S], fma(yi[t * S], yj[t * S], a));
           acc[q] = a;
         }
       }
       if (threadIdx.x < E) {
         double a = accb;
         for (int t = 0; t < run_n; ++t)
-          a = fma(sJx[t * Emax + threadIdx.x], sR[2 * t], fma(sJy[t * Emax + threadIdx.x], sR[2 * t + 1], a));
+          a = fma(sJx[t * S + threadIdx.x], sR[2 * t], fma(sJy[t * S + threadIdx.x], sR[2 * t + 1], a));
         accb = a;
       }
       pos += run_n;
@@ -843,9 +859,12 @@ __global__ void __launch_bounds__(kCellThreads)
     };
 #pragma unroll
     for (int q = 0; q < MAXPAIRS; ++q) {
-      if (threadIdx.x + q * kCellThreads < npairs) add_H(L, sys, gcol(pi[q]), gcol(pj[q]), acc[q]);
+      if (threadIdx.x + q * kCellThreads < npairs) {
+        const int gi = gcol(pi[q]) - L.nbd, gj = gcol(pj[q]) - L.nbd;  // both dense, gi <= gj
+        atomicAdd(&sys.C[static_cast<int64_t>(gi) * L.nd + gj], acc[q]);
+      }
     }
-    if (threadIdx.x < E) add_b(L, sys, gcol(threadIdx.x), accb);
+    if (threadIdx.x < E) atomicAdd(&sys.bd[gcol(threadIdx.x) - L.nbd], accb);
   }
 }
 
@@ -857,7 +876,7 @@ void launch_accumulate_cells(const ProblemDev& pb, const Layout& L, const ObsOut
   if (Emax == 0) return;
   const int npairs = Emax * (Emax + 1) / 2;
   const int per_thread = (npairs + kCellThreads - 1) / kCellThreads;
-  const size_t smem = (2 * static_cast<size_t>(kCellTile) * Emax + 2 * kCellTile + 18 * kCellTile) * sizeof(double);
+  const size_t smem = (2 * static_cast<size_t>(kCellTile) * (Emax | 1) + 2 * kCellTile + 18 * kCellTile) * sizeof(double);
   const unsigned blocks = static_cast<unsigned>((pb.n_obs + kCellChunk - 1) / kCellChunk);
 #define B200BA_LAUNCH_CELLS(MP)                                                                              \
   do {                                                                                                       \
