@@ -44,7 +44,9 @@ def test_choose_nice_camera_orientation_keeps_the_cost():
         adj.set_state(fs)
         e1 = adj.evaluate(opt)
     assert abs(e1["total_cost"] - e0["total_cost"]) < 1e-7 * e0["total_cost"]
-    assert np.abs(e1["residuals"] - e0["residuals"]).max() < 1e-6
+    v = (e0["costs"] >= 0) & (e1["costs"] >= 0)  # invalid residuals are NaN
+    assert v.sum() >= len(v) - 2
+    assert np.abs(e1["residuals"][v] - e0["residuals"][v]).max() < 1e-6
 
 
 @pytest.mark.gpu
