@@ -126,6 +126,26 @@ struct b200ba_handle {
   double* h_scal = nullptr;  // pinned [16]
   int* h_flags = nullptr;    // pinned [2]
 
+  // host copies of the observations (caller's order) for layout-time block grouping
+  std::vector<uint32_t> h_obs_imageset, h_obs_camera, h_obs_point;
+  std::vector<float> h_obs_xy;
+  // structured Schur contraction (groups of Schur blocks with compacted column support)
+  int group_blocks_n = 0;                 // blocks per group
+  int n_groups = 0;
+  std::vector<int> group_start;           // [n_groups + 1] into group_blocks
+  std::vector<int> group_count;           // m_g of the current build
+  int* d_group_of_block = nullptr;
+  int* d_group_blocks = nullptr;
+  uint8_t* d_flags = nullptr;
+  int* d_cols = nullptr;
+  int* d_count = nullptr;
+  int* h_count = nullptr;                 // pinned
+  double* d_Wc = nullptr;
+  double* d_P = nullptr;
+  double* d_u = nullptr;
+  bool use_grouped = false;
+  int force_grouped = -1;                 // B200BA_GROUPED=0|1 overrides the cost model
+
   // multi-GPU
   void* comm = nullptr;
   int rank = 0, n_ranks = 1;
@@ -376,6 +396,59 @@ int make_layout(b200ba_handle* h, const b200ba_options* opt) {
   h->potrf_lwork = lwork;
   if (dev_alloc(h, &h->d_potrf_work, std::max(1, lwork))) return 1;
 
+  // ---- groups of Schur blocks for the structured contraction ------------------------------------
+  {
+    const int nb = L.nblocks;
+    int gb = (L.bs == 3) ? 64 : 32;
+    if (const char* e = getenv("B200BA_GROUP_BLOCKS")) gb = std::max(1, atoi(e));
+    h->group_blocks_n = gb;
+    std::vector<int> order(nb);
+    for (int i = 0; i < nb; ++i) order[i] = i;
+    if (L.eliminate_points && h->n_obs > 0) {
+      // order the pattern points along a Z-curve of the centroid of their measured pixels: points
+      // that are neighbours in the image share most of their control-point support
+      std::vector<double> sx(nb, 0.0), sy(nb, 0.0);
+      std::vector<int> cnt(nb, 0);
+      for (int64_t o = 0; o < h->n_obs; ++o) {
+        const int p = static_cast<int>(h->h_obs_point[o]);
+        sx[p] += h->h_obs_xy[2 * o];
+        sy[p] += h->h_obs_xy[2 * o + 1];
+        cnt[p]++;
+      }
+      const double qx = std::max(1.0, h->cams_host[0].width / 64.0), qy = std::max(1.0, h->cams_host[0].height / 64.0);
+      std::vector<uint32_t> zkey(nb, 0);
+      for (int p = 0; p < nb; ++p) {
+        if (!cnt[p]) continue;
+        uint32_t ux = static_cast<uint32_t>(std::min(1023.0, std::max(0.0, sx[p] / cnt[p] / qx)));
+        uint32_t uy = static_cast<uint32_t>(std::min(1023.0, std::max(0.0, sy[p] / cnt[p] / qy)));
+        uint32_t z = 0;
+        for (int b = 0; b < 10; ++b) z |= ((ux >> b) & 1u) << (2 * b) | ((uy >> b) & 1u) << (2 * b + 1);
+        zkey[p] = z;
+      }
+      std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return zkey[a] < zkey[b]; });
+    }
+    h->n_groups = (nb + gb - 1) / gb;
+    h->group_start.assign(h->n_groups + 1, 0);
+    std::vector<int> gob(std::max(1, nb), 0);
+    for (int g = 0; g < h->n_groups; ++g) {
+      h->group_start[g] = g * gb;
+      for (int i = g * gb; i < std::min(nb, (g + 1) * gb); ++i) gob[order[i]] = g;
+    }
+    h->group_start[h->n_groups] = nb;
+    h->group_count.assign(std::max(1, h->n_groups), 0);
+    if (dev_alloc(h, &h->d_group_of_block, std::max(1, nb))) return 1;
+    if (dev_alloc(h, &h->d_group_blocks, std::max(1, nb))) return 1;
+    CUDA_TRY(h, cudaMemcpy(h->d_group_of_block, gob.data(), std::max(1, nb) * sizeof(int), cudaMemcpyHostToDevice));
+    if (nb > 0) CUDA_TRY(h, cudaMemcpy(h->d_group_blocks, order.data(), nb * sizeof(int), cudaMemcpyHostToDevice));
+    if (dev_alloc(h, &h->d_flags, static_cast<size_t>(std::max(1, h->n_groups)) * std::max(1, L.nd))) return 1;
+    if (dev_alloc(h, &h->d_cols, static_cast<size_t>(std::max(1, h->n_groups)) * std::max(1, L.nd))) return 1;
+    if (dev_alloc(h, &h->d_count, std::max(1, h->n_groups))) return 1;
+    if (h->h_count) cudaFreeHost(h->h_count);
+    CUDA_TRY(h, cudaMallocHost(reinterpret_cast<void**>(&h->h_count), std::max(1, h->n_groups) * sizeof(int)));
+    if (dev_alloc(h, &h->d_Wc, static_cast<size_t>(gb) * L.bs * std::max(1, L.nd))) return 1;
+    if (dev_alloc(h, &h->d_P, static_cast<size_t>(std::max(1, L.nd)) * std::max(1, L.nd))) return 1;
+    if (dev_alloc(h, &h->d_u, std::max(1, L.nbd))) return 1;
+  }
   return 0;
 }
 
@@ -452,10 +525,32 @@ int build_system(b200ba_handle* h, double huber, double* cost, double* n_valid) 
   // ONE all-reduce per build covers D, b_p, B, b_d, the cost scalars and the trace
   if (all_reduce(h, h->sys.base, static_cast<size_t>(h->reduce_count))) return 1;
   CUDA_TRY(h, cudaMemcpyAsync(h->h_scal, h->sys.scalars, 9 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  if (h->n_groups > 0 && h->L.nd > 0 && h->force_grouped != 0) {
+    // exact column support of every group of Schur blocks, from the (global) B itself
+    ScopedPhase ph(h, PH_SCHUR);
+    CUDA_TRY(h, cudaMemsetAsync(h->d_flags, 0, static_cast<size_t>(h->n_groups) * h->L.nd, h->stream));
+    launch_group_support(h->L.bs, h->L.nblocks, h->L.nd, h->sys.B, h->d_group_of_block, h->d_flags, h->stream);
+    launch_compact_columns(h->n_groups, h->L.nd, h->d_flags, h->d_cols, h->d_count, h->stream);
+    CUDA_TRY(h, cudaMemcpyAsync(h->h_count, h->d_count, h->n_groups * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    h->timings.kernel_launches += 2;
+  }
   if (sync_stream(h)) return 1;
   *cost = h->h_scal[3];
   *n_valid = h->h_scal[4];
   h->trace_H = h->h_scal[8];
+  // cost model: grouped contraction sum_g k_g m_g^2 (+ scatter) against the dense n_d^2 * nbd
+  h->use_grouped = false;
+  if (h->n_groups > 0 && h->L.nd > 0 && h->force_grouped != 0) {
+    double grouped = 0;
+    for (int g = 0; g < h->n_groups; ++g) {
+      const double kg = static_cast<double>(h->group_start[g + 1] - h->group_start[g]) * h->L.bs;
+      const double mg = h->h_count[g];
+      h->group_count[g] = h->h_count[g];
+      grouped += mg * mg * (kg + 24.0);  // + ~24 flop-equivalents per scattered entry
+    }
+    const double dense = static_cast<double>(h->L.nd) * h->L.nd * h->L.nbd;
+    h->use_grouped = (h->force_grouped == 1) || grouped < 0.6 * dense;
+  }
   return 0;
 }
 
@@ -464,43 +559,82 @@ int build_system(b200ba_handle* h, double huber, double* cost, double* n_valid) 
 int solve_system(b200ba_handle* h, double lambda, int* spd) {
   const Layout& L = h->L;
   const double one = 1.0, minus_one = -1.0;
-  // Point range of this rank for the contraction: S = sum_r (C_r - W_r^T W_r) + lambda I, where
-  // C_r is the rank's partial dense block and W_r the rows of W = L^-1 B of its points (B, D are
-  // global after the per-build all-reduce). With one rank this is the plain S = C + lambda I - W^T W.
-  const int p0 = static_cast<int>(static_cast<int64_t>(L.nblocks) * h->rank / h->n_ranks);
-  const int p1 = static_cast<int>(static_cast<int64_t>(L.nblocks) * (h->rank + 1) / h->n_ranks);
-  const int k_rows = L.bs * (p1 - p0);
-  double* rhs_tail = h->d_S + static_cast<size_t>(L.nd) * L.nd;
-  {
+  bool grouped_done = false;
+  if (h->use_grouped) {
+    // ---- structured contraction: per group gather -> compact rank-k update -> scatter ----------
     ScopedPhase ph(h, PH_SCHUR);
+    const double zero = 0.0;
     CUDA_TRY(h, cudaMemsetAsync(h->d_fail, 0, sizeof(int), h->stream));
     launch_schur_blocks(L.bs, L.nblocks, h->sys.Dblk, h->sys.bp, lambda, h->d_Linv, h->d_v, h->d_fail, h->stream);
-    launch_schur_scale_rows(L.bs, L.nblocks, L.nd, h->sys.B, h->d_Linv, h->d_W, h->stream);
+    launch_block_solve_t(L.bs, L.nblocks, h->d_Linv, h->d_v, h->d_u, h->stream);  // u = D^-1 b_block
     CUDA_TRY(h, cudaMemcpyAsync(h->d_S, h->sys.C, static_cast<size_t>(L.nd) * L.nd * sizeof(double),
                                 cudaMemcpyDeviceToDevice, h->stream));
-    CUDA_TRY(h, cudaMemsetAsync(rhs_tail, 0, L.nd * sizeof(double), h->stream));
     h->timings.kernel_launches += 2;
-    if (k_rows > 0 && L.nd > 0) {
-      const double zero = 0.0;
-      const double* Wr = h->d_W + static_cast<size_t>(L.bs) * p0 * L.nd;
-      // row-major W [nbd x nd] is the column-major nd x nbd matrix W^T: S -= W_r^T W_r (lower)
-      CUBLAS_TRY(h, cublasDsyrk(h->cublas, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_N, L.nd, k_rows, &minus_one, Wr, L.nd,
-                                &one, h->d_S, L.nd));
-      // partial reduced right-hand side: -W_r^T v_r
-      CUBLAS_TRY(h, cublasDgemv(h->cublas, CUBLAS_OP_N, L.nd, k_rows, &minus_one, Wr, L.nd, h->d_v + L.bs * p0, 1, &zero,
-                                rhs_tail, 1));
+    for (int g = h->rank; g < h->n_groups; g += h->n_ranks) {
+      const int nblk = h->group_start[g + 1] - h->group_start[g];
+      const int kg = nblk * L.bs, mg = h->group_count[g];
+      if (mg == 0 || kg == 0) continue;
+      const int* cols = h->d_cols + static_cast<size_t>(g) * L.nd;
+      launch_gather_scale(L.bs, nblk, L.nd, mg, h->sys.B, h->d_Linv, h->d_group_blocks + h->group_start[g], cols, h->d_Wc,
+                          h->stream);
+      // row-major Wc [kg x mg] is the column-major mg x kg panel: P = Wc^T Wc (lower)
+      CUBLAS_TRY(h, cublasDsyrk(h->cublas, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_N, mg, kg, &one, h->d_Wc, mg, &zero, h->d_P, mg));
+      launch_scatter_sub(L.nd, mg, cols, h->d_P, h->d_S, h->stream);
+      h->timings.kernel_launches += 2;
     }
+    grouped_done = true;
   }
-  if (h->n_ranks > 1) {
-    if (all_reduce(h, h->d_S, static_cast<size_t>(L.nd) * L.nd + L.nd)) return 1;
-  }
-  {
+  if (grouped_done) {
+    if (h->n_ranks > 1) {
+      if (all_reduce(h, h->d_S, static_cast<size_t>(L.nd) * L.nd)) return 1;
+    }
     ScopedPhase ph(h, PH_SCHUR);
     launch_add_diagonal(L.nd, h->d_S, L.nd, lambda, h->stream);
-    // x_dense <- b_d - W^T v
+    // x_dense <- b_d - B^T u   (B is global after the per-build all-reduce: no partial sums here)
     CUDA_TRY(h, cudaMemcpyAsync(h->d_x + L.nbd, h->sys.bd, L.nd * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
-    CUBLAS_TRY(h, cublasDaxpy(h->cublas, L.nd, &one, rhs_tail, 1, h->d_x + L.nbd, 1));
+    if (L.nbd > 0 && L.nd > 0)
+      CUBLAS_TRY(h, cublasDgemv(h->cublas, CUBLAS_OP_N, L.nd, L.nbd, &minus_one, h->sys.B, L.nd, h->d_u, 1, &one,
+                                h->d_x + L.nbd, 1));
     h->timings.kernel_launches += 1;
+  } else {
+    // Point range of this rank for the contraction: S = sum_r (C_r - W_r^T W_r) + lambda I, where
+    // C_r is the rank's partial dense block and W_r the rows of W = L^-1 B of its points (B, D are
+    // global after the per-build all-reduce). With one rank this is the plain S = C + lambda I - W^T W.
+    const int p0 = static_cast<int>(static_cast<int64_t>(L.nblocks) * h->rank / h->n_ranks);
+    const int p1 = static_cast<int>(static_cast<int64_t>(L.nblocks) * (h->rank + 1) / h->n_ranks);
+    const int k_rows = L.bs * (p1 - p0);
+    double* rhs_tail = h->d_S + static_cast<size_t>(L.nd) * L.nd;
+    {
+      ScopedPhase ph(h, PH_SCHUR);
+      CUDA_TRY(h, cudaMemsetAsync(h->d_fail, 0, sizeof(int), h->stream));
+      launch_schur_blocks(L.bs, L.nblocks, h->sys.Dblk, h->sys.bp, lambda, h->d_Linv, h->d_v, h->d_fail, h->stream);
+      launch_schur_scale_rows(L.bs, L.nblocks, L.nd, h->sys.B, h->d_Linv, h->d_W, h->stream);
+      CUDA_TRY(h, cudaMemcpyAsync(h->d_S, h->sys.C, static_cast<size_t>(L.nd) * L.nd * sizeof(double),
+                                  cudaMemcpyDeviceToDevice, h->stream));
+      CUDA_TRY(h, cudaMemsetAsync(rhs_tail, 0, L.nd * sizeof(double), h->stream));
+      h->timings.kernel_launches += 2;
+      if (k_rows > 0 && L.nd > 0) {
+        const double zero = 0.0;
+        const double* Wr = h->d_W + static_cast<size_t>(L.bs) * p0 * L.nd;
+        // row-major W [nbd x nd] is the column-major nd x nbd matrix W^T: S -= W_r^T W_r (lower)
+        CUBLAS_TRY(h, cublasDsyrk(h->cublas, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_N, L.nd, k_rows, &minus_one, Wr, L.nd,
+                                  &one, h->d_S, L.nd));
+        // partial reduced right-hand side: -W_r^T v_r
+        CUBLAS_TRY(h, cublasDgemv(h->cublas, CUBLAS_OP_N, L.nd, k_rows, &minus_one, Wr, L.nd, h->d_v + L.bs * p0, 1, &zero,
+                                  rhs_tail, 1));
+      }
+    }
+    if (h->n_ranks > 1) {
+      if (all_reduce(h, h->d_S, static_cast<size_t>(L.nd) * L.nd + L.nd)) return 1;
+    }
+    {
+      ScopedPhase ph(h, PH_SCHUR);
+      launch_add_diagonal(L.nd, h->d_S, L.nd, lambda, h->stream);
+      // x_dense <- b_d - W^T v
+      CUDA_TRY(h, cudaMemcpyAsync(h->d_x + L.nbd, h->sys.bd, L.nd * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+      CUBLAS_TRY(h, cublasDaxpy(h->cublas, L.nd, &one, rhs_tail, 1, h->d_x + L.nbd, 1));
+      h->timings.kernel_launches += 1;
+    }
   }
   {
     ScopedPhase ph(h, PH_FACTOR);
@@ -509,7 +643,16 @@ int solve_system(b200ba_handle* h, double lambda, int* spd) {
     CUSOLVER_TRY(h, cusolverDnDpotrs(h->cusolver, CUBLAS_FILL_MODE_LOWER, L.nd, 1, h->d_S, L.nd, h->d_x + L.nbd, L.nd,
                                      h->d_info + 1));
   }
-  {
+  if (grouped_done) {
+    ScopedPhase ph(h, PH_SCHUR);
+    // t = B x_d ; x_block = u - D^-1 t   (W is never materialised on this path)
+    const double zero = 0.0;
+    if (L.nbd > 0 && L.nd > 0)
+      CUBLAS_TRY(h, cublasDgemv(h->cublas, CUBLAS_OP_T, L.nd, L.nbd, &one, h->sys.B, L.nd, h->d_x + L.nbd, 1, &zero,
+                                h->d_y, 1));
+    launch_block_backsub2(L.bs, L.nblocks, h->d_Linv, h->d_u, h->d_y, h->d_x, h->stream);
+    h->timings.kernel_launches += 1;
+  } else {
     ScopedPhase ph(h, PH_SCHUR);
     // y = v - W x_d ; x_p = L^-T y
     CUDA_TRY(h, cudaMemcpyAsync(h->d_y, h->d_v, L.nbd * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
@@ -555,6 +698,9 @@ void free_handle_buffers(b200ba_handle* h) {
   F(h->out_trial.residual); F(h->out_trial.cost);
   F(h->sys.base); F(h->d_W); F(h->d_S); F(h->d_Linv); F(h->d_v); F(h->d_y); F(h->d_x); F(h->d_potrf_work);
   F(h->d_info); F(h->d_fail); F(h->d_straggler_list); F(h->d_straggler_count); F(h->d_perm); F(h->d_lp_stage);
+  F(h->d_group_of_block); F(h->d_group_blocks); F(h->d_flags); F(h->d_cols); F(h->d_count); F(h->d_Wc); F(h->d_P); F(h->d_u);
+  if (h->h_count) cudaFreeHost(h->h_count);
+  h->h_count = nullptr;
   F(h->d_partial); F(h->d_scal);
   if (h->h_scal) cudaFreeHost(h->h_scal);
   if (h->h_flags) cudaFreeHost(h->h_flags);
@@ -733,6 +879,13 @@ int b200ba_create(const b200ba_problem* p, int device, b200ba_handle** out) {
     TRYC(cuda_ok(cudaMemcpy(h->d_perm, h->perm.data(), n * sizeof(uint32_t), cudaMemcpyHostToDevice), "H2D"));
   }
   TRYC(dev_alloc(h, &h->d_lp_stage, n));
+  if (n > 0) {
+    h->h_obs_imageset.assign(p->obs_imageset, p->obs_imageset + n);
+    h->h_obs_camera.assign(p->obs_camera, p->obs_camera + n);
+    h->h_obs_point.assign(p->obs_point, p->obs_point + n);
+    h->h_obs_xy.assign(p->obs_xy, p->obs_xy + 2 * n);
+  }
+  if (const char* e = getenv("B200BA_GROUPED")) h->force_grouped = atoi(e);
   h->pb.n_obs = n;
   h->pb.obs_imageset = h->d_obs_imageset;
   h->pb.obs_camera = h->d_obs_camera;

@@ -27,6 +27,15 @@ void launch_schur_blocks(int bs, int n_blocks, const double* Dblk, const double*
 void launch_schur_scale_rows(int bs, int n_blocks, int nd, const double* B, const double* Linv, double* W,
                              cudaStream_t s);
 void launch_schur_backsub(int bs, int n_blocks, const double* Linv, const double* y, double* xp, cudaStream_t s);
+void launch_group_support(int bs, int nblocks, int nd, const double* B, const int* group_of_block, uint8_t* flags,
+                          cudaStream_t s);
+void launch_compact_columns(int ngroups, int nd, const uint8_t* flags, int* cols, int* count, cudaStream_t s);
+void launch_gather_scale(int bs, int nblocks_in_group, int nd, int m, const double* B, const double* Linv,
+                         const int* blocks, const int* cols, double* Wc, cudaStream_t s);
+void launch_scatter_sub(int nd, int m, const int* cols, const double* P, double* S, cudaStream_t s);
+void launch_block_solve_t(int bs, int n_blocks, const double* Linv, const double* v, double* u, cudaStream_t s);
+void launch_block_backsub2(int bs, int n_blocks, const double* Linv, const double* u, const double* t, double* xb,
+                           cudaStream_t s);
 void launch_add_diagonal(int n, double* M, int64_t ld, double lambda, cudaStream_t s);
 void launch_trace(int n_blocks, int bs, const double* Dblk, int nd, const double* C, double* out, cudaStream_t s);
 void launch_update_state(const ProblemDev& pb, const Layout& L, const StateDev& src, const StateDev& dst,

@@ -16,6 +16,10 @@ def main():
     dist = distributed.init_process_group("nccl")
     torch.cuda.set_device(local)
     worst = 0.0
+    # second sweep with the structured (grouped) Schur contraction forced on
+    if os.environ.get("MGPU_FORCE_GROUPED"):
+        os.environ["B200BA_GROUPED"] = "1"
+        os.environ["B200BA_GROUP_BLOCKS"] = "7"
     for cfg, kw in ((2, dict(n_imagesets=12, lattice=(12, 10), image_size=(410, 290))),
                     (4, dict(n_imagesets=10, lattice=(10, 8), image_size=(410, 290))),
                     (1, dict(n_imagesets=8, lattice=(10, 10)))):

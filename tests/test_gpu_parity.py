@@ -310,6 +310,10 @@ def test_multi_gpu_matches_single_gpu():
            "127.0.0.1", "--master-port", "29533", os.path.join(root, "tests", "mgpu_check.py")]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
     assert r.returncode == 0 and "MGPU_OK" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
+    env = dict(os.environ, MGPU_FORCE_GROUPED="1")
+    cmd[cmd.index("29533")] = "29534"
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, env=env)
+    assert r.returncode == 0 and "MGPU_OK" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
 
 
 def test_straggler_pass_equals_main_pass(oracle_lib):
@@ -364,3 +368,27 @@ def test_full_size_other_configs(cfg):
         t = adj.timings()
         print(f"config {cfg}: n_obs {sp.n_obs} total {t.total_ms:.1f} ms jac {t.jacobian_kernel_ms:.3f} acc {t.accumulate_ms:.2f} "
               f"schur {t.schur_ms:.1f} factor {t.factor_ms:.1f} trial {t.trial_cost_ms:.2f} straggler {t.straggler_ms:.2f}")
+
+
+@pytest.mark.parametrize("cfg,eliminate_points", [(2, 1), (4, 1), (3, 1), (1, 1), (2, 0)])
+def test_structured_contraction_equals_dense(oracle_lib, cfg, eliminate_points, monkeypatch):
+    """The grouped, support-compacted Schur contraction (exact zeros of B skipped) must give the
+    LM loop of the dense contraction: forced on (B200BA_GROUPED=1) vs forced off (=0) vs oracle."""
+    sp = _small(cfg)
+    opt = cabi.default_options(max_iteration_count=5, eliminate_points=eliminate_points)
+    reps, states = [], []
+    for mode in ("1", "0"):
+        monkeypatch.setenv("B200BA_GROUPED", mode)
+        monkeypatch.setenv("B200BA_GROUP_BLOCKS", "7")  # several uneven groups on the small problems
+        st = sp.init_state.copy()
+        with api.BundleAdjuster(sp.problem) as adj:
+            reps.append(adj.optimize_host(st, opt))
+        states.append(st)
+    assert reps[0].trace()[2] == reps[1].trace()[2]
+    assert np.allclose(reps[0].trace()[0], reps[1].trace()[0], rtol=1e-9)
+    assert np.abs(states[0].points - states[1].points).max() < 1e-9
+    for a, b in zip(states[0].intrinsics, states[1].intrinsics):
+        assert np.abs(a - b).max() < 1e-9
+    _, orep = oracle_lib.optimize(sp.problem, sp.init_state, opt)
+    assert reps[0].trace()[2] == orep.trace()[2]
+    assert np.allclose(reps[0].trace()[0], orep.trace()[0], rtol=1e-7)
