@@ -140,8 +140,10 @@ struct b200ba_handle {
   int* d_cols = nullptr;
   int* d_count = nullptr;
   int* h_count = nullptr;                 // pinned
-  double* d_Wc = nullptr;
-  double* d_P = nullptr;
+  double* d_Wc = nullptr;                 // 2 panels (double-buffered)
+  double* d_P = nullptr;                  // 2 result buffers (double-buffered)
+  size_t wc_stride = 0, p_stride = 0;
+  cudaEvent_t ev_syrk[2] = {nullptr, nullptr}, ev_scatter[2] = {nullptr, nullptr}, ev_s_ready = nullptr;
   double* d_u = nullptr;
   bool use_grouped = false;
   int force_grouped = -1;                 // B200BA_GROUPED=0|1 overrides the cost model
@@ -399,7 +401,7 @@ int make_layout(b200ba_handle* h, const b200ba_options* opt) {
   // ---- groups of Schur blocks for the structured contraction ------------------------------------
   {
     const int nb = L.nblocks;
-    int gb = (L.bs == 3) ? 64 : 32;
+    int gb = (L.bs == 3) ? 96 : 48;  // ~288 rows per group: measured optimum on B200 (config 2: 64 -> 12.0 ms, 96 -> 11.6 ms, 160 -> 11.7 ms)
     if (const char* e = getenv("B200BA_GROUP_BLOCKS")) gb = std::max(1, atoi(e));
     h->group_blocks_n = gb;
     std::vector<int> order(nb);
@@ -445,8 +447,15 @@ int make_layout(b200ba_handle* h, const b200ba_options* opt) {
     if (dev_alloc(h, &h->d_count, std::max(1, h->n_groups))) return 1;
     if (h->h_count) cudaFreeHost(h->h_count);
     CUDA_TRY(h, cudaMallocHost(reinterpret_cast<void**>(&h->h_count), std::max(1, h->n_groups) * sizeof(int)));
-    if (dev_alloc(h, &h->d_Wc, static_cast<size_t>(gb) * L.bs * std::max(1, L.nd))) return 1;
-    if (dev_alloc(h, &h->d_P, static_cast<size_t>(std::max(1, L.nd)) * std::max(1, L.nd))) return 1;
+    h->wc_stride = static_cast<size_t>(gb) * L.bs * std::max(1, L.nd);
+    h->p_stride = static_cast<size_t>(std::max(1, L.nd)) * std::max(1, L.nd);
+    if (dev_alloc(h, &h->d_Wc, 2 * h->wc_stride)) return 1;
+    if (dev_alloc(h, &h->d_P, 2 * h->p_stride)) return 1;
+    for (int i = 0; i < 2; ++i) {
+      if (!h->ev_syrk[i]) CUDA_TRY(h, cudaEventCreateWithFlags(&h->ev_syrk[i], cudaEventDisableTiming));
+      if (!h->ev_scatter[i]) CUDA_TRY(h, cudaEventCreateWithFlags(&h->ev_scatter[i], cudaEventDisableTiming));
+    }
+    if (!h->ev_s_ready) CUDA_TRY(h, cudaEventCreateWithFlags(&h->ev_s_ready, cudaEventDisableTiming));
     if (dev_alloc(h, &h->d_u, std::max(1, L.nbd))) return 1;
   }
   return 0;
@@ -570,18 +579,34 @@ int solve_system(b200ba_handle* h, double lambda, int* spd) {
     CUDA_TRY(h, cudaMemcpyAsync(h->d_S, h->sys.C, static_cast<size_t>(L.nd) * L.nd * sizeof(double),
                                 cudaMemcpyDeviceToDevice, h->stream));
     h->timings.kernel_launches += 2;
+    // The compact rank-k updates (compute-bound, main stream) and the scatters into S (memory-
+    // bound, side stream) are software-pipelined over two P / Wc buffers. All scatters run on the
+    // side stream, hence in order: plain read-modify-write, no atomics.
+    CUDA_TRY(h, cudaEventRecord(h->ev_s_ready, h->stream));          // S = C_r is in place
+    CUDA_TRY(h, cudaStreamWaitEvent(h->side_stream, h->ev_s_ready, 0));
+    int it = 0;
     for (int g = h->rank; g < h->n_groups; g += h->n_ranks) {
       const int nblk = h->group_start[g + 1] - h->group_start[g];
       const int kg = nblk * L.bs, mg = h->group_count[g];
       if (mg == 0 || kg == 0) continue;
+      const int b = it & 1;
+      double* Wc = h->d_Wc + b * h->wc_stride;
+      double* P = h->d_P + b * h->p_stride;
       const int* cols = h->d_cols + static_cast<size_t>(g) * L.nd;
-      launch_gather_scale(L.bs, nblk, L.nd, mg, h->sys.B, h->d_Linv, h->d_group_blocks + h->group_start[g], cols, h->d_Wc,
+      if (it >= 2) CUDA_TRY(h, cudaStreamWaitEvent(h->stream, h->ev_scatter[b], 0));  // buffer b is free again
+      launch_gather_scale(L.bs, nblk, L.nd, mg, h->sys.B, h->d_Linv, h->d_group_blocks + h->group_start[g], cols, Wc,
                           h->stream);
       // row-major Wc [kg x mg] is the column-major mg x kg panel: P = Wc^T Wc (lower)
-      CUBLAS_TRY(h, cublasDsyrk(h->cublas, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_N, mg, kg, &one, h->d_Wc, mg, &zero, h->d_P, mg));
-      launch_scatter_sub(L.nd, mg, cols, h->d_P, h->d_S, h->stream);
+      CUBLAS_TRY(h, cublasDsyrk(h->cublas, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_N, mg, kg, &one, Wc, mg, &zero, P, mg));
+      CUDA_TRY(h, cudaEventRecord(h->ev_syrk[b], h->stream));
+      CUDA_TRY(h, cudaStreamWaitEvent(h->side_stream, h->ev_syrk[b], 0));
+      launch_scatter_sub(L.nd, mg, cols, P, h->d_S, h->side_stream);
+      CUDA_TRY(h, cudaEventRecord(h->ev_scatter[b], h->side_stream));
       h->timings.kernel_launches += 2;
+      ++it;
     }
+    // join: every scatter has landed before S is used
+    for (int b = 0; b < 2 && b < it; ++b) CUDA_TRY(h, cudaStreamWaitEvent(h->stream, h->ev_scatter[b], 0));
     grouped_done = true;
   }
   if (grouped_done) {
