@@ -146,6 +146,7 @@ struct b200ba_handle {
   cudaEvent_t ev_syrk[2] = {nullptr, nullptr}, ev_scatter[2] = {nullptr, nullptr}, ev_s_ready = nullptr;
   double* d_u = nullptr;
   bool use_grouped = false;
+  std::vector<double> grp_sums;           // [sx | sy | count] per Schur block (see build_groups)
   int force_grouped = -1;                 // B200BA_GROUPED=0|1 overrides the cost model
 
   // multi-GPU
@@ -296,6 +297,85 @@ void resolve_timings(b200ba_handle* h) {
   }
   h->pending.clear();
 }
+// All-reduces the centroid sums over the ranks (no-op without a communicator).
+int reduce_group_sums(b200ba_handle* h) {
+  if (h->n_ranks <= 1 || !h->comm || h->grp_sums.empty()) return 0;
+  const size_t n = h->grp_sums.size();
+  double* d = nullptr;
+  CUDA_TRY(h, cudaMalloc(reinterpret_cast<void**>(&d), n * sizeof(double)));
+  cudaMemcpy(d, h->grp_sums.data(), n * sizeof(double), cudaMemcpyHostToDevice);
+  const int rc = g_nccl.AllReduce(d, d, n, kNcclDouble, kNcclSum, h->comm, h->stream);
+  const cudaError_t ce = cudaStreamSynchronize(h->stream);
+  if (rc == 0 && ce == cudaSuccess) cudaMemcpy(h->grp_sums.data(), d, n * sizeof(double), cudaMemcpyDeviceToHost);
+  cudaFree(d);
+  if (rc != 0 || ce != cudaSuccess) {
+    h->error = "all-reduce of the group centroids failed";
+    return 1;
+  }
+  return 0;
+}
+
+// Groups of Schur blocks for the structured contraction, from the centroid sums in h->grp_sums
+// ([sx | sy | count] per block). Must produce the same grouping on every rank: the ranks split
+// the GROUPS among themselves (solve_system), so a rank-dependent order would drop / repeat blocks.
+int build_groups(b200ba_handle* h, bool allocate) {
+  const Layout& L = h->L;
+  const int nb = L.nblocks;
+  int gb = (L.bs == 3) ? 96 : 48;  // ~288 rows per group: measured optimum on B200 (config 2: 64 -> 12.0 ms, 96 -> 11.6 ms, 160 -> 11.7 ms)
+  if (const char* e = getenv("B200BA_GROUP_BLOCKS")) gb = std::max(1, atoi(e));
+  h->group_blocks_n = gb;
+  std::vector<int> order(nb);
+  for (int i = 0; i < nb; ++i) order[i] = i;
+  if (L.eliminate_points && nb > 0) {
+    // order the pattern points along a Z-curve of the centroid of their measured pixels: points
+    // that are neighbours in the image share most of their control-point support
+    const double* sx = h->grp_sums.data();
+    const double* sy = sx + nb;
+    const double* cnt = sy + nb;
+    const double qx = std::max(1.0, h->cams_host[0].width / 64.0), qy = std::max(1.0, h->cams_host[0].height / 64.0);
+    std::vector<uint32_t> zkey(nb, 0);
+    for (int p = 0; p < nb; ++p) {
+      if (cnt[p] <= 0) continue;
+      uint32_t ux = static_cast<uint32_t>(std::min(1023.0, std::max(0.0, sx[p] / cnt[p] / qx)));
+      uint32_t uy = static_cast<uint32_t>(std::min(1023.0, std::max(0.0, sy[p] / cnt[p] / qy)));
+      uint32_t z = 0;
+      for (int b = 0; b < 10; ++b) z |= ((ux >> b) & 1u) << (2 * b) | ((uy >> b) & 1u) << (2 * b + 1);
+      zkey[p] = z;
+    }
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return zkey[a] < zkey[b]; });
+  }
+  h->n_groups = (nb + gb - 1) / gb;
+  h->group_start.assign(h->n_groups + 1, 0);
+  std::vector<int> gob(std::max(1, nb), 0);
+  for (int g = 0; g < h->n_groups; ++g) {
+    h->group_start[g] = g * gb;
+    for (int i = g * gb; i < std::min(nb, (g + 1) * gb); ++i) gob[order[i]] = g;
+  }
+  h->group_start[h->n_groups] = nb;
+  h->group_count.assign(std::max(1, h->n_groups), 0);
+  if (allocate) {
+    if (dev_alloc(h, &h->d_group_of_block, std::max(1, nb))) return 1;
+    if (dev_alloc(h, &h->d_group_blocks, std::max(1, nb))) return 1;
+    if (dev_alloc(h, &h->d_flags, static_cast<size_t>(std::max(1, h->n_groups)) * std::max(1, L.nd))) return 1;
+    if (dev_alloc(h, &h->d_cols, static_cast<size_t>(std::max(1, h->n_groups)) * std::max(1, L.nd))) return 1;
+    if (dev_alloc(h, &h->d_count, std::max(1, h->n_groups))) return 1;
+    if (h->h_count) cudaFreeHost(h->h_count);
+    CUDA_TRY(h, cudaMallocHost(reinterpret_cast<void**>(&h->h_count), std::max(1, h->n_groups) * sizeof(int)));
+    h->wc_stride = static_cast<size_t>(gb) * L.bs * std::max(1, L.nd);
+    h->p_stride = static_cast<size_t>(std::max(1, L.nd)) * std::max(1, L.nd);
+    if (dev_alloc(h, &h->d_Wc, 2 * h->wc_stride)) return 1;
+    if (dev_alloc(h, &h->d_P, 2 * h->p_stride)) return 1;
+    for (int i = 0; i < 2; ++i) {
+      if (!h->ev_syrk[i]) CUDA_TRY(h, cudaEventCreateWithFlags(&h->ev_syrk[i], cudaEventDisableTiming));
+      if (!h->ev_scatter[i]) CUDA_TRY(h, cudaEventCreateWithFlags(&h->ev_scatter[i], cudaEventDisableTiming));
+    }
+    if (!h->ev_s_ready) CUDA_TRY(h, cudaEventCreateWithFlags(&h->ev_s_ready, cudaEventDisableTiming));
+    if (dev_alloc(h, &h->d_u, std::max(1, L.nbd))) return 1;
+  }
+  CUDA_TRY(h, cudaMemcpy(h->d_group_of_block, gob.data(), std::max(1, nb) * sizeof(int), cudaMemcpyHostToDevice));
+  if (nb > 0) CUDA_TRY(h, cudaMemcpy(h->d_group_blocks, order.data(), nb * sizeof(int), cudaMemcpyHostToDevice));
+  return 0;
+}
 
 // ---- layout / buffers ----------------------------------------------------------------------
 int make_layout(b200ba_handle* h, const b200ba_options* opt) {
@@ -400,63 +480,20 @@ int make_layout(b200ba_handle* h, const b200ba_options* opt) {
 
   // ---- groups of Schur blocks for the structured contraction ------------------------------------
   {
+    // centroid sums of the measured pixels of every pattern point (this rank's observations;
+    // b200ba_comm_init all-reduces them so that every rank derives the SAME grouping)
     const int nb = L.nblocks;
-    int gb = (L.bs == 3) ? 96 : 48;  // ~288 rows per group: measured optimum on B200 (config 2: 64 -> 12.0 ms, 96 -> 11.6 ms, 160 -> 11.7 ms)
-    if (const char* e = getenv("B200BA_GROUP_BLOCKS")) gb = std::max(1, atoi(e));
-    h->group_blocks_n = gb;
-    std::vector<int> order(nb);
-    for (int i = 0; i < nb; ++i) order[i] = i;
-    if (L.eliminate_points && h->n_obs > 0) {
-      // order the pattern points along a Z-curve of the centroid of their measured pixels: points
-      // that are neighbours in the image share most of their control-point support
-      std::vector<double> sx(nb, 0.0), sy(nb, 0.0);
-      std::vector<int> cnt(nb, 0);
+    h->grp_sums.assign(3 * static_cast<size_t>(std::max(1, nb)), 0.0);
+    if (L.eliminate_points) {
       for (int64_t o = 0; o < h->n_obs; ++o) {
         const int p = static_cast<int>(h->h_obs_point[o]);
-        sx[p] += h->h_obs_xy[2 * o];
-        sy[p] += h->h_obs_xy[2 * o + 1];
-        cnt[p]++;
+        h->grp_sums[p] += h->h_obs_xy[2 * o];
+        h->grp_sums[nb + p] += h->h_obs_xy[2 * o + 1];
+        h->grp_sums[2 * nb + p] += 1.0;
       }
-      const double qx = std::max(1.0, h->cams_host[0].width / 64.0), qy = std::max(1.0, h->cams_host[0].height / 64.0);
-      std::vector<uint32_t> zkey(nb, 0);
-      for (int p = 0; p < nb; ++p) {
-        if (!cnt[p]) continue;
-        uint32_t ux = static_cast<uint32_t>(std::min(1023.0, std::max(0.0, sx[p] / cnt[p] / qx)));
-        uint32_t uy = static_cast<uint32_t>(std::min(1023.0, std::max(0.0, sy[p] / cnt[p] / qy)));
-        uint32_t z = 0;
-        for (int b = 0; b < 10; ++b) z |= ((ux >> b) & 1u) << (2 * b) | ((uy >> b) & 1u) << (2 * b + 1);
-        zkey[p] = z;
-      }
-      std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return zkey[a] < zkey[b]; });
     }
-    h->n_groups = (nb + gb - 1) / gb;
-    h->group_start.assign(h->n_groups + 1, 0);
-    std::vector<int> gob(std::max(1, nb), 0);
-    for (int g = 0; g < h->n_groups; ++g) {
-      h->group_start[g] = g * gb;
-      for (int i = g * gb; i < std::min(nb, (g + 1) * gb); ++i) gob[order[i]] = g;
-    }
-    h->group_start[h->n_groups] = nb;
-    h->group_count.assign(std::max(1, h->n_groups), 0);
-    if (dev_alloc(h, &h->d_group_of_block, std::max(1, nb))) return 1;
-    if (dev_alloc(h, &h->d_group_blocks, std::max(1, nb))) return 1;
-    CUDA_TRY(h, cudaMemcpy(h->d_group_of_block, gob.data(), std::max(1, nb) * sizeof(int), cudaMemcpyHostToDevice));
-    if (nb > 0) CUDA_TRY(h, cudaMemcpy(h->d_group_blocks, order.data(), nb * sizeof(int), cudaMemcpyHostToDevice));
-    if (dev_alloc(h, &h->d_flags, static_cast<size_t>(std::max(1, h->n_groups)) * std::max(1, L.nd))) return 1;
-    if (dev_alloc(h, &h->d_cols, static_cast<size_t>(std::max(1, h->n_groups)) * std::max(1, L.nd))) return 1;
-    if (dev_alloc(h, &h->d_count, std::max(1, h->n_groups))) return 1;
-    if (h->h_count) cudaFreeHost(h->h_count);
-    CUDA_TRY(h, cudaMallocHost(reinterpret_cast<void**>(&h->h_count), std::max(1, h->n_groups) * sizeof(int)));
-    h->wc_stride = static_cast<size_t>(gb) * L.bs * std::max(1, L.nd);
-    h->p_stride = static_cast<size_t>(std::max(1, L.nd)) * std::max(1, L.nd);
-    if (dev_alloc(h, &h->d_Wc, 2 * h->wc_stride)) return 1;
-    if (dev_alloc(h, &h->d_P, 2 * h->p_stride)) return 1;
-    for (int i = 0; i < 2; ++i) {
-      if (!h->ev_syrk[i]) CUDA_TRY(h, cudaEventCreateWithFlags(&h->ev_syrk[i], cudaEventDisableTiming));
-      if (!h->ev_scatter[i]) CUDA_TRY(h, cudaEventCreateWithFlags(&h->ev_scatter[i], cudaEventDisableTiming));
-    }
-    if (!h->ev_s_ready) CUDA_TRY(h, cudaEventCreateWithFlags(&h->ev_s_ready, cudaEventDisableTiming));
-    if (dev_alloc(h, &h->d_u, std::max(1, L.nbd))) return 1;
+    if (reduce_group_sums(h)) return 1;
+    if (build_groups(h, true)) return 1;
   }
   return 0;
 }
@@ -1442,6 +1479,11 @@ int b200ba_comm_init(b200ba_handle* h, const uint8_t id[B200BA_NCCL_UNIQUE_ID_BY
   }
   h->rank = rank;
   h->n_ranks = n_ranks;
+  // every rank must derive the same groups of Schur blocks: reduce the centroid sums
+  if (h->L.eliminate_points && h->L.nblocks > 0 && !h->grp_sums.empty()) {
+    if (reduce_group_sums(h)) return 1;
+    if (build_groups(h, false)) return 1;
+  }
   return 0;
 }
 
