@@ -197,6 +197,10 @@ class CameraModel:
     def calibration_max_y(self): return self.m_calibration_max_y
     def type(self): return self.m_type
 
+    def Scale(self, factor):
+        """camera_model.h:127-129: only non-central models carry metric quantities."""
+        return None
+
     @staticmethod
     def IsCentral(type_) -> bool:
         return CameraModel.Type(type_) != CameraModel.Type.NoncentralGeneric and \
@@ -457,6 +461,19 @@ class BAState:
 
     def num_cameras(self): return len(self.intrinsics)
     def num_imagesets(self): return len(self.image_used)
+
+    def image_tr_global(self, camera_index: int, imageset_index: int) -> np.ndarray:
+        """ba_state.h:65-67: camera_tr_rig[camera] * rig_tr_global[imageset] as [qw qx qy qz t]."""
+        from .synthetic import pose_mul
+        return pose_mul(self.camera_tr_rig[camera_index], self.rig_tr_global[imageset_index])
+
+    def ScaleState(self, scaling_factor: float):
+        """ba_state.cc:60-76: scales every translation, the points and the models' metric parts."""
+        self.camera_tr_rig[:, 4:7] *= scaling_factor
+        self.rig_tr_global[:, 4:7] *= scaling_factor
+        self.points *= scaling_factor
+        for m in self.intrinsics:
+            m.Scale(scaling_factor)
 
     def ComputeFeatureIdToPointsIndex(self, dataset: Dataset):
         """ba_state.cc:78-91."""

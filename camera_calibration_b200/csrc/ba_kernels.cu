@@ -461,9 +461,29 @@ static int jac_minb() {
   if (v < 0) {
     const char* e = getenv("B200BA_JAC_MINB");
     v = e ? atoi(e) : 4;
-    if (v < 2 || v > 4) v = 4;
+    if (v < 2 || v > 6) v = 4;
   }
   return v;
+}
+
+// Threads per block of the main pass (tuning knob B200BA_JAC_THREADS=32|64|128; the kernel is
+// compiled for at most 128) and its evaluation budget (B200BA_EVAL_BUDGET, default 16).
+static int jac_threads() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("B200BA_JAC_THREADS");
+    v = e ? atoi(e) : 128;
+    if (v != 32 && v != 64 && v != 128) v = 128;
+  }
+  return v;
+}
+static int main_eval_budget() {
+  static bool read = false;
+  if (!read) {
+    read = true;
+    if (const char* e = getenv("B200BA_EVAL_BUDGET")) g_main_eval_budget = atoi(e) < 1 ? 1 : atoi(e);
+  }
+  return g_main_eval_budget;
 }
 
 // Straggler pass geometry: a fixed grid that loops over the device-side list (its length is not
@@ -474,10 +494,10 @@ constexpr int kStragglerThreads = 128;
 template <int MODEL, bool JAC, int MINB>
 static void launch_rj_model(const ProblemDev& pb, const Layout& L, const StateDev& st, double2* lp,
                             const ObsOut& out, double huber, uint32_t* list, int* count, cudaStream_t s) {
-  const int threads = 128;
+  const int threads = jac_threads();
   const unsigned blocks = static_cast<unsigned>((pb.n_obs + threads - 1) / threads);
   residual_jacobian_kernel<MODEL, JAC, MINB, false><<<blocks, threads, 0, s>>>(pb, L, st, lp, out, huber, list, count,
-                                                                               g_main_eval_budget);
+                                                                               main_eval_budget());
   if (g_main_done_event) cudaEventRecord(g_main_done_event, s);
 }
 
@@ -493,6 +513,8 @@ static void launch_rj(int model, const ProblemDev& pb, const Layout& L, const St
       switch (jac_minb()) {
         case 2: launch_rj_model<B200BA_MODEL_CENTRAL_GENERIC, JAC, 2>(pb, L, st, lp, out, huber, list, count, s); break;
         case 3: launch_rj_model<B200BA_MODEL_CENTRAL_GENERIC, JAC, 3>(pb, L, st, lp, out, huber, list, count, s); break;
+        case 5: launch_rj_model<B200BA_MODEL_CENTRAL_GENERIC, JAC, 5>(pb, L, st, lp, out, huber, list, count, s); break;
+        case 6: launch_rj_model<B200BA_MODEL_CENTRAL_GENERIC, JAC, 6>(pb, L, st, lp, out, huber, list, count, s); break;
         default: launch_rj_model<B200BA_MODEL_CENTRAL_GENERIC, JAC, 4>(pb, L, st, lp, out, huber, list, count, s);
       }
       break;

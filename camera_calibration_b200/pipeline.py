@@ -1,7 +1,9 @@
 """The callers either side of the hot path: the product's outer bundle-adjustment
 loop ``RunBundleAdjustment`` (applications/camera_calibration/src/camera_calibration/calibration.cc:187-304)
 with its per-iteration checkpoint and ``ChooseNiceCameraOrientation``
-(models/central_generic.cc:570-621). Host logic only; every numerical step (un-projection, the LM
+(models/central_generic.cc:570-621), the outlier deletion between BA rounds
+(``DeleteOutlierFeatures``, calibration.cc:62-184) and ``ScaleToMetric``
+(calibration.cc:307-370; 8f-4). Host logic only; every numerical step (un-projection, the LM
 iteration) runs in ``libb200ba.so``.
 """
 from __future__ import annotations
@@ -116,6 +118,89 @@ def RunBundleAdjustment(use_cuda: bool, schur_mode: SchurMode, max_iteration_cou
             break
         last_cost = cost
     return costs
+
+
+def DeleteOutlierFeatures(camera_index: int, dataset: Dataset, state: BAState, outlier_removal_factor: float,
+                          project_many: Optional[Callable] = None) -> int:
+    """calibration.cc:62-184 (the quartile rule between BA rounds): re-project every feature of one
+    camera from the centre of the calibrated area (``Project``, no warm start), take the first and
+    third quartile q1, q3 of the error magnitudes, and erase the features that fail to project or
+    whose error exceeds ``q3 + outlier_removal_factor (q3 - q1)``. Imagesets left with fewer than
+    three features of this camera are marked unused. Returns the number of removed features.
+    The projections run on the device (``CameraModel.ProjectMany`` -> ``b200ba_project``);
+    ``project_many(model, local_points) -> (pixels, ok)`` may replace it (host-logic tests)."""
+    model = state.intrinsics[camera_index]
+    if project_many is None:
+        project_many = lambda m, lp: m.ProjectMany(lp)  # noqa: E731
+    spans = []  # (imageset, first, last) into the concatenated feature list
+    chunks = []
+    n = 0
+    for i in range(dataset.ImagesetCount()):
+        if not state.image_used[i]:
+            continue
+        f = dataset.GetImageset(i).FeaturesOfCamera(camera_index)
+        T = state.image_tr_global(camera_index, i)
+        R = synthetic.quat_to_rot(T[:4])
+        chunks.append(state.points[f["index"]] @ R.T + T[4:7])
+        spans.append((i, n, n + len(f["index"])))
+        n += len(f["index"])
+    if n == 0:
+        return 0
+    pixels, ok = project_many(model, np.concatenate(chunks))
+    xy = np.concatenate([dataset.GetImageset(i).FeaturesOfCamera(camera_index)["xy"] for i, _, _ in spans])
+    err = np.linalg.norm(pixels - xy.astype(np.float64), axis=1)
+    errors = np.sort(err[ok])
+    if len(errors) < 8:  # too few to detect outliers reliably (calibration.cc:97-100)
+        return 0
+    # index = float(0.25f * size + 0.5f) truncated, in float arithmetic like the reference
+    first_quartile = errors[int(np.float32(0.25) * np.float32(len(errors)) + np.float32(0.5))]
+    third_quartile = errors[int(np.float32(0.75) * np.float32(len(errors)) + np.float32(0.5))]
+    threshold = third_quartile + np.float32(outlier_removal_factor) * (third_quartile - first_quartile)
+    remove = ~ok | (err > threshold)
+    removed = 0
+    for i, a, b in spans:
+        f = dataset.GetImageset(i).FeaturesOfCamera(camera_index)
+        keep = ~remove[a:b]
+        if not keep.all():
+            for key in list(f.keys()):
+                f[key] = f[key][keep]
+            removed += int((~keep).sum())
+        if int(keep.sum()) < 3:
+            state.image_used[i] = False
+    if removed:
+        dataset._b200_context = None
+    return removed
+
+
+def ScaleToMetric(dataset: Dataset, state: BAState) -> float:
+    """calibration.cc:307-370: geometric-mean ratio of the known pattern cell length to the
+    optimised distance of neighbouring corners (right and down neighbours), applied with
+    ``BAState.ScaleState``. Returns the factor."""
+    log_sum, count = 0.0, 0
+    for geometry in getattr(dataset, "known_geometries", []):
+        position_to_index = {}
+        for feature_id, position in geometry.feature_id_to_position.items():
+            idx = state.feature_id_to_points_index.get(feature_id)
+            if idx is not None:
+                position_to_index[tuple(position)] = idx
+        if not position_to_index:
+            continue
+        for feature_id, position in geometry.feature_id_to_position.items():
+            index = position_to_index.get(tuple(position))
+            if index is None:
+                continue
+            for dx, dy in ((1, 0), (0, 1)):
+                neighbor = position_to_index.get((position[0] + dx, position[1] + dy))
+                if neighbor is None:
+                    continue
+                actual = float(np.linalg.norm(state.points[index] - state.points[neighbor]))
+                log_sum += math.log(geometry.cell_length_in_meters / actual)
+                count += 1
+    if count == 0:
+        raise ValueError("ScaleToMetric: no neighbouring corners with known geometry (the reference divides by zero here)")
+    factor = math.exp(log_sum / count)
+    state.ScaleState(factor)
+    return factor
 
 
 def BundleAdjustment(state_directory: str, model_input_directory: str, model_output_directory: str,

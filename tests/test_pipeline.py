@@ -123,3 +123,119 @@ def test_bundle_adjustment_tool(tmp_path):
     st = io.LoadBAState(out)
     assert st is not None and len(st.points) == sp.problem.n_points
     assert pipeline.BundleAdjustment(str(tmp_path / "nope"), d, out) == 1
+
+
+def _outlier_scene(seed=0):
+    """Small central-generic scene at the true state with a few corrupted features."""
+    sp = synthetic.make_problem(2, n_imagesets=6, lattice=(9, 7), image_size=(410, 290), seed=seed)
+    ds, st = api.dataset_from_flat(sp.problem, sp.gt_state)
+    rng = np.random.default_rng(seed)
+    corrupted = []
+    for i in (1, 3, 4):
+        f = ds.GetImageset(i).FeaturesOfCamera(0)
+        k = int(rng.integers(0, len(f["id"])))
+        f["xy"][k] += np.float32(7.5)
+        corrupted.append((i, int(f["id"][k])))
+    return sp, ds, st, corrupted
+
+
+def _reference_outlier_rule(ds, st, project_many, factor):
+    """Literal per-feature restatement of calibration.cc:62-184 for the test."""
+    errs = []
+    per = {}
+    for i in range(ds.ImagesetCount()):
+        if not st.image_used[i]:
+            continue
+        f = ds.GetImageset(i).FeaturesOfCamera(0)
+        T = st.image_tr_global(0, i)
+        R = synthetic.quat_to_rot(T[:4])
+        lp = st.points[f["index"]] @ R.T + T[4:7]
+        px, ok = project_many(st.intrinsics[0], lp)
+        e = np.linalg.norm(px - f["xy"].astype(np.float64), axis=1)
+        per[i] = (e, ok)
+        errs += list(e[ok])
+    errs = sorted(errs)
+    q1 = errs[int(np.float32(0.25) * np.float32(len(errs)) + np.float32(0.5))]
+    q3 = errs[int(np.float32(0.75) * np.float32(len(errs)) + np.float32(0.5))]
+    thr = q3 + np.float32(factor) * (q3 - q1)
+    return {i: set(ds.GetImageset(i).FeaturesOfCamera(0)["id"][ok & (e <= thr)].tolist()) for i, (e, ok) in per.items()}
+
+
+def _check_outlier_deletion(project_many):
+    sp, ds, st, corrupted = _outlier_scene()
+    expect = _reference_outlier_rule(ds, st, project_many, 1.5)
+    before = sum(len(ds.GetImageset(i).FeaturesOfCamera(0)["id"]) for i in range(ds.ImagesetCount()))
+    removed = pipeline.DeleteOutlierFeatures(0, ds, st, 1.5, project_many=project_many)
+    after = sum(len(ds.GetImageset(i).FeaturesOfCamera(0)["id"]) for i in range(ds.ImagesetCount()))
+    assert removed == before - after and removed >= len(corrupted)
+    for i in range(ds.ImagesetCount()):
+        f = ds.GetImageset(i).FeaturesOfCamera(0)
+        assert set(f["id"].tolist()) == expect[i]
+        assert len(f["xy"]) == len(f["id"]) == len(f["index"]) == len(f["last_projection"])
+    for i, fid in corrupted:
+        assert fid not in ds.GetImageset(i).FeaturesOfCamera(0)["id"]
+    # an imageset left with < 3 features of the camera is dropped from the state
+    sp, ds, st, _ = _outlier_scene(1)
+    f = ds.GetImageset(2).FeaturesOfCamera(0)
+    for key in list(f.keys()):
+        f[key] = f[key][:3]
+    f["xy"][0] += np.float32(40)
+    pipeline.DeleteOutlierFeatures(0, ds, st, 1.5, project_many=project_many)
+    assert st.image_used[2] is False and all(st.image_used[i] for i in (0, 1, 3, 4, 5))
+
+
+def test_delete_outlier_features_host_logic(oracle_lib):
+    """Quartile rule (calibration.cc:62-184) with the projections done by the CPU restatement."""
+    from oracle import oracle
+
+    def project_many(model, lp):
+        px, ok = oracle.project(model.c_camera(), model.flat_intrinsics(), lp)
+        return px, ok.astype(bool)
+    _check_outlier_deletion(project_many)
+
+
+@pytest.mark.gpu
+def test_delete_outlier_features_on_device():
+    _check_outlier_deletion(lambda model, lp: model.ProjectMany(lp))
+
+
+def test_scale_to_metric():
+    """calibration.cc:307-370 + ba_state.cc:60-76 on a 6x5 pattern shrunk by a known factor."""
+    ds = api.Dataset(1)
+    st = api.BAState()
+    g = io.KnownGeometry()
+    g.cell_length_in_meters = 0.02
+    rng = np.random.default_rng(3)
+    pts = []
+    for y in range(5):
+        for x in range(6):
+            fid = 100 + x + 6 * y
+            g.feature_id_to_position[fid] = (x, y)
+            if (x, y) != (2, 2):  # one corner of the pattern was never triangulated
+                st.feature_id_to_points_index[fid] = len(pts)
+                pts.append([0.02 * x, 0.02 * y, 0.0])
+    ds.known_geometries = [g]
+    true_scale = 3.7
+    st.points = np.array(pts) / true_scale + 1e-6 * rng.standard_normal((len(pts), 3))
+    st.rig_tr_global = np.tile(np.array([1.0, 0, 0, 0, 0.1, 0.2, 0.3]), (2, 1))
+    st.camera_tr_rig = np.array([[1.0, 0, 0, 0, 0.01, 0.0, 0.0]])
+    st.image_used = [True, True]
+    m = api.NoncentralGenericModel(6, 5, 0, 0, 99, 79, 100, 80)
+    m.SetPointGrid(np.ones((5, 6, 3)))
+    st.intrinsics = [m]
+    p0 = st.points.copy()
+    factor = pipeline.ScaleToMetric(ds, st)
+    assert abs(factor - true_scale) < 1e-2
+    assert np.allclose(st.points, factor * p0)
+    assert np.allclose(st.rig_tr_global[:, 4:], factor * np.array([0.1, 0.2, 0.3])) and np.allclose(st.rig_tr_global[:, :4], [1, 0, 0, 0])
+    assert np.allclose(st.camera_tr_rig[0, 4:], [0.01 * factor, 0, 0])
+    assert np.allclose(m.point_grid(), factor)
+    # literal restatement of the averaging
+    logs = []
+    idx = st.feature_id_to_points_index
+    for fid, (x, y) in g.feature_id_to_position.items():
+        for dx, dy in ((1, 0), (0, 1)):
+            nid = 100 + (x + dx) + 6 * (y + dy)
+            if x + dx < 6 and y + dy < 5 and fid in idx and nid in idx:
+                logs.append(np.log(0.02 / np.linalg.norm(p0[idx[fid]] - p0[idx[nid]])))
+    assert abs(factor - np.exp(np.mean(logs))) < 1e-12
