@@ -39,12 +39,15 @@ struct NcclApi {
   int (*GetUniqueId)(void*) = nullptr;
   int (*CommInitRank)(void**, int, NcclUniqueId, int) = nullptr;
   int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+  int (*Broadcast)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
   int (*CommDestroy)(void*) = nullptr;
   const char* (*GetErrorString)(int) = nullptr;
 };
 // ncclDataType_t / ncclRedOp_t values (nccl.h): ncclFloat64 = 8, ncclSum = 0
 constexpr int kNcclDouble = 8;
+constexpr int kNcclInt32 = 2;
 constexpr int kNcclSum = 0;
+constexpr int kNcclMax = 2;
 
 NcclApi g_nccl;
 bool load_nccl(std::string* err) {
@@ -64,15 +67,18 @@ bool load_nccl(std::string* err) {
   *reinterpret_cast<void**>(&g_nccl.GetUniqueId) = dlsym(lib, "ncclGetUniqueId");
   *reinterpret_cast<void**>(&g_nccl.CommInitRank) = dlsym(lib, "ncclCommInitRank");
   *reinterpret_cast<void**>(&g_nccl.AllReduce) = dlsym(lib, "ncclAllReduce");
+  *reinterpret_cast<void**>(&g_nccl.Broadcast) = dlsym(lib, "ncclBroadcast");
   *reinterpret_cast<void**>(&g_nccl.CommDestroy) = dlsym(lib, "ncclCommDestroy");
   *reinterpret_cast<void**>(&g_nccl.GetErrorString) = dlsym(lib, "ncclGetErrorString");
-  if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllReduce || !g_nccl.CommDestroy) {
+  if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllReduce || !g_nccl.Broadcast || !g_nccl.CommDestroy) {
     *err = "libnccl lacks a required symbol";
     g_nccl.lib = nullptr;
     return false;
   }
   return true;
 }
+
+constexpr int kMaxCholPanels = 1024;
 
 enum Phase { PH_JAC = 0, PH_ACC, PH_SCHUR, PH_FACTOR, PH_TRIAL, PH_UPDATE, PH_ALLREDUCE, PH_STRAGGLER, PH_COUNT };
 
@@ -114,6 +120,8 @@ struct b200ba_handle {
   int64_t reduce_count = 0;  // doubles of sys.base covered by the per-build all-reduce
   double* d_potrf_work = nullptr;
   int potrf_lwork = 0;
+  int chol_mode = -1;                     // B200BA_DIST_CHOL=0|1 overrides: 1 = column-block Cholesky (see factor_dense)
+  int chol_nb = 512;                      // its panel width (B200BA_CHOL_NB)
   int *d_info = nullptr, *d_fail = nullptr;
   // Static cell-major processing order: device position -> index in the caller's (reference)
   // observation order. Computed once at create time from the cell of the measured pixel.
@@ -475,6 +483,12 @@ int make_layout(b200ba_handle* h, const b200ba_options* opt) {
   if (dev_alloc(h, &h->d_x, L.dof)) return 1;
   int lwork = 0;
   CUSOLVER_TRY(h, cusolverDnDpotrf_bufferSize(h->cusolver, CUBLAS_FILL_MODE_LOWER, L.nd, h->d_S, std::max(1, L.nd), &lwork));
+  {
+    int lw2 = 0;
+    const int nbp = std::max(1, std::min(L.nd, h->chol_nb));
+    CUSOLVER_TRY(h, cusolverDnDpotrf_bufferSize(h->cusolver, CUBLAS_FILL_MODE_LOWER, nbp, h->d_S, std::max(1, L.nd), &lw2));
+    lwork = std::max(lwork, lw2);
+  }
   h->potrf_lwork = lwork;
   if (dev_alloc(h, &h->d_potrf_work, std::max(1, lwork))) return 1;
 
@@ -600,6 +614,82 @@ int build_system(b200ba_handle* h, double huber, double* cost, double* n_valid) 
   return 0;
 }
 
+__global__ void fold_panel_info_kernel(const int* __restrict__ panel_info, int n, int* __restrict__ info) {
+  int worst = 0;
+  for (int i = threadIdx.x; i < n; i += 32) worst = max(worst, panel_info[i] != 0 ? 1 : 0);
+  for (int o = 16; o > 0; o >>= 1) worst = max(worst, __shfl_xor_sync(0xffffffffu, worst, o));
+  if (threadIdx.x == 0) info[0] = worst;
+}
+
+// Cholesky factorisation of the reduced system S (column-major, lower) in place; info[0] != 0
+// when a pivot was not positive.
+//   default: cusolverDnDpotrf on the whole matrix (replicated on every rank).
+//   B200BA_DIST_CHOL=1: right-looking factorisation over column blocks of width nb, dealt round-robin
+//   to the ranks. The owner of block k factors its diagonal tile and solves the tile column below
+//   it, broadcasts the finished column block (whole columns: contiguous in the column-major S),
+//   then every rank applies the rank-nb update to the column blocks IT owns. Each rank thereby
+//   does 1/N of the n^3/3 update flops instead of all of them, and ends with the complete L (its
+//   own blocks computed, the others received), so the triangular solves stay local.
+int factor_dense(b200ba_handle* h) {
+  const Layout& L = h->L;
+  const int nd = L.nd;
+  const int nb = h->chol_nb;
+  const int nblk = (nd + nb - 1) / nb;
+  // Opt-in (B200BA_DIST_CHOL=1). Measured on config 2 (n_d = 13 080, nb = 512): the factorisation
+  // takes 40.5 ms on one B200 and 32.1 ms on two, against 24.7 ms for cusolver's potrf replicated on
+  // every rank -- the panel chain (potrf(512) + trsm + broadcast, ~0.75 ms x 26 panels) is serial
+  // without look-ahead. Until the look-ahead / faster panel lands the
+  // replicated potrf stays the default.
+  bool blocked = (h->chol_mode == 1) && nd > nb;
+  if (nblk > kMaxCholPanels) blocked = false;
+  if (!blocked) {
+    CUSOLVER_TRY(h, cusolverDnDpotrf(h->cusolver, CUBLAS_FILL_MODE_LOWER, nd, h->d_S, nd, h->d_potrf_work, h->potrf_lwork,
+                                     h->d_info));
+    return 0;
+  }
+  const double one = 1.0, minus_one = -1.0;
+  int* panel_info = h->d_info + 2;
+  CUDA_TRY(h, cudaMemsetAsync(panel_info, 0, nblk * sizeof(int), h->stream));
+  for (int k = 0; k < nblk; ++k) {
+    const int owner = k % h->n_ranks;
+    const int j0 = k * nb, w = std::min(nb, nd - j0), below = nd - j0 - w;
+    double* Akk = h->d_S + static_cast<size_t>(j0) * nd + j0;
+    if (h->rank == owner) {
+      CUSOLVER_TRY(h, cusolverDnDpotrf(h->cusolver, CUBLAS_FILL_MODE_LOWER, w, Akk, nd, h->d_potrf_work, h->potrf_lwork,
+                                       panel_info + k));
+      if (below > 0)  // L_below = A_below L_kk^-T
+        CUBLAS_TRY(h, cublasDtrsm(h->cublas, CUBLAS_SIDE_RIGHT, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_T, CUBLAS_DIAG_NON_UNIT, below,
+                                  w, &one, Akk, nd, Akk + w, nd));
+    }
+    if (h->n_ranks > 1 && h->comm) {
+      double* col = h->d_S + static_cast<size_t>(j0) * nd;
+      const int rc = g_nccl.Broadcast(col, col, static_cast<size_t>(nd) * w, kNcclDouble, owner, h->comm, h->stream);
+      if (rc != 0) {
+        h->error = std::string("ncclBroadcast: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "error");
+        return 1;
+      }
+    }
+    // trailing update of the column blocks this rank owns
+    for (int j = k + 1; j < nblk; ++j) {
+      if (j % h->n_ranks != h->rank) continue;
+      const int c0 = j * nb, wj = std::min(nb, nd - c0);
+      const double* Lj = h->d_S + static_cast<size_t>(j0) * nd + c0;  // rows c0.. of column block k
+      CUBLAS_TRY(h, cublasDgemm(h->cublas, CUBLAS_OP_N, CUBLAS_OP_T, nd - c0, wj, w, &minus_one, Lj, nd, Lj, nd, &one,
+                                h->d_S + static_cast<size_t>(c0) * nd + c0, nd));
+    }
+  }
+  fold_panel_info_kernel<<<1, 32, 0, h->stream>>>(panel_info, nblk, h->d_info);
+  if (h->n_ranks > 1 && h->comm) {
+    // every rank must take the same branch of the LM loop
+    const int rc = g_nccl.AllReduce(h->d_info, h->d_info, 1, kNcclInt32, kNcclMax, h->comm, h->stream);
+    if (rc != 0) {
+      h->error = "ncclAllReduce (factorisation status) failed";
+      return 1;
+    }
+  }
+  return 0;
+}
+
 // Hot loop 2: Schur complement solve for a given lambda (LV/lm_optimizer.h:1246-1369).
 // Leaves x = [x_points | x_dense] in d_x. *spd = 0 when a factorisation met a non-positive pivot.
 int solve_system(b200ba_handle* h, double lambda, int* spd) {
@@ -700,8 +790,7 @@ int solve_system(b200ba_handle* h, double lambda, int* spd) {
   }
   {
     ScopedPhase ph(h, PH_FACTOR);
-    CUSOLVER_TRY(h, cusolverDnDpotrf(h->cusolver, CUBLAS_FILL_MODE_LOWER, L.nd, h->d_S, L.nd, h->d_potrf_work,
-                                     h->potrf_lwork, h->d_info));
+    if (factor_dense(h)) return 1;
     CUSOLVER_TRY(h, cusolverDnDpotrs(h->cusolver, CUBLAS_FILL_MODE_LOWER, L.nd, 1, h->d_S, L.nd, h->d_x + L.nbd, L.nd,
                                      h->d_info + 1));
   }
@@ -948,6 +1037,8 @@ int b200ba_create(const b200ba_problem* p, int device, b200ba_handle** out) {
     h->h_obs_xy.assign(p->obs_xy, p->obs_xy + 2 * n);
   }
   if (const char* e = getenv("B200BA_GROUPED")) h->force_grouped = atoi(e);
+  if (const char* e = getenv("B200BA_DIST_CHOL")) h->chol_mode = atoi(e);
+  if (const char* e = getenv("B200BA_CHOL_NB")) h->chol_nb = std::max(32, atoi(e));
   h->pb.n_obs = n;
   h->pb.obs_imageset = h->d_obs_imageset;
   h->pb.obs_camera = h->d_obs_camera;
@@ -965,7 +1056,7 @@ int b200ba_create(const b200ba_problem* p, int device, b200ba_handle** out) {
   TRYC(cuda_ok(cudaMemset(h->d_last_projection, 0, std::max<int64_t>(1, n) * sizeof(double2)), "memset"));
   TRYC(dev_alloc(h, &h->d_straggler_list, n));
   TRYC(dev_alloc(h, &h->d_straggler_count, 1));
-  TRYC(dev_alloc(h, &h->d_info, 2));
+  TRYC(dev_alloc(h, &h->d_info, 2 + kMaxCholPanels));
   TRYC(dev_alloc(h, &h->d_fail, 1));
   TRYC(dev_alloc(h, &h->d_partial, cost_reduce_partial_size()));
   TRYC(dev_alloc(h, &h->d_scal, 16));

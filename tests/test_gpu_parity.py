@@ -314,6 +314,30 @@ def test_multi_gpu_matches_single_gpu():
     cmd[cmd.index("29533")] = "29534"
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, env=env)
     assert r.returncode == 0 and "MGPU_OK" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
+    env = dict(os.environ, MGPU_DIST_CHOL="1")
+    cmd[cmd.index("29534")] = "29535"
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, env=env)
+    assert r.returncode == 0 and "MGPU_OK" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
+
+
+def test_column_block_cholesky_matches_potrf(monkeypatch):
+    """B200BA_DIST_CHOL=1 runs the multi-rank factorisation (column blocks, here all owned by the
+    one rank) instead of cusolver's potrf: same LM trajectory and state."""
+    sp = synthetic.make_problem(2, n_imagesets=12, lattice=(12, 10), image_size=(410, 290))
+    opt = cabi.default_options(max_iteration_count=5)
+    out = []
+    for mode in ("0", "1"):
+        monkeypatch.setenv("B200BA_DIST_CHOL", mode)
+        monkeypatch.setenv("B200BA_CHOL_NB", "96")
+        with api.BundleAdjuster(sp.problem) as adj:
+            st = sp.init_state.copy()
+            rep = adj.optimize_host(st, opt)
+            out.append((rep.trace(), st))
+    (c0, l0, a0), s0 = out[0]
+    (c1, l1, a1), s1 = out[1]
+    assert a0 == a1 and np.allclose(c0, c1, rtol=1e-10)
+    assert np.abs(s0.points - s1.points).max() < 1e-9
+    assert max(np.abs(x - y).max() for x, y in zip(s0.intrinsics, s1.intrinsics)) < 1e-9
 
 
 def test_straggler_pass_equals_main_pass(oracle_lib):
