@@ -263,6 +263,22 @@ def run_b200(args):
 
     # ---- end to end: host buffers in, host buffers out, every step (b200ba_optimize_host) --------
     st = state0.copy()
+    # the caller's state buffers live in pinned host memory (the copies in the timed region are
+    # plain DMA transfers, as the e2e contract asks)
+    pinned = []
+
+    def pin(a):
+        try:
+            t = torch.empty(a.shape, dtype=torch.float64).pin_memory()
+        except Exception:  # pragma: no cover - pinning refused: stay pageable
+            return a
+        pinned.append(t)
+        v = t.numpy()
+        v[...] = a
+        return v
+    st.points, st.rig_tr_global, st.camera_tr_rig = pin(st.points), pin(st.rig_tr_global), pin(st.camera_tr_rig)
+    st.intrinsics = [pin(a) for a in st.intrinsics]
+    st.last_projection = pin(st.last_projection)
     lam2 = -1.0
     for _ in range(W):
         opt.init_lambda = lam2
@@ -312,7 +328,8 @@ def run_b200(args):
                          "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_obs": bpo, "obs_per_launch": n_local, "avg_launch_ms": jac_avg_ms},
             "e2e": {"value": 1e3 / (e2e_ms / K), "unit": "LM iterations/s", "h2d_bytes_per_step": int(state_bytes),
-                    "d2h_bytes_per_step": int(state_bytes), "ms_per_step": e2e_ms / K},
+                    "d2h_bytes_per_step": int(state_bytes), "ms_per_step": e2e_ms / K,
+                    "host_memory": "pinned" if pinned else "pageable"},
             "gpu_launches": int(launches), "clocks": clocks,
         }
         if world == 1 and not args.no_cpu_baseline:
