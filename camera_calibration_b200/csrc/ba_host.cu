@@ -702,15 +702,18 @@ int solve_system(b200ba_handle* h, double lambda, int* spd) {
     const double zero = 0.0;
     CUDA_TRY(h, cudaMemsetAsync(h->d_fail, 0, sizeof(int), h->stream));
     launch_schur_blocks(L.bs, L.nblocks, h->sys.Dblk, h->sys.bp, lambda, h->d_Linv, h->d_v, h->d_fail, h->stream);
-    launch_block_solve_t(L.bs, L.nblocks, h->d_Linv, h->d_v, h->d_u, h->stream);  // u = D^-1 b_block
+    // S = C_r is copied on the side stream (0.4 ms of pure HBM traffic at config 2) underneath the
+    // block factorisations and the first rank-k update; the scatters follow it in stream order.
+    CUDA_TRY(h, cudaEventRecord(h->ev_s_ready, h->stream));  // everything that used S before is done
+    CUDA_TRY(h, cudaStreamWaitEvent(h->side_stream, h->ev_s_ready, 0));
     CUDA_TRY(h, cudaMemcpyAsync(h->d_S, h->sys.C, static_cast<size_t>(L.nd) * L.nd * sizeof(double),
-                                cudaMemcpyDeviceToDevice, h->stream));
+                                cudaMemcpyDeviceToDevice, h->side_stream));
+    CUDA_TRY(h, cudaEventRecord(h->ev_s_ready, h->side_stream));
+    launch_block_solve_t(L.bs, L.nblocks, h->d_Linv, h->d_v, h->d_u, h->stream);  // u = D^-1 b_block
     h->timings.kernel_launches += 2;
     // The compact rank-k updates (compute-bound, main stream) and the scatters into S (memory-
     // bound, side stream) are software-pipelined over two P / Wc buffers. All scatters run on the
     // side stream, hence in order: plain read-modify-write, no atomics.
-    CUDA_TRY(h, cudaEventRecord(h->ev_s_ready, h->stream));          // S = C_r is in place
-    CUDA_TRY(h, cudaStreamWaitEvent(h->side_stream, h->ev_s_ready, 0));
     int it = 0;
     for (int g = h->rank; g < h->n_groups; g += h->n_ranks) {
       const int nblk = h->group_start[g + 1] - h->group_start[g];
@@ -733,6 +736,7 @@ int solve_system(b200ba_handle* h, double lambda, int* spd) {
       ++it;
     }
     // join: every scatter has landed before S is used
+    CUDA_TRY(h, cudaStreamWaitEvent(h->stream, h->ev_s_ready, 0));  // the copy (covers a rank without groups)
     for (int b = 0; b < 2 && b < it; ++b) CUDA_TRY(h, cudaStreamWaitEvent(h->stream, h->ev_scatter[b], 0));
     grouped_done = true;
   }
