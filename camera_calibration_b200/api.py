@@ -321,6 +321,146 @@ class CentralGenericModel(CameraModel):
     def flat_intrinsics(self): return self.m_grid.reshape(-1)
     def set_flat_intrinsics(self, a): self.m_grid = np.array(a, dtype=np.float64).reshape(self.m_grid.shape)
 
+    # ---- pixel <-> grid maps (central_grid.h:127-154); the first is evaluated in FLOAT there ----
+    @staticmethod
+    def GridPointToPixelCornerConvStatic(x, y, min_x, min_y, max_x, max_y, grid_width, grid_height):
+        f = np.float32
+        px = f(min_x) + ((f(x) - f(1)) / (f(grid_width) - f(3))) * f(max_x + 1 - min_x)
+        py = f(min_y) + ((f(y) - f(1)) / (f(grid_height) - f(3))) * f(max_y + 1 - min_y)
+        return np.array([px, py], dtype=np.float64)
+
+    def GridPointToPixelCornerConv(self, x, y):
+        return CentralGenericModel.GridPointToPixelCornerConvStatic(
+            x, y, self.m_calibration_min_x, self.m_calibration_min_y, self.m_calibration_max_x,
+            self.m_calibration_max_y, self.m_grid.shape[1], self.m_grid.shape[0])
+
+    def PixelCornerConvToGridPoint(self, x, y):
+        """Vectorised over arrays of pixel coordinates; double arithmetic with the float constant
+        (grid - 3.f) like the reference."""
+        gw, gh = self.m_grid.shape[1], self.m_grid.shape[0]
+        x = np.asarray(x, dtype=np.float64)
+        y = np.asarray(y, dtype=np.float64)
+        gx = 1.0 + float(np.float32(gw) - np.float32(3)) * (x - self.m_calibration_min_x) / (self.m_calibration_max_x + 1 - self.m_calibration_min_x)
+        gy = 1.0 + float(np.float32(gh) - np.float32(3)) * (y - self.m_calibration_min_y) / (self.m_calibration_max_y + 1 - self.m_calibration_min_y)
+        return np.stack([gx, gy], axis=-1)
+
+    # ---- model fitting (row f-4) --------------------------------------------------------------
+    def _fit_grid_points(self, grid_points, directions, max_iteration_count, fit_fn=None):
+        """FitToPixelDirectionsImpl (central_generic.cc:551-568) on the device
+        (``b200ba_fit_directions``). ``fit_fn(gw, gh, grid, grid_points, directions, iterations)
+        -> (grid, report)`` replaces the device call in host-logic tests."""
+        gp = np.ascontiguousarray(grid_points, dtype=np.float64).reshape(-1, 2)
+        d = np.ascontiguousarray(directions, dtype=np.float64).reshape(-1, 3)
+        gh, gw = self.m_grid.shape[:2]
+        if fit_fn is not None:
+            grid, rep = fit_fn(gw, gh, self.m_grid, gp, d, int(max_iteration_count))
+            self.m_grid = np.array(grid, dtype=np.float64).reshape(gh, gw, 3)
+            return rep
+        lib = cabi.load_library()
+        g = np.ascontiguousarray(self.m_grid, dtype=np.float64).reshape(-1).copy()
+        rep = cabi.FitReport()
+        _check(lib.b200ba_fit_directions(-1, gw, gh, _dp(g), len(gp), _dp(gp), _dp(d), int(max_iteration_count),
+                                         C.byref(rep)))
+        self.m_grid = g.reshape(gh, gw, 3)
+        return rep
+
+    def FitToPixelDirections(self, pixels, directions, max_iteration_count, fit_fn=None):
+        """central_generic.cc:424-431."""
+        px = np.asarray(pixels, dtype=np.float64).reshape(-1, 2)
+        return self._fit_grid_points(self.PixelCornerConvToGridPoint(px[:, 0], px[:, 1]), directions,
+                                     max_iteration_count, fit_fn)
+
+    def FitToDenseModel(self, dense_model, subsample_step: int, max_iteration_count: int, fit_fn=None) -> bool:
+        """central_generic.cc:267-422. ``dense_model`` [height, width, 3]: one direction per pixel,
+        NaN where the source model is undefined. Initialises every control point from the closest
+        valid pixel (search radius < 5), extrapolates the rest linearly from their neighbours, then
+        fits the grid to the sub-sampled dense directions."""
+        dense = np.asarray(dense_model, dtype=np.float64)
+        dh, dw = dense.shape[:2]
+        gh, gw = self.m_grid.shape[:2]
+        scale_x = dw / float(self.m_width)
+        scale_y = dh / float(self.m_height)
+        valid = ~np.isnan(dense[:, :, 0])
+        grid = np.full((gh, gw, 3), np.nan)
+        have_nan = False
+        for gy in range(gh):
+            for gx in range(gw):
+                p = self.GridPointToPixelCornerConv(gx, gy)
+                cx, cy = int(scale_x * p[0]), int(scale_y * p[1])  # cast<int>: truncation
+                if cx < 0 or cy < 0 or cx >= dw or cy >= dh:
+                    have_nan = True
+                    continue
+                if valid[cy, cx]:
+                    grid[gy, gx] = dense[cy, cx]
+                    continue
+                found = False
+                for radius in range(1, 5):
+                    min_x, min_y, max_x, max_y = cx - radius, cy - radius, cx + radius, cy + radius
+                    for x in range(max(0, min_x), min(dw - 1, max_x) + 1):  # top and bottom
+                        if min_y >= 0 and valid[min_y, x]:
+                            grid[gy, gx] = dense[min_y, x]
+                            found = True
+                            break
+                        if max_y < dh and valid[max_y, x]:
+                            grid[gy, gx] = dense[max_y, x]
+                            found = True
+                            break
+                    if found:
+                        break
+                    for y in range(max(0, min_y), min(dh - 1, max_y) + 1):  # left and right
+                        if min_x >= 0 and valid[y, min_x]:
+                            grid[gy, gx] = dense[y, min_x]
+                            found = True
+                            break
+                        if max_x < dw and valid[y, max_x]:
+                            grid[gy, gx] = dense[y, max_x]
+                            found = True
+                            break
+                    if found:
+                        break
+                if not found:
+                    have_nan = True
+        # linear steps from the neighbours, in place like the reference (sweep order matters)
+        iteration = 0
+        while have_nan and iteration < dw + dh:
+            have_nan = False
+            for gy in range(gh):
+                for gx in range(gw):
+                    if not np.isnan(grid[gy, gx]).any():
+                        continue
+                    total = np.zeros(3)
+                    count = 0
+                    for dx, dy in ((0, 1), (0, -1), (1, 0), (-1, 0)):
+                        nx1, ny1, nx2, ny2 = gx + dx, gy + dy, gx + 2 * dx, gy + 2 * dy
+                        if nx2 < 0 or ny2 < 0 or nx2 >= gw or ny2 >= gh:
+                            continue
+                        v1, v2 = grid[ny1, nx1], grid[ny2, nx2]
+                        if np.isnan(v1).any() or np.isnan(v2).any():
+                            continue
+                        total += v1 + (v1 - v2)
+                        count += 1
+                    if count > 0:
+                        grid[gy, gx] = total / np.linalg.norm(total)
+                    else:
+                        have_nan = True
+            iteration += 1
+        if have_nan:
+            return False
+        self.m_grid = grid
+        # samples: every subsample_step-th pixel of the calibrated area with a valid direction
+        model_to_camera_x = float(self.m_width) / dw
+        model_to_camera_y = float(self.m_height) / dh
+        ys = np.arange(self.m_calibration_min_y, self.m_calibration_max_y + 1, subsample_step)
+        xs = np.arange(self.m_calibration_min_x, self.m_calibration_max_x + 1, subsample_step)
+        dmx = (scale_x * xs).astype(np.int64)
+        dmy = (scale_y * ys).astype(np.int64)
+        DY, DX = np.meshgrid(dmy, dmx, indexing="ij")
+        ok = valid[DY, DX]
+        half = float(np.float32(0.5))
+        gp = self.PixelCornerConvToGridPoint(model_to_camera_x * (DX[ok] + half), model_to_camera_y * (DY[ok] + half))
+        self._fit_grid_points(gp, dense[DY[ok], DX[ok]], max_iteration_count, fit_fn)
+        return True
+
 
 class NoncentralGenericModel(CameraModel):
     """APP/models/noncentral_generic.h:46-290."""
@@ -345,6 +485,21 @@ class NoncentralGenericModel(CameraModel):
     def Scale(self, factor):
         """noncentral_generic.cc:148-154."""
         self.m_point_grid = factor * self.m_point_grid
+
+    def InitializeFromCentralGenericModel(self, other: "CentralGenericModel"):
+        """noncentral_generic.cc:136-146: same directions, all line origins at the optical centre."""
+        self.m_direction_grid = other.grid().copy()
+        self.m_point_grid = np.zeros_like(self.m_direction_grid)
+        self.m_calibration_min_x, self.m_calibration_min_y = other.calibration_min_x(), other.calibration_min_y()
+        self.m_calibration_max_x, self.m_calibration_max_y = other.calibration_max_x(), other.calibration_max_y()
+        self.m_width, self.m_height = other.width(), other.height()
+
+    def PixelCornerConvToGridPoint(self, x, y):
+        """noncentral_generic.h:167-171."""
+        gw, gh = self.m_direction_grid.shape[1], self.m_direction_grid.shape[0]
+        gx = 1.0 + float(np.float32(gw) - np.float32(3)) * (x - self.m_calibration_min_x) / (self.m_calibration_max_x + 1 - self.m_calibration_min_x)
+        gy = 1.0 + float(np.float32(gh) - np.float32(3)) * (y - self.m_calibration_min_y) / (self.m_calibration_max_y + 1 - self.m_calibration_min_y)
+        return np.array([gx, gy])
 
     def duplicate(self):
         m = NoncentralGenericModel(self.m_point_grid.shape[1], self.m_point_grid.shape[0], self.m_calibration_min_x,

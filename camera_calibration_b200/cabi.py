@@ -169,6 +169,17 @@ class Timings(C.Structure):
     ]
 
 
+class FitReport(C.Structure):
+    """b200ba_fit_report."""
+    _fields_ = [
+        ("initial_cost", C.c_double),
+        ("final_cost", C.c_double),
+        ("final_lambda", C.c_double),
+        ("num_iterations_performed", C.c_int32),
+        ("lm_attempts", C.c_int32),
+    ]
+
+
 def _ptr(a: np.ndarray, ctype):
     return a.ctypes.data_as(C.POINTER(ctype))
 
@@ -321,6 +332,8 @@ SYMBOLS = {
     "b200ba_schur_solve": (C.c_int, [C.c_int, C.c_int32, C.c_int32, C.c_int32, _D, _D, _D, _D, _D, _D]),
     "b200ba_project": (C.c_int, [C.c_int, C.POINTER(Camera), _D, C.c_int64, _D, _D, _I32]),
     "b200ba_unproject": (C.c_int, [C.c_int, C.POINTER(Camera), _D, C.c_int64, _D, _D, _D, _I32]),
+    "b200ba_fit_directions": (C.c_int, [C.c_int, C.c_int32, C.c_int32, _D, C.c_int64, _D, _D, C.c_int32,
+                                        C.POINTER(FitReport)]),
     "b200ba_nccl_unique_id": (C.c_int, [C.POINTER(C.c_uint8)]),
     "b200ba_comm_init": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint8), C.c_int, C.c_int]),
     "b200ba_get_timings": (C.c_int, [C.c_void_p, C.POINTER(Timings)]),

@@ -1542,6 +1542,146 @@ int b200ba_unproject(int device, const b200ba_camera* cam, const double* intrins
   return model_io(device, cam, intrinsics, n, pixels, 2, nullptr, directions, origins, ok, false);
 }
 
+// CentralGenericModel::FitToPixelDirectionsImpl (APP/models/central_generic.cc:551-568):
+// LMOptimizer<double>::Optimize(max_iteration_count, max_lm_attempts = 10, init_lambda = -1,
+// init_lambda_factor = 0.001f) over the direction grid (LV/lm_optimizer.h:628-991 without the
+// Schur structure: SolveDensely). H (row-major upper == column-major lower) is built by
+// dirfit_kernel<true>; every attempt factors a copy of H + lambda I with cuSOLVER.
+int b200ba_fit_directions(int device, int32_t gw, int32_t gh, double* grid, int64_t n, const double* grid_points,
+                          const double* directions, int32_t max_iteration_count, b200ba_fit_report* report) {
+  if (gw < 4 || gh < 4 || !grid || n < 0 || (n > 0 && (!grid_points || !directions)) || !report) {
+    g_create_error = "b200ba_fit_directions: bad argument";
+    return 2;
+  }
+  for (int64_t i = 0; i < n; ++i) {
+    const double gx = grid_points[2 * i], gy = grid_points[2 * i + 1];
+    if (!(gx >= 1.0 && gx < gw - 2 && gy >= 1.0 && gy < gh - 2)) {
+      g_create_error = "b200ba_fit_directions: a grid point has no complete 4x4 support";
+      return 2;
+    }
+  }
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    g_create_error = "no CUDA device available (this library has no CPU fallback)";
+    return 3;
+  }
+  if (device >= 0) cudaSetDevice(device);
+  memset(report, 0, sizeof(*report));
+  const int G = gw * gh, dof = 2 * G;
+  const size_t nn = static_cast<size_t>(std::max<int64_t>(1, n));
+  double *dgrid = nullptr, *dtrial = nullptr, *dtan = nullptr, *dgp = nullptr, *ddir = nullptr, *dH = nullptr,
+         *dS = nullptr, *db = nullptr, *dx = nullptr, *dcost = nullptr, *dsum = nullptr, *dwork = nullptr;
+  int* dinfo = nullptr;
+  cublasHandle_t cb = nullptr;
+  cusolverDnHandle_t cs = nullptr;
+  int rc = 0;
+  auto ok = [&](cudaError_t e) {
+    if (e != cudaSuccess && rc == 0) {
+      g_create_error = cudaGetErrorString(e);
+      rc = 1;
+    }
+  };
+  const size_t hbytes = sizeof(double) * static_cast<size_t>(dof) * dof;
+  ok(cudaMalloc(&dgrid, sizeof(double) * 3 * G));
+  ok(cudaMalloc(&dtrial, sizeof(double) * 3 * G));
+  ok(cudaMalloc(&dtan, sizeof(double) * 6 * G));
+  ok(cudaMalloc(&dgp, sizeof(double) * 2 * nn));
+  ok(cudaMalloc(&ddir, sizeof(double) * 3 * nn));
+  ok(cudaMalloc(&dH, hbytes));
+  ok(cudaMalloc(&dS, hbytes));
+  ok(cudaMalloc(&db, sizeof(double) * dof));
+  ok(cudaMalloc(&dx, sizeof(double) * dof));
+  ok(cudaMalloc(&dcost, sizeof(double) * nn));
+  ok(cudaMalloc(&dsum, sizeof(double) * 2));
+  ok(cudaMalloc(&dinfo, sizeof(int) * 2));
+  if (rc == 0 && (cublasCreate(&cb) != CUBLAS_STATUS_SUCCESS || cusolverDnCreate(&cs) != CUSOLVER_STATUS_SUCCESS)) {
+    g_create_error = "cuBLAS / cuSOLVER initialisation failed";
+    rc = 1;
+  }
+  int lwork = 0;
+  if (rc == 0) {
+    if (cusolverDnDpotrf_bufferSize(cs, CUBLAS_FILL_MODE_LOWER, dof, dS, dof, &lwork) != CUSOLVER_STATUS_SUCCESS) {
+      g_create_error = "cusolverDnDpotrf_bufferSize failed";
+      rc = 1;
+    }
+    ok(cudaMalloc(&dwork, sizeof(double) * std::max(1, lwork)));
+  }
+  if (rc == 0) {
+    ok(cudaMemcpy(dgrid, grid, sizeof(double) * 3 * G, cudaMemcpyHostToDevice));
+    if (n > 0) {
+      ok(cudaMemcpy(dgp, grid_points, sizeof(double) * 2 * n, cudaMemcpyHostToDevice));
+      ok(cudaMemcpy(ddir, directions, sizeof(double) * 3 * n, cudaMemcpyHostToDevice));
+    }
+  }
+  double lambda = 0, last_cost = 0;
+  const double init_lambda_factor = static_cast<double>(0.001f);  // the call site passes a float literal
+  for (int iteration = 0; rc == 0 && iteration < max_iteration_count; ++iteration) {
+    launch_dirfit_tangents(G, dgrid, dtan, 0);
+    ok(cudaMemsetAsync(dH, 0, hbytes, 0));
+    ok(cudaMemsetAsync(db, 0, sizeof(double) * dof, 0));
+    launch_dirfit(true, gw, n, dgp, ddir, dgrid, dtan, dH, db, dof, dcost, dsum, 0);
+    ok(cudaMemcpy(&last_cost, dsum, sizeof(double), cudaMemcpyDeviceToHost));
+    if (rc) break;
+    if (iteration == 0) report->initial_cost = last_cost;
+    if (last_cost == 0) break;
+    if (iteration == 0) {
+      double trace = 0;  // the diagonal of J^T J is non-negative: sum |h_ii| = trace
+      if (cublasDasum(cb, dof, dH, dof + 1, &trace) != CUBLAS_STATUS_SUCCESS) {
+        g_create_error = "cublasDasum failed";
+        rc = 1;
+        break;
+      }
+      lambda = init_lambda_factor * trace / dof;
+    }
+    bool applied = false;
+    for (int attempt = 0; rc == 0 && attempt < 10; ++attempt) {
+      report->lm_attempts++;
+      ok(cudaMemcpyAsync(dS, dH, hbytes, cudaMemcpyDeviceToDevice, 0));
+      launch_add_diagonal(dof, dS, dof, lambda, 0);
+      ok(cudaMemcpyAsync(dx, db, sizeof(double) * dof, cudaMemcpyDeviceToDevice, 0));
+      int info[2] = {0, 0};
+      if (cusolverDnDpotrf(cs, CUBLAS_FILL_MODE_LOWER, dof, dS, dof, dwork, lwork, dinfo) != CUSOLVER_STATUS_SUCCESS ||
+          cusolverDnDpotrs(cs, CUBLAS_FILL_MODE_LOWER, dof, 1, dS, dof, dx, dof, dinfo + 1) != CUSOLVER_STATUS_SUCCESS) {
+        g_create_error = "cuSOLVER potrf / potrs failed";
+        rc = 1;
+        break;
+      }
+      ok(cudaMemcpy(info, dinfo, sizeof(info), cudaMemcpyDeviceToHost));
+      if (rc) break;
+      if (info[0] != 0) {  // not positive definite: the reference's NaN-update branch
+        lambda = 2.f * lambda;
+        continue;
+      }
+      launch_dirfit_update(G, dgrid, dx, dtrial, 0);
+      launch_dirfit(false, gw, n, dgp, ddir, dtrial, dtan, nullptr, nullptr, dof, dcost, dsum + 1, 0);
+      double test_cost = 0;
+      ok(cudaMemcpy(&test_cost, dsum + 1, sizeof(double), cudaMemcpyDeviceToHost));
+      if (rc) break;
+      if (test_cost < last_cost) {  // CostIsSmallerThan: every residual is valid in both states
+        std::swap(dgrid, dtrial);
+        lambda = 0.5f * lambda;
+        applied = true;
+        report->num_iterations_performed += 1;
+        last_cost = test_cost;
+        break;
+      }
+      lambda = 2.f * lambda;
+    }
+    if (!applied || last_cost == 0) break;
+  }
+  if (rc == 0) {
+    ok(cudaGetLastError());
+    ok(cudaMemcpy(grid, dgrid, sizeof(double) * 3 * G, cudaMemcpyDeviceToHost));
+    report->final_cost = last_cost;
+    report->final_lambda = lambda;
+  }
+  cudaFree(dgrid); cudaFree(dtrial); cudaFree(dtan); cudaFree(dgp); cudaFree(ddir); cudaFree(dH); cudaFree(dS);
+  cudaFree(db); cudaFree(dx); cudaFree(dcost); cudaFree(dsum); cudaFree(dinfo); cudaFree(dwork);
+  if (cb) cublasDestroy(cb);
+  if (cs) cusolverDnDestroy(cs);
+  return rc;
+}
+
 // ---- multi-GPU -------------------------------------------------------------------------------------
 int b200ba_nccl_unique_id(uint8_t id[B200BA_NCCL_UNIQUE_ID_BYTES]) {
   std::string err;

@@ -1599,4 +1599,177 @@ void launch_symmetrize(int n, double* M, cudaStream_t s) {
   symmetrize_kernel<<<grid, block, 0, s>>>(n, M);
 }
 
+// ---- direction-grid fit: CentralGenericBSplineDirectionCostFunction -----------
+// (APP/models/central_generic.cc:152-228, residual / Jacobian of :86-150). One thread per sample
+// (grid point, measured unit direction): r = normalise(sum w G) - m; d r / d (local update of
+// control point k) = w_k / |s| (I - u u^T) [t1 t2]_k. A warp holds 32 consecutive samples of a
+// raster scan, which almost always share the 4x4 support: the 3 x 32 Jacobians are staged in
+// shared memory and lane L sums the (a <= c) pairs p = L, L + 32, ... of J^T J over the 32
+// samples before ONE atomic per entry; a warp that straddles a cell border falls back to one set
+// of atomics per sample. Not a hot path (<= 90 000 samples, <= 3 LM iterations per resampling).
+__global__ void dirfit_tangents_kernel(int G, const double* __restrict__ grid, double* __restrict__ tan) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= G) return;
+  d3 t1, t2;
+  compute_tangents(ld3(grid + 3 * static_cast<int64_t>(i)), t1, t2);
+  double* o = tan + 6 * static_cast<int64_t>(i);
+  o[0] = t1.x; o[1] = t1.y; o[2] = t1.z;
+  o[3] = t2.x; o[4] = t2.y; o[5] = t2.z;
+}
+
+// support of grid point (gx, gy): top-left control point and the fractions in [0, 1)
+// (ix = floor(g + 2), x0 = ix - 3, frac = g + 2 - x0 - 3: central_generic.cc:94-98 in the
+// u-form of bspline_basis)
+__device__ __forceinline__ void dirfit_locate(double g, int& i0, double& u) {
+  const double f = floor(g + 2.0);
+  i0 = static_cast<int>(f) - 3;
+  u = (g + 2.0) - f;
+}
+
+constexpr int kDirfitRow = 33;  // padded row of the staged Jacobians (lane = sample)
+
+template <bool JAC>
+__global__ void __launch_bounds__(32) dirfit_kernel(int gw, int64_t n, const double* __restrict__ gp,
+                                                    const double* __restrict__ dirs, const double* __restrict__ grid,
+                                                    const double* __restrict__ tan, double* __restrict__ H,
+                                                    double* __restrict__ b, int dof, double* __restrict__ cost) {
+  __shared__ double sJ[JAC ? 96 * kDirfitRow : 1];
+  __shared__ double sR[JAC ? 3 * kDirfitRow : 1];
+  const int lane = threadIdx.x;
+  const int64_t i = blockIdx.x * 32ll + lane;
+  const bool active = i < n;
+  int x0 = 0, y0 = 0;
+  d3 r = mk3(0, 0, 0);
+  if (active) {
+    double fu, fv;
+    dirfit_locate(gp[2 * i], x0, fu);
+    dirfit_locate(gp[2 * i + 1], y0, fv);
+    double wx[4], dwx[4], wy[4], dwy[4];
+    bspline_basis(fu, wx, dwx);
+    bspline_basis(fv, wy, dwy);
+    d3 v, vx, vy;
+    spline3(grid, gw, x0, y0, wx, dwx, wy, dwy, v, vx, vy);
+    const double inv = 1.0 / sqrt(dot3(v, v));
+    const d3 u = inv * v;
+    r = u - mk3(dirs[3 * i], dirs[3 * i + 1], dirs[3 * i + 2]);
+    cost[i] = 0.5 * dot3(r, r);
+    if (JAC) {
+#pragma unroll 1
+      for (int k = 0; k < 16; ++k) {
+        const int seq = (x0 + (k & 3)) + (y0 + (k >> 2)) * gw;
+        const double w = sel4(wx, k & 3) * sel4(wy, k >> 2) * inv;
+        const d3 t1 = ld3(tan + 6 * static_cast<int64_t>(seq)), t2 = ld3(tan + 6 * static_cast<int64_t>(seq) + 3);
+        const d3 c1 = w * (t1 - dot3(u, t1) * u);
+        const d3 c2 = w * (t2 - dot3(u, t2) * u);
+        sJ[(0 * 32 + 2 * k) * kDirfitRow + lane] = c1.x;
+        sJ[(1 * 32 + 2 * k) * kDirfitRow + lane] = c1.y;
+        sJ[(2 * 32 + 2 * k) * kDirfitRow + lane] = c1.z;
+        sJ[(0 * 32 + 2 * k + 1) * kDirfitRow + lane] = c2.x;
+        sJ[(1 * 32 + 2 * k + 1) * kDirfitRow + lane] = c2.y;
+        sJ[(2 * 32 + 2 * k + 1) * kDirfitRow + lane] = c2.z;
+      }
+    }
+  }
+  if (!JAC) return;
+  if (!active) {
+    for (int row = 0; row < 96; ++row) sJ[row * kDirfitRow + lane] = 0.0;
+  }
+  sR[0 * kDirfitRow + lane] = r.x;
+  sR[1 * kDirfitRow + lane] = r.y;
+  sR[2 * kDirfitRow + lane] = r.z;
+  // inactive lanes adopt lane 0's support (their contributions are zero)
+  const int key = x0 + y0 * gw;
+  const int key0 = __shfl_sync(0xffffffffu, key, 0);
+  const bool uniform = __all_sync(0xffffffffu, !active || key == key0);
+  __syncwarp();
+  if (uniform) {
+    const int bx0 = __shfl_sync(0xffffffffu, x0, 0), by0 = __shfl_sync(0xffffffffu, y0, 0);
+    auto gidx = [&](int a) { return 2 * ((bx0 + ((a >> 1) & 3)) + (by0 + (a >> 3)) * gw) + (a & 1); };
+    // b: lane a owns entry a
+    {
+      double acc = 0;
+      for (int q = 0; q < 3; ++q)
+        for (int s2 = 0; s2 < 32; ++s2) acc = fma(sJ[(q * 32 + lane) * kDirfitRow + s2], sR[q * kDirfitRow + s2], acc);
+      atomicAdd(&b[gidx(lane)], acc);
+    }
+    // H: pairs (a <= c) in row-major order of the upper triangle, p = lane, lane + 32, ...
+    int a = 0, c = lane;  // pair index lane in row a = 0 (32 entries)
+    for (int p = lane; p < 528; p += 32) {
+      // advance (a, c) so that it is the p-th pair: rows have 32 - a entries
+      while (c >= 32) {
+        c = c - 32 + (a + 1);  // wrap into the next row, which starts at column a + 1
+        ++a;
+      }
+      double acc = 0;
+      for (int q = 0; q < 3; ++q) {
+        const double* ja = sJ + (q * 32 + a) * kDirfitRow;
+        const double* jc = sJ + (q * 32 + c) * kDirfitRow;
+        for (int s2 = 0; s2 < 32; ++s2) acc = fma(ja[s2], jc[s2], acc);
+      }
+      atomicAdd(&H[static_cast<int64_t>(gidx(a)) * dof + gidx(c)], acc);
+      c += 32;
+    }
+  } else if (active) {
+    auto gidx = [&](int a) { return 2 * ((x0 + ((a >> 1) & 3)) + (y0 + (a >> 3)) * gw) + (a & 1); };
+    for (int a = 0; a < 32; ++a) {
+      const double j0 = sJ[(0 * 32 + a) * kDirfitRow + lane], j1 = sJ[(1 * 32 + a) * kDirfitRow + lane],
+                   j2 = sJ[(2 * 32 + a) * kDirfitRow + lane];
+      atomicAdd(&b[gidx(a)], fma(j0, r.x, fma(j1, r.y, j2 * r.z)));
+      const int64_t rowoff = static_cast<int64_t>(gidx(a)) * dof;
+      for (int c = a; c < 32; ++c)
+        atomicAdd(&H[rowoff + gidx(c)], fma(j0, sJ[(0 * 32 + c) * kDirfitRow + lane],
+                                            fma(j1, sJ[(1 * 32 + c) * kDirfitRow + lane],
+                                                j2 * sJ[(2 * 32 + c) * kDirfitRow + lane])));
+    }
+  }
+}
+
+// deterministic sum of n doubles (one block)
+__global__ void dirfit_sum_kernel(int64_t n, const double* __restrict__ v, double* __restrict__ out) {
+  __shared__ double sh[1024];
+  double acc = 0;
+  for (int64_t i = threadIdx.x; i < n; i += 1024) acc += v[i];
+  sh[threadIdx.x] = acc;
+  __syncthreads();
+  for (int o = 512; o > 0; o >>= 1) {
+    if (threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[0] = sh[0];
+}
+
+// DirectionGridStateWithLocalUpdates::operator-= (central_generic.cc:65-80):
+// d <- normalise(d - x0 t1 - x1 t2) with the tangents of the OLD direction
+__global__ void dirfit_update_kernel(int G, const double* __restrict__ grid, const double* __restrict__ x,
+                                     double* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= G) return;
+  const d3 d = ld3(grid + 3 * static_cast<int64_t>(i));
+  d3 t1, t2;
+  compute_tangents(d, t1, t2);
+  const d3 nd = (d + (-x[2 * i]) * t1) + (-x[2 * i + 1]) * t2;
+  const double n = sqrt(dot3(nd, nd));
+  out[3 * static_cast<int64_t>(i)] = nd.x / n;
+  out[3 * static_cast<int64_t>(i) + 1] = nd.y / n;
+  out[3 * static_cast<int64_t>(i) + 2] = nd.z / n;
+}
+
+void launch_dirfit_tangents(int G, const double* grid, double* tan, cudaStream_t s) {
+  if (G > 0) dirfit_tangents_kernel<<<(G + 127) / 128, 128, 0, s>>>(G, grid, tan);
+}
+void launch_dirfit(bool jac, int gw, int64_t n, const double* gp, const double* dirs, const double* grid,
+                   const double* tan, double* H, double* b, int dof, double* cost, double* cost_sum, cudaStream_t s) {
+  if (n > 0) {
+    const unsigned blocks = static_cast<unsigned>((n + 31) / 32);
+    if (jac)
+      dirfit_kernel<true><<<blocks, 32, 0, s>>>(gw, n, gp, dirs, grid, tan, H, b, dof, cost);
+    else
+      dirfit_kernel<false><<<blocks, 32, 0, s>>>(gw, n, gp, dirs, grid, tan, H, b, dof, cost);
+  }
+  dirfit_sum_kernel<<<1, 1024, 0, s>>>(n, cost, cost_sum);
+}
+void launch_dirfit_update(int G, const double* grid, const double* x, double* out, cudaStream_t s) {
+  if (G > 0) dirfit_update_kernel<<<(G + 127) / 128, 128, 0, s>>>(G, grid, x, out);
+}
+
 }  // namespace b200ba

@@ -50,6 +50,11 @@ void launch_unproject_pixels(const CamDev& c, const double* intr, int64_t n, con
 void launch_generic_block_inverse(int bs, int nb, int nd, const double* D, const double* B, const double* b1,
                                   double* DinvB, double* Dinvb, cudaStream_t s);
 void launch_symmetrize(int n, double* M, cudaStream_t s);
+// direction-grid fit (b200ba_fit_directions)
+void launch_dirfit_tangents(int G, const double* grid, double* tan, cudaStream_t s);
+void launch_dirfit(bool jac, int gw, int64_t n, const double* gp, const double* dirs, const double* grid,
+                   const double* tan, double* H, double* b, int dof, double* cost, double* cost_sum, cudaStream_t s);
+void launch_dirfit_update(int G, const double* grid, const double* x, double* out, cudaStream_t s);
 void launch_permute_double2(int64_t n, const uint32_t* perm, const double2* src, double2* dst, bool scatter,
                             cudaStream_t s);
 

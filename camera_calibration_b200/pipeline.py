@@ -3,7 +3,7 @@ loop ``RunBundleAdjustment`` (applications/camera_calibration/src/camera_calibra
 with its per-iteration checkpoint and ``ChooseNiceCameraOrientation``
 (models/central_generic.cc:570-621), the outlier deletion between BA rounds
 (``DeleteOutlierFeatures``, calibration.cc:62-184) and ``ScaleToMetric``
-(calibration.cc:307-370; 8f-4). Host logic only; every numerical step (un-projection, the LM
+(calibration.cc:307-370; 8f-4) and the pyramid step ``ResampleModel`` (calibration.cc:373-522; 8f-4). Host logic only; every numerical step (un-projection, the LM
 iteration) runs in ``libb200ba.so``.
 """
 from __future__ import annotations
@@ -201,6 +201,79 @@ def ScaleToMetric(dataset: Dataset, state: BAState) -> float:
     factor = math.exp(log_sum / count)
     state.ScaleState(factor)
     return factor
+
+
+def _interpolate_bilinear(image: np.ndarray, x: float, y: float) -> np.ndarray:
+    """libvis Image::InterpolateBilinear for vector pixels (libvis/image.h:152-176): integer part by
+    truncation, FLOAT weights, double accumulation."""
+    ix, iy = int(x), int(y)
+    fx = np.float32(x - ix)
+    fy = np.float32(y - iy)
+    fx_inv = np.float32(1) - fx
+    fy_inv = np.float32(1) - fy
+    return (float(fx_inv * fy_inv) * image[iy, ix] + float(fx * fy_inv) * image[iy, ix + 1]
+            + float(fx_inv * fy) * image[iy + 1, ix] + float(fx * fy) * image[iy + 1, ix + 1])
+
+
+def ResampleModel(model_to_optimize: CameraModel, camera_tr_rig: np.ndarray, calibration_min_x: int,
+                  calibration_min_y: int, calibration_max_x: int, calibration_max_y: int,
+                  model_type: CameraModel.Type, target_resolution_x: int, target_resolution_y: int,
+                  fit_fn=None, unproject_many=None):
+    """calibration.cc:373-522 for the generic target models (the radial / thin-prism / OpenCV
+    targets are outside this path): returns ``(ok, new_model)``; ``camera_tr_rig`` is untouched for
+    these targets (only the parametric fits rotate it).
+      * NoncentralGeneric -> NoncentralGeneric: both grids re-sampled bilinearly (:386-424);
+      * otherwise a dense direction image of the old model (one ``Unproject`` per pixel centre, on
+        the device) is fitted by a CentralGenericModel of the target resolution
+        (``FitToDenseModel(dense, step, 3)``; at most 300 x 300 samples), optionally wrapped into a
+        NoncentralGenericModel with zero origins."""
+    T = CameraModel.Type
+    model_type = T(model_type)
+    if model_to_optimize.type() == T.NoncentralGeneric and model_type == T.NoncentralGeneric:
+        old = model_to_optimize
+        ogh, ogw = old.direction_grid().shape[:2]
+        new_points = np.zeros((target_resolution_y, target_resolution_x, 3))
+        new_dirs = np.zeros((target_resolution_y, target_resolution_x, 3))
+        for y in range(target_resolution_y):
+            for x in range(target_resolution_x):
+                pixel = CentralGenericModel.GridPointToPixelCornerConvStatic(
+                    x, y, calibration_min_x, calibration_min_y, calibration_max_x, calibration_max_y,
+                    target_resolution_x, target_resolution_y)
+                g = old.PixelCornerConvToGridPoint(pixel[0], pixel[1])
+                g = np.minimum(np.maximum(g, 0.0), np.array([ogw - 1.001, ogh - 1.001]))
+                new_points[y, x] = _interpolate_bilinear(old.point_grid(), g[0], g[1])
+                new_dirs[y, x] = _interpolate_bilinear(old.direction_grid(), g[0], g[1])
+        new = api.NoncentralGenericModel(target_resolution_x, target_resolution_y, calibration_min_x, calibration_min_y,
+                                         calibration_max_x, calibration_max_y, old.width(), old.height())
+        new.SetPointGrid(new_points)
+        new.SetDirectionGrid(new_dirs)
+        return True, new
+    if model_to_optimize.type() == T.NoncentralGeneric:
+        return False, model_to_optimize  # not implemented in the reference either (:426-429)
+    if model_type not in (T.CentralGeneric, T.NoncentralGeneric):
+        return False, model_to_optimize  # parametric targets: outside this path
+    # dense direction model of the old camera
+    w, h = model_to_optimize.width(), model_to_optimize.height()
+    xs, ys = np.meshgrid(np.arange(w) + 0.5, np.arange(h) + 0.5)
+    pixels = np.stack([xs.ravel(), ys.ravel()], -1)
+    if unproject_many is None:
+        unproject_many = lambda m, px: m.UnprojectMany(px)  # noqa: E731
+    dirs, _, ok = unproject_many(model_to_optimize, pixels)
+    dense = np.where(ok[:, None], dirs, np.nan).reshape(h, w, 3)
+    area_w = calibration_max_x - calibration_min_x + 1
+    area_h = calibration_max_y - calibration_min_y + 1
+    # std::round(int / int): the integer quotient is already integral
+    subsample_step = max(1, min(area_w // 300, area_h // 300))
+    new_central = CentralGenericModel(target_resolution_x, target_resolution_y, calibration_min_x, calibration_min_y,
+                                      calibration_max_x, calibration_max_y, w, h)
+    if not new_central.FitToDenseModel(dense, subsample_step, 3, fit_fn=fit_fn):
+        return False, model_to_optimize
+    if model_type == T.NoncentralGeneric:
+        new = api.NoncentralGenericModel(target_resolution_x, target_resolution_y, calibration_min_x, calibration_min_y,
+                                         calibration_max_x, calibration_max_y, w, h)
+        new.InitializeFromCentralGenericModel(new_central)
+        return True, new
+    return True, new_central
 
 
 def BundleAdjustment(state_directory: str, model_input_directory: str, model_output_directory: str,

@@ -215,6 +215,29 @@ B200BA_API int b200ba_project(int device, const b200ba_camera* cam, const double
 B200BA_API int b200ba_unproject(int device, const b200ba_camera* cam, const double* intrinsics, int64_t n,
                      const double* pixels, double* directions, double* origins, int32_t* ok);
 
+/* ---- model resampling (row f-4): CentralGenericModel::FitToPixelDirectionsImpl --------
+ * (APP/models/central_generic.cc:551-568 with the cost function of :152-228 and the state of
+ * :40-83). Levenberg-Marquardt over the direction grid -- 2 local DoF per control point in its
+ * tangent frame -- so that the normalised B-spline un-projection at n grid points matches n unit
+ * directions: LMOptimizer::Optimize(max_iteration_count, max_lm_attempts = 10, init_lambda = -1,
+ * init_lambda_factor = 0.001f), quadratic loss (cost = 1/2 sum r^2 over the 3n scalar residuals),
+ * dense solve. Called by FitToDenseModel / FitToPixelDirections when a model is resampled to
+ * another grid resolution (APP/calibration.cc:373-522).
+ *   grid         [3 * grid_width * grid_height] in/out, row-major, unit directions
+ *   grid_points  [2 n] grid coordinates (PixelCornerConvToGridPoint of the sample pixels); each
+ *                must have its 4x4 support inside the grid (1 <= g < size - 2)
+ *   directions   [3 n] */
+typedef struct b200ba_fit_report {
+  double initial_cost;
+  double final_cost;
+  double final_lambda;
+  int32_t num_iterations_performed;
+  int32_t lm_attempts; /* total number of linear solves */
+} b200ba_fit_report;
+B200BA_API int b200ba_fit_directions(int device, int32_t grid_width, int32_t grid_height, double* grid, int64_t n,
+                          const double* grid_points, const double* directions, int32_t max_iteration_count,
+                          b200ba_fit_report* report);
+
 /* ---- multi-GPU: imagesets sharded over ranks, one NCCL all-reduce per H/b build --- */
 #define B200BA_NCCL_UNIQUE_ID_BYTES 128
 B200BA_API int b200ba_nccl_unique_id(uint8_t id[B200BA_NCCL_UNIQUE_ID_BYTES]);

@@ -1806,6 +1806,142 @@ int oracle_project(const b200ba_camera* cam, const double* intrinsics, int64_t n
   return 0;
 }
 
+// CentralGenericBSplineDirectionCostFunction::Compute (APP/models/central_generic.cc:152-228):
+// Compute<true>  -> ComputeUnprojectedDirectionResidualAndJacobianWrtGridUpdates (:86-150): the
+//                   normalised spline and d/d(control point) = w/|s| (I - u u^T) (generated code
+//                   central_generic_jacobians.cc:31-317 re-derived), chained with [t1 t2] of the
+//                   control point (DirectionJacobianWrtLocalUpdate, direction_parametrization.h:62-70);
+// Compute<false> -> UnprojectFromGrid (b_spline.h fast evaluation, normalised).
+// Quadratic loss: cost entry 1/2 r^2 per scalar residual.
+static double dirfit_compute(bool jac, int gw, int gh, const std::vector<double>& grid, int64_t n,
+                             const double* gp, const double* dirs, std::vector<double>* H,
+                             std::vector<double>* b, std::vector<double>* costs) {
+  const int dof = 2 * gw * gh;
+  std::vector<Tangents> tan;
+  if (jac) {
+    tan.resize(size_t(gw) * gh);
+    for (int i = 0; i < gw * gh; ++i) tan[i] = compute_tangents(grid_at(grid.data(), gw, i % gw, i / gw));
+    std::fill(H->begin(), H->end(), 0.0);
+    std::fill(b->begin(), b->end(), 0.0);
+  }
+  costs->clear();
+  double cost = 0;
+  for (int64_t i = 0; i < n; ++i) {
+    const V3 m = mk(dirs[3 * i], dirs[3 * i + 1], dirs[3 * i + 2]);
+    const double gx = gp[2 * i], gy = gp[2 * i + 1];
+    V3 r;
+    if (!jac) {
+      r = normalized(bspline_surface(grid.data(), gw, gx, gy)) - m;
+    } else {
+      const int ix = static_cast<int>(std::floor(gx + 2)), iy = static_cast<int>(std::floor(gy + 2));
+      const int x0 = ix - 3, y0 = iy - 3;
+      double wx[4], wy[4];
+      bspline_weights(gx + 2 - x0, wx);
+      bspline_weights(gy + 2 - y0, wy);
+      V3 sum = mk(0, 0, 0);
+      for (int rr = 0; rr < 4; ++rr) {
+        V3 a = mk(0, 0, 0);
+        for (int c = 0; c < 4; ++c) a = a + wx[c] * grid_at(grid.data(), gw, x0 + c, y0 + rr);
+        sum = sum + wy[rr] * a;
+      }
+      const double inv_n = 1.0 / std::sqrt(dot(sum, sum));
+      const V3 u = inv_n * sum;
+      r = u - m;
+      double J[3][32];
+      int idx[32];
+      for (int rr = 0; rr < 4; ++rr)
+        for (int c = 0; c < 4; ++c) {
+          const int k = c + 4 * rr;
+          const int seq = (x0 + c) + (y0 + rr) * gw;
+          const double w = wx[c] * wy[rr] * inv_n;
+          const Tangents& t = tan[seq];
+          const V3 c1 = w * (t.t1 - dot(u, t.t1) * u);
+          const V3 c2 = w * (t.t2 - dot(u, t.t2) * u);
+          idx[2 * k] = 2 * seq;
+          idx[2 * k + 1] = 2 * seq + 1;
+          for (int q = 0; q < 3; ++q) {
+            J[q][2 * k] = comp(c1, q);
+            J[q][2 * k + 1] = comp(c2, q);
+          }
+        }
+      // three scalar residuals, each AddResidualWithJacobian(residual, indices, row)
+      for (int q = 0; q < 3; ++q) {
+        const double rq = comp(r, q);
+        for (int a = 0; a < 32; ++a) {
+          (*b)[idx[a]] += J[q][a] * rq;
+          for (int c = a; c < 32; ++c) (*H)[size_t(idx[a]) * dof + idx[c]] += J[q][a] * J[q][c];
+        }
+      }
+    }
+    for (int q = 0; q < 3; ++q) {
+      const double c = 0.5 * comp(r, q) * comp(r, q);
+      costs->push_back(c);
+      cost += c;
+    }
+  }
+  return cost;
+}
+
+// CentralGenericModel::FitToPixelDirectionsImpl (APP/models/central_generic.cc:551-568):
+// LMOptimizer<double>::Optimize(state, cost, max_iteration_count, max_lm_attempts 10,
+// init_lambda -1, init_lambda_factor 0.001f) with DirectionGridStateWithLocalUpdates (:40-83),
+// no Schur structure -> SolveDensely (LV/lm_optimizer.h:1013-1024).
+int oracle_fit_directions(int32_t gw, int32_t gh, double* grid_io, int64_t n, const double* grid_points,
+                          const double* directions, int32_t max_iteration_count, b200ba_fit_report* report) {
+  if (gw < 4 || gh < 4 || !grid_io || n < 0 || !report) return 1;
+  memset(report, 0, sizeof(*report));
+  const int dof = 2 * gw * gh;
+  std::vector<double> grid(grid_io, grid_io + size_t(3) * gw * gh);
+  std::vector<double> H(size_t(dof) * dof), b(dof), x(dof), orig_diag(dof), costs, test_costs;
+  double lambda = 0, last_cost = 0;
+  const double init_lambda_factor = static_cast<double>(0.001f);
+  for (int iteration = 0; iteration < max_iteration_count; ++iteration) {
+    last_cost = dirfit_compute(true, gw, gh, grid, n, grid_points, directions, &H, &b, &costs);
+    if (iteration == 0) report->initial_cost = last_cost;
+    if (last_cost == 0) break;
+    if (iteration == 0) {
+      lambda = 0;
+      for (int i = 0; i < dof; ++i) lambda += H[size_t(i) * dof + i];
+      lambda = init_lambda_factor * lambda / dof;
+    }
+    for (int i = 0; i < dof; ++i) orig_diag[i] = H[size_t(i) * dof + i];
+    bool applied = false;
+    for (int attempt = 0; attempt < 10; ++attempt) {
+      report->lm_attempts++;
+      for (int i = 0; i < dof; ++i) H[size_t(i) * dof + i] = orig_diag[i] + lambda;
+      ldlt_solve(dof, H.data(), dof, b.data(), 1, 1, x.data(), 1);
+      if (std::isnan(x[0])) {
+        lambda = 2.f * lambda;
+        continue;
+      }
+      // DirectionGridStateWithLocalUpdates::operator-= (central_generic.cc:65-80)
+      std::vector<double> updated = grid;
+      for (int i = 0; i < gw * gh; ++i) {
+        const V3 d = grid_at(grid.data(), gw, i % gw, i / gw);
+        const V3 nd = apply_local_update_to_direction(d, compute_tangents(d), -x[2 * i], -x[2 * i + 1]);
+        updated[3 * i] = nd.x;
+        updated[3 * i + 1] = nd.y;
+        updated[3 * i + 2] = nd.z;
+      }
+      const double test_cost = dirfit_compute(false, gw, gh, updated, n, grid_points, directions, nullptr, nullptr, &test_costs);
+      if (cost_is_smaller_than(test_costs, costs)) {
+        grid = updated;
+        lambda = 0.5f * lambda;
+        applied = true;
+        report->num_iterations_performed += 1;
+        last_cost = test_cost;
+        break;
+      }
+      lambda = 2.f * lambda;
+    }
+    if (!applied || last_cost == 0) break;
+  }
+  report->final_cost = last_cost;
+  report->final_lambda = lambda;
+  std::copy(grid.begin(), grid.end(), grid_io);
+  return 0;
+}
+
 int oracle_unproject(const b200ba_camera* cam, const double* intrinsics, int64_t n,
                      const double* pixels, double* directions, double* origins, int32_t* ok) {
   std::vector<double> p(intrinsics, intrinsics + intr_size(cam));

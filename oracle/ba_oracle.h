@@ -62,6 +62,12 @@ int oracle_unproject_jacobian(const b200ba_camera* cam, const double* intrinsics
                               const double* pixels, double* directions, double* origins,
                               double* jac, int32_t* ok);
 
+/* CentralGenericModel::FitToPixelDirectionsImpl (APP/models/central_generic.cc:551-568); the
+ * arguments of b200ba_fit_directions. */
+int oracle_fit_directions(int32_t grid_width, int32_t grid_height, double* grid, int64_t n,
+                          const double* grid_points, const double* directions,
+                          int32_t max_iteration_count, b200ba_fit_report* report);
+
 /* b_spline.h: fast (EvalUniformCubicBSplineSurface :65-104) and slow (:168-186) evaluation
  * of a 3-vector grid at grid coordinates (x, y). */
 int oracle_bspline_eval(int32_t gw, int32_t gh, const double* grid, double x, double y, int slow,

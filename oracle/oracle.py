@@ -193,6 +193,23 @@ def project(cam: Camera, intrinsics, local_points, initial_pixels=None):
     return px, ok.astype(bool)
 
 
+def fit_directions(gw: int, gh: int, grid, grid_points, directions, max_iteration_count: int):
+    """Returns (new grid [gh, gw, 3], FitReport)."""
+    from camera_calibration_b200.cabi import FitReport
+    g = np.ascontiguousarray(grid, dtype=np.float64).reshape(-1).copy()
+    gp = np.ascontiguousarray(grid_points, dtype=np.float64).reshape(-1, 2)
+    d = np.ascontiguousarray(directions, dtype=np.float64).reshape(-1, 3)
+    rep = FitReport()
+    f = lib().oracle_fit_directions
+    f.restype = C.c_int
+    f.argtypes = [C.c_int32, C.c_int32, C.POINTER(C.c_double), C.c_int64, C.POINTER(C.c_double),
+                  C.POINTER(C.c_double), C.c_int32, C.POINTER(FitReport)]
+    rc = f(gw, gh, _p(g), len(gp), _p(gp), _p(d), max_iteration_count, C.byref(rep))
+    if rc != 0:
+        raise RuntimeError("oracle_fit_directions failed")
+    return g.reshape(gh, gw, 3), rep
+
+
 def unproject(cam: Camera, intrinsics, pixels, with_jacobian=False):
     px = np.ascontiguousarray(pixels, dtype=np.float64).reshape(-1, 2)
     n = len(px)

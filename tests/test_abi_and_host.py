@@ -36,12 +36,12 @@ def test_struct_layouts_match_header():
     src = r'''
 #include <stdio.h>
 #include "b200ba.h"
-int main(){printf("%zu %zu %zu %zu %zu %zu\n", sizeof(b200ba_camera), sizeof(b200ba_problem), sizeof(b200ba_state),
- sizeof(b200ba_options), sizeof(b200ba_report), sizeof(b200ba_timings));return 0;}'''
+int main(){printf("%zu %zu %zu %zu %zu %zu %zu\n", sizeof(b200ba_camera), sizeof(b200ba_problem), sizeof(b200ba_state),
+ sizeof(b200ba_options), sizeof(b200ba_report), sizeof(b200ba_timings), sizeof(b200ba_fit_report));return 0;}'''
     exe = "/tmp/_b200ba_sizes"
     subprocess.run(["gcc", "-x", "c", "-", "-I", os.path.join(ROOT, "include"), "-o", exe], input=src.encode(), check=True)
     sizes = [int(v) for v in subprocess.check_output([exe]).split()]
-    mine = [C.sizeof(t) for t in (cabi.Camera, cabi.Problem, cabi.State, cabi.Options, cabi.Report, cabi.Timings)]
+    mine = [C.sizeof(t) for t in (cabi.Camera, cabi.Problem, cabi.State, cabi.Options, cabi.Report, cabi.Timings, cabi.FitReport)]
     assert sizes == mine
 
 
