@@ -181,7 +181,7 @@ def run_reference(args):
         "impl": "reference", "metric": "LM iterations/sec", "value": val, "unit": "LM iterations/s",
         "n_gpus": args.gpus, "steps": steps, "warmup": args.warmup, "ms_per_step": 1e3 * sec,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": workload_config(sp, args, 1),
+        "config": workload_config(sp, args, max(1, args.gpus)),  # the same config object as the b200 arm's line
         "cpu_baseline": {k: base[k] for k in ("unit", "cores", "kind", "sample")} | {"value": val},
         "e2e": {"value": val, "unit": "LM iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,

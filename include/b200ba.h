@@ -266,6 +266,15 @@ B200BA_API int b200ba_get_timings(const b200ba_handle* h, b200ba_timings* t);
 
 B200BA_API const char* b200ba_version(void);
 
+/* ---- diagnostics (not part of the reference interface) ---------------------------------
+ * Evaluation budget of the main residual/Jacobian pass (default 16 spline evaluations per
+ * observation; what exceeds it is redone by the straggler pass). 1 sends every observation of
+ * a generic camera through the straggler pass (tests). Process-wide. */
+B200BA_API void b200ba_debug_set_eval_budget(int budget);
+/* Spline evaluations the projection LM spent per observation in the last pass that wrote
+ * Jacobians; counts [n_obs], caller's observation order. */
+B200BA_API int b200ba_debug_eval_counts(b200ba_handle* h, uint16_t* counts);
+
 #ifdef __cplusplus
 }
 #endif

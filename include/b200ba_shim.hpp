@@ -71,6 +71,32 @@ class CentralGenericModel : public CameraModel {
   bool GetGridResolution(int* rx, int* ry) const override { *rx = gw; *ry = gh; return true; }
   std::vector<double>& flat_intrinsics() override { return grid; }
   static constexpr int IntrinsicsJacobianSize = 2 * 16;
+  // central_grid.h:150-154 (double arithmetic with the float constant (grid - 3.f))
+  Vec2d PixelCornerConvToGridPoint(double x, double y) const {
+    return Vec2d{1.0 + static_cast<double>(gw - 3.f) * (x - m_calibration_min_x) / (m_calibration_max_x + 1 - m_calibration_min_x),
+                 1.0 + static_cast<double>(gh - 3.f) * (y - m_calibration_min_y) / (m_calibration_max_y + 1 - m_calibration_min_y)};
+  }
+  // central_generic.cc:424-431 + :551-568: the LM over the direction grid runs in the library
+  void FitToPixelDirections(const std::vector<Vec2d>& pixels, const std::vector<Vec3d>& directions,
+                            int max_iteration_count) {
+    std::vector<double> gp, d;
+    gp.reserve(2 * pixels.size());
+    d.reserve(3 * directions.size());
+    for (const Vec2d& p : pixels) {
+      const Vec2d g = PixelCornerConvToGridPoint(p.x, p.y);
+      gp.push_back(g.x);
+      gp.push_back(g.y);
+    }
+    for (const Vec3d& v : directions) {
+      d.push_back(v.x);
+      d.push_back(v.y);
+      d.push_back(v.z);
+    }
+    b200ba_fit_report rep;
+    if (b200ba_fit_directions(-1, gw, gh, grid.data(), static_cast<int64_t>(pixels.size()), gp.data(), d.data(),
+                              max_iteration_count, &rep) != 0)
+      throw std::runtime_error(std::string("b200ba_fit_directions: ") + b200ba_last_error(nullptr));
+  }
   int gw, gh;
   std::vector<double> grid;
 };

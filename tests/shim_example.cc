@@ -51,6 +51,17 @@ int main() {
     double c1 = OptimizeJointly(dataset, &state, 3, lambda, 1e-4, 0, false, true, SchurMode::Dense, &lambda, &performed,
                                 false, false, false, false, false, false);
     std::printf("shim: cost after 1 iteration %.6g, after 4 iterations %.6g\n", c0, c1);
+    // model fitting (FitToPixelDirections): pull the grid towards a shifted pinhole camera
+    std::vector<Vec2d> pixels;
+    std::vector<Vec3d> directions;
+    for (int y = 0; y < H; y += 8)
+      for (int x = 0; x < W; x += 8) {
+        pixels.push_back(Vec2d{x + 0.5, y + 0.5});
+        double d[3] = {(x + 0.5 - (W / 2.0 - 4)) / 200.0, (y + 0.5 - (H / 2.0 + 6)) / 200.0, 1.0};
+        const double n = std::sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+        directions.push_back(Vec3d{d[0] / n, d[1] / n, d[2] / n});
+      }
+    model->FitToPixelDirections(pixels, directions, 5);
     return (c1 <= c0) ? 0 : 1;
   } catch (const std::exception& e) {
     std::printf("shim: error: %s\n", e.what());
