@@ -276,6 +276,64 @@ def ResampleModel(model_to_optimize: CameraModel, camera_tr_rig: np.ndarray, cal
     return True, new_central
 
 
+def ComputeGridResolution(calibration_area_width: int, calibration_area_height: int, exterior_cells_per_side: int,
+                          approx_pixels_per_cell: int):
+    """calibration.cc:531-540: integer division, + 0.5f, + the exterior cells, truncated."""
+    rx = int(np.float32(calibration_area_width // approx_pixels_per_cell) + np.float32(0.5) + np.float32(2 * exterior_cells_per_side))
+    ry = int(np.float32(calibration_area_height // approx_pixels_per_cell) + np.float32(0.5) + np.float32(2 * exterior_cells_per_side))
+    return rx, ry
+
+
+def ComputeGridResolutionForModel(model: CameraModel, approx_pixels_per_cell: int):
+    """calibration.cc:542-560."""
+    w = model.calibration_max_x() - model.calibration_min_x() + 1
+    h = model.calibration_max_y() - model.calibration_min_y() + 1
+    exterior = model.exterior_cells_per_side() if hasattr(model, "exterior_cells_per_side") else 0
+    return ComputeGridResolution(w, h, exterior, approx_pixels_per_cell)
+
+
+def CalcGridResolutionForLevel(pyramid_level: int, full_resolution_x: int, full_resolution_y: int):
+    """calibration.cc:566-569."""
+    f = math.pow(1.333, -pyramid_level)
+    return int(full_resolution_x * f + float(np.float32(0.5))), int(full_resolution_y * f + float(np.float32(0.5)))
+
+
+def ComputeIntegerBoundingRectForFeatures(dataset: Dataset, camera_index: int, image_used):
+    """calibration.cc:615-641: (min_x, min_y, max_x, max_y) of the truncated feature positions."""
+    min_x = min_y = np.iinfo(np.int32).max
+    max_x = max_y = 0
+    for i in range(dataset.ImagesetCount()):
+        if not image_used[i]:
+            continue
+        xy = dataset.GetImageset(i).FeaturesOfCamera(camera_index)["xy"]
+        if len(xy) == 0:
+            continue
+        t = xy.astype(np.int64)  # static_cast<int>: truncation
+        min_x, min_y = min(min_x, int(t[:, 0].min())), min(min_y, int(t[:, 1].min()))
+        max_x, max_y = max(max_x, int(t[:, 0].max())), max(max_y, int(t[:, 1].max()))
+    return min_x, min_y, max_x, max_y
+
+
+def ResampleModelsIfNecessary(dataset: Dataset, state: BAState, model_type: CameraModel.Type,
+                              approx_pixels_per_cell: int, pyramid_level: int, fit_fn=None, unproject_many=None) -> int:
+    """calibration.cc:572-612: re-sample every camera whose grid resolution differs from the one
+    wanted on this pyramid level, or whose type differs. Returns the number of re-sampled models."""
+    count = 0
+    for c in range(dataset.num_cameras()):
+        model = state.intrinsics[c]
+        loaded = model.GetGridResolution()
+        fx, fy = ComputeGridResolutionForModel(model, approx_pixels_per_cell)
+        dx, dy = CalcGridResolutionForLevel(pyramid_level, fx, fy)
+        if (loaded and tuple(loaded) != (dx, dy)) or model.type() != CameraModel.Type(model_type):
+            ok, new = ResampleModel(model, state.camera_tr_rig[c], model.calibration_min_x(), model.calibration_min_y(),
+                                    model.calibration_max_x(), model.calibration_max_y(), model_type, dx, dy,
+                                    fit_fn=fit_fn, unproject_many=unproject_many)
+            if ok:
+                state.intrinsics[c] = new
+                count += 1
+    return count
+
+
 def BundleAdjustment(state_directory: str, model_input_directory: str, model_output_directory: str,
                      max_iteration_count: int = 30) -> int:
     """The ``--bundle_adjustment`` tool (tools/bundle_adjustment.cc:50-220): load

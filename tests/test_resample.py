@@ -177,3 +177,38 @@ def test_model_optimization_on_device():
 @pytest.mark.gpu
 def test_resample_real_camera_on_device():
     _resample_real_camera(None, device_unproject_many)
+
+
+def test_grid_resolution_helpers():
+    """calibration.cc:531-569,615-641; SURVEY.md 8d: 2050x1450 at 25 px per cell -> 84x60."""
+    assert pipeline.ComputeGridResolution(2050, 1450, 1, 25) == (84, 60)
+    assert pipeline.ComputeGridResolution(1200, 950, 1, 25) == (50, 40)
+    m = api.CentralGenericModel(84, 60, 0, 0, 2049, 1449, 2050, 1450)
+    assert pipeline.ComputeGridResolutionForModel(m, 25) == (84, 60)
+    assert pipeline.CalcGridResolutionForLevel(0, 84, 60) == (84, 60)
+    assert pipeline.CalcGridResolutionForLevel(2, 84, 60) == (int(84 * 1.333 ** -2 + 0.5), int(60 * 1.333 ** -2 + 0.5))
+    ds = api.Dataset(1)
+    for k, off in enumerate((0.0, 7.9)):
+        s = ds.NewImageset()
+        s.SetFeaturesOfCamera(0, np.array([[10.7 + off, 20.2], [300.9, 250.99 - off]]), [1, 2])
+    assert pipeline.ComputeIntegerBoundingRectForFeatures(ds, 0, [True, True]) == (10, 20, 300, 250)
+    assert pipeline.ComputeIntegerBoundingRectForFeatures(ds, 0, [False, True]) == (18, 20, 300, 243)
+
+
+def test_resample_models_if_necessary(oracle_lib):
+    cam, grid = helpers.real_camera()
+    old = api.CentralGenericModel(cam.grid_width, cam.grid_height, cam.calibration_min_x, cam.calibration_min_y,
+                                  cam.calibration_max_x, cam.calibration_max_y, cam.width, cam.height)
+    old.SetGrid(grid)
+    st = api.BAState()
+    st.intrinsics = [old]
+    st.camera_tr_rig = np.array([[1.0, 0, 0, 0, 0, 0, 0]])
+    ds = api.Dataset(1)
+    want = pipeline.CalcGridResolutionForLevel(1, *pipeline.ComputeGridResolutionForModel(old, 50))
+    n = pipeline.ResampleModelsIfNecessary(ds, st, api.CameraModel.Type.CentralGeneric, 50, 1, fit_fn=oracle_fit,
+                                           unproject_many=oracle_unproject_many)
+    assert n == 1 and st.intrinsics[0].GetGridResolution() == want
+    # already at the wanted resolution and type: untouched
+    m = st.intrinsics[0]
+    assert pipeline.ResampleModelsIfNecessary(ds, st, api.CameraModel.Type.CentralGeneric, 50, 1, fit_fn=oracle_fit,
+                                              unproject_many=oracle_unproject_many) == 0 and st.intrinsics[0] is m
