@@ -242,7 +242,13 @@ B200BA_API int b200ba_fit_directions(int device, int32_t grid_width, int32_t gri
 #define B200BA_NCCL_UNIQUE_ID_BYTES 128
 B200BA_API int b200ba_nccl_unique_id(uint8_t id[B200BA_NCCL_UNIQUE_ID_BYTES]);
 /* Every rank creates its handle from ITS shard of the observations (all ranks use the
- * same n_imagesets / n_points / cameras) and then joins the communicator. */
+ * same n_imagesets / n_points / cameras) and then joins the communicator. After that
+ * b200ba_optimize / b200ba_optimize_host / b200ba_build_system are COLLECTIVE: every rank must
+ * issue the same sequence of them with the same options. The first call after
+ * b200ba_comm_init that needs the device layout (any of the above or b200ba_evaluate) also
+ * all-reduces the bookkeeping that makes the ranks group the Schur blocks identically, so it
+ * must be made by every rank too; later b200ba_evaluate / b200ba_get_state /
+ * b200ba_get_jacobians calls are rank-local. */
 B200BA_API int b200ba_comm_init(b200ba_handle* h, const uint8_t id[B200BA_NCCL_UNIQUE_ID_BYTES], int rank,
                      int n_ranks);
 
