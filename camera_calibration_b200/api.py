@@ -86,6 +86,13 @@ class BundleAdjuster:
         _check(self.lib.b200ba_get_state(self._h, C.byref(cs)), self._h)
         return st
 
+    def snapshot_state(self):
+        """Device-side copy of (state, last_projection) into the handle's snapshot slot."""
+        _check(self.lib.b200ba_snapshot_state(self._h), self._h)
+
+    def restore_state(self):
+        _check(self.lib.b200ba_restore_state(self._h), self._h)
+
     def optimize(self, opt: Options) -> Report:
         rep = Report()
         _check(self.lib.b200ba_optimize(self._h, C.byref(opt), C.byref(rep)), self._h)
@@ -659,47 +666,66 @@ class OptimizationReport:
     solve_time: float = 0.0
 
 
+def _flatten(dataset: Dataset, state: BAState):
+    """Flat observation arrays in the reference's residual order + the slices that map them back."""
+    used = [i for i, u in enumerate(state.image_used) if u]
+    oi, oc, op, oxy = [], [], [], []
+    slices = []  # (imageset, camera, start, stop) into the flat arrays
+    pos = 0
+    for seq, i in enumerate(used):
+        s = dataset.GetImageset(i)
+        for c in range(dataset.num_cameras()):
+            f = s.FeaturesOfCamera(c)
+            n = len(f["id"])
+            if n and int(np.min(f["index"])) < 0:
+                raise B200BAError("PointFeature::index not set: call BAState.ComputeFeatureIdToPointsIndex first")
+            oi.append(np.full(n, seq, np.uint32))
+            oc.append(np.full(n, c, np.uint32))
+            op.append(f["index"].astype(np.uint32))
+            oxy.append(np.asarray(f["xy"], dtype=np.float32).reshape(-1, 2))
+            slices.append((i, c, pos, pos + n))
+            pos += n
+    cat = lambda l, e: np.concatenate(l) if l else e
+    return (used, slices, cat(oi, np.zeros(0, np.uint32)), cat(oc, np.zeros(0, np.uint32)), cat(op, np.zeros(0, np.uint32)),
+            cat(oxy, np.zeros((0, 2), np.float32)))
+
+
 class _Context:
     """Flattened problem + device handle cached on the Dataset between calls (the product
-    calls OptimizeJointly with max_iteration_count=1 in a loop, APP/calibration.cc:227-237)."""
+    calls OptimizeJointly with max_iteration_count=1 in a loop, APP/calibration.cc:227-237).
+    The reference reads the live Dataset and models on every call, so the cache is validated
+    against the CONTENT of both on every call (observation arrays and camera structs compared
+    bytewise) -- never against object identity."""
 
-    def __init__(self, dataset: Dataset, state: BAState):
-        used = [i for i, u in enumerate(state.image_used) if u]
+    def __init__(self, dataset: Dataset, state: BAState, flat=None):
+        used, slices, oi, oc, op, oxy = flat if flat is not None else _flatten(dataset, state)
         self.used = used
-        self.key = (tuple(used), tuple(id(m) for m in state.intrinsics), len(state.points))
-        oi, oc, op, oxy = [], [], [], []
-        self.slices = []  # (imageset, camera, start, stop) into the flat arrays
-        pos = 0
-        for seq, i in enumerate(used):
-            s = dataset.GetImageset(i)
-            for c in range(dataset.num_cameras()):
-                f = s.FeaturesOfCamera(c)
-                n = len(f["id"])
-                if n and int(np.min(f["index"])) < 0:
-                    raise B200BAError("PointFeature::index not set: call BAState.ComputeFeatureIdToPointsIndex first")
-                oi.append(np.full(n, seq, np.uint32))
-                oc.append(np.full(n, c, np.uint32))
-                op.append(f["index"].astype(np.uint32))
-                oxy.append(f["xy"])
-                self.slices.append((i, c, pos, pos + n))
-                pos += n
+        self.slices = slices
         cams = [m.c_camera() for m in state.intrinsics]
-        self.problem = FlatProblem(cams, len(used), len(state.points),
-                                   np.concatenate(oi) if oi else np.zeros(0, np.uint32),
-                                   np.concatenate(oc) if oc else np.zeros(0, np.uint32),
-                                   np.concatenate(op) if op else np.zeros(0, np.uint32),
-                                   np.concatenate(oxy) if oxy else np.zeros((0, 2), np.float32))
+        self.cam_bytes = [bytes(c) for c in cams]
+        self.problem = FlatProblem(cams, len(used), len(state.points), oi, oc, op, oxy)
         self.adjuster = BundleAdjuster(self.problem)
+
+    def matches(self, state: BAState, flat) -> bool:
+        used, slices, oi, oc, op, oxy = flat
+        p = self.problem
+        return (used == self.used and len(state.points) == p.n_points
+                and [bytes(m.c_camera()) for m in state.intrinsics] == self.cam_bytes
+                and oi.shape == p.obs_imageset.shape and np.array_equal(oc, p.obs_camera)
+                and np.array_equal(oi, p.obs_imageset) and np.array_equal(op, p.obs_point)
+                and np.array_equal(oxy.reshape(-1), np.asarray(p.obs_xy).reshape(-1)))
 
 
 def _run(dataset: Dataset, state: BAState, opt: Options) -> Report:
     if len(state.image_used) != len(state.rig_tr_global):
         raise B200BAError("image_used and rig_tr_global differ in size")  # CHECK_EQ, joint_optimization.cc:72
     ctx = getattr(dataset, "_b200_context", None)
-    used = [i for i, u in enumerate(state.image_used) if u]
-    key = (tuple(used), tuple(id(m) for m in state.intrinsics), len(state.points))
-    if ctx is None or ctx.key != key:
-        ctx = _Context(dataset, state)
+    flat = _flatten(dataset, state)
+    used = flat[0]
+    if ctx is None or not ctx.matches(state, flat):
+        if ctx is not None:
+            ctx.adjuster.close()
+        ctx = _Context(dataset, state, flat)
         dataset._b200_context = ctx
     lastp = np.zeros((ctx.problem.n_obs, 2))
     for (i, c, a, b) in ctx.slices:
@@ -720,8 +746,6 @@ def _run(dataset: Dataset, state: BAState, opt: Options) -> Report:
         d.set_flat_intrinsics(a)
         new_models.append(d)
     state.intrinsics = new_models
-    # the cached context is keyed on model identity: re-key it to the duplicated models
-    ctx.key = (tuple(used), tuple(id(m) for m in state.intrinsics), len(state.points))
     for (i, c, a, b) in ctx.slices:
         dataset.GetImageset(i).FeaturesOfCamera(c)["last_projection"] = fs.last_projection[a:b].copy()
     return rep

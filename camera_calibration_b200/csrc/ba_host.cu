@@ -108,6 +108,10 @@ struct b200ba_handle {
   int cur = 0;
   double2* d_last_projection = nullptr;
   bool have_state = false;
+  // device-side snapshot of (state, last_projection): b200ba_snapshot_state / b200ba_restore_state
+  StateDev snap{};
+  double2* d_snap_lp = nullptr;
+  bool have_snapshot = false;
 
   // layout-dependent buffers
   Layout L{};
@@ -388,9 +392,10 @@ int build_groups(b200ba_handle* h, bool allocate) {
 // ---- layout / buffers ----------------------------------------------------------------------
 int make_layout(b200ba_handle* h, const b200ba_options* opt) {
   if (opt->regularization_weight != 0) {
-    // the reference logs an error and ignores it (joint_optimization.cc:299-305)
-    h->error = "regularization_weight must be 0 (disabled in the reference)";
-    return 2;
+    // the reference logs an error and carries on without the term (joint_optimization.cc:299-305)
+    static bool warned = false;
+    if (!warned) fprintf(stderr, "[b200ba] regularization_weight is ignored (the term is disabled in the reference, joint_optimization.cc:299-305)\n");
+    warned = true;
   }
   Layout L{};
   memset(&L, 0, sizeof(L));
@@ -849,6 +854,8 @@ void free_handle_buffers(b200ba_handle* h) {
     F(h->st[i].image_tr_global); F(h->st[i].tangents);
   }
   F(h->d_last_projection);
+  F(h->snap.points); F(h->snap.rig_tr_global); F(h->snap.camera_tr_rig); F(h->snap.intrinsics); F(h->d_snap_lp);
+  h->have_snapshot = false;
   F(h->out.residual); F(h->out.cost); F(h->out.jac); F(h->out.cell); F(h->out.has_jac); F(h->out.evals);
   F(h->out_trial.residual); F(h->out_trial.cost);
   F(h->sys.base); F(h->d_W); F(h->d_S); F(h->d_Linv); F(h->d_v); F(h->d_y); F(h->d_x); F(h->d_potrf_work);
@@ -1078,6 +1085,11 @@ void b200ba_destroy(b200ba_handle* h) {
   if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
   resolve_timings(h);
   for (auto e : h->event_pool) cudaEventDestroy(e);
+  for (int i = 0; i < 2; ++i) {
+    if (h->ev_syrk[i]) cudaEventDestroy(h->ev_syrk[i]);
+    if (h->ev_scatter[i]) cudaEventDestroy(h->ev_scatter[i]);
+  }
+  if (h->ev_s_ready) cudaEventDestroy(h->ev_s_ready);
   free_handle_buffers(h);
   if (h->cublas) cublasDestroy(h->cublas);
   if (h->cusolver) cusolverDnDestroy(h->cusolver);
@@ -1134,6 +1146,47 @@ int b200ba_get_state(b200ba_handle* h, b200ba_state* s) {
   return 0;
 }
 
+// Device-side copy of the optimised state and the warm-start cache (no host round trip). Used to
+// restart a trajectory from the same point (bench.py) and by callers that want to roll back.
+static int copy_state_dev(b200ba_handle* h, const StateDev& src, const double2* src_lp, StateDev& dst, double2* dst_lp) {
+  CUDA_TRY(h, cudaMemcpyAsync(dst.points, src.points, 3 * sizeof(double) * h->n_points, cudaMemcpyDeviceToDevice, h->stream));
+  CUDA_TRY(h, cudaMemcpyAsync(dst.rig_tr_global, src.rig_tr_global, 7 * sizeof(double) * h->n_imagesets, cudaMemcpyDeviceToDevice, h->stream));
+  CUDA_TRY(h, cudaMemcpyAsync(dst.camera_tr_rig, src.camera_tr_rig, 7 * sizeof(double) * h->n_cameras, cudaMemcpyDeviceToDevice, h->stream));
+  CUDA_TRY(h, cudaMemcpyAsync(dst.intrinsics, src.intrinsics, sizeof(double) * h->intr_total, cudaMemcpyDeviceToDevice, h->stream));
+  CUDA_TRY(h, cudaMemcpyAsync(dst_lp, src_lp, sizeof(double2) * std::max<int64_t>(1, h->n_obs), cudaMemcpyDeviceToDevice, h->stream));
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+int b200ba_snapshot_state(b200ba_handle* h) {
+  if (!h) return 1;
+  if (!h->have_state) {
+    h->error = "no state";
+    return 2;
+  }
+  CUDA_TRY(h, cudaSetDevice(h->device));
+  if (!h->snap.points) {
+    if (dev_alloc(h, &h->snap.points, 3 * static_cast<size_t>(h->n_points))) return 1;
+    if (dev_alloc(h, &h->snap.rig_tr_global, 7 * static_cast<size_t>(h->n_imagesets))) return 1;
+    if (dev_alloc(h, &h->snap.camera_tr_rig, 7 * static_cast<size_t>(h->n_cameras))) return 1;
+    if (dev_alloc(h, &h->snap.intrinsics, h->intr_total)) return 1;
+    if (dev_alloc(h, &h->d_snap_lp, h->n_obs)) return 1;
+  }
+  if (copy_state_dev(h, h->st[h->cur], h->d_last_projection, h->snap, h->d_snap_lp)) return 1;
+  h->have_snapshot = true;
+  return 0;
+}
+
+int b200ba_restore_state(b200ba_handle* h) {
+  if (!h) return 1;
+  if (!h->have_snapshot) {
+    h->error = "no snapshot: call b200ba_snapshot_state first";
+    return 2;
+  }
+  CUDA_TRY(h, cudaSetDevice(h->device));
+  return copy_state_dev(h, h->snap, h->d_snap_lp, h->st[h->cur], h->d_last_projection);
+}
+
 int32_t b200ba_degrees_of_freedom(const b200ba_handle* h, const b200ba_options* opt) {
   if (!h || !opt) return -1;
   int n_intr = 0;
@@ -1157,6 +1210,12 @@ int b200ba_optimize(b200ba_handle* h, const b200ba_options* opt, b200ba_report* 
   const Layout& L = h->L;
   const double huber = opt->huber_parameter;
   double lambda = 0, init_lambda = opt->init_lambda;
+  // on-the-fly block processing (pose elimination with an *OnTheFly Schur mode) starts from a fixed
+  // lambda when none is handed in (joint_optimization.cc:801-804)
+  if (!opt->eliminate_points && init_lambda < 0 &&
+      (opt->schur_mode == B200BA_SCHUR_DENSE_ONTHEFLY || opt->schur_mode == B200BA_SCHUR_SPARSE_ONTHEFLY))
+    init_lambda = 0.0001f;
+  report->final_lambda = init_lambda;  // what optimizer.lambda() holds if no iteration changes it
   double final_cost = -1;
   // n_valid / sum |r|^2 of the CURRENT state, taken from the passes the LM loop makes anyway (the
   // base pass of a build, or the trial pass of an accepted step) -- no extra pass for statistics

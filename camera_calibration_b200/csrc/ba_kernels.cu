@@ -148,7 +148,6 @@ constexpr int kUnlimitedEvals = 1 << 30;
 // ObsOut::has_jac states
 constexpr uint8_t kJacNone = 0, kJacValid = 1, kJacPending = 2, kJacLate = 3;
 static int g_main_eval_budget = 16;
-static cudaEvent_t g_main_done_event = nullptr;  // recorded between the main and the straggler pass
 void set_main_eval_budget(int b) { g_main_eval_budget = b < 1 ? 1 : b; }
 
 template <int MODEL, bool JAC, bool STRAGGLER>
@@ -493,12 +492,13 @@ constexpr int kStragglerThreads = 128;
 
 template <int MODEL, bool JAC, int MINB>
 static void launch_rj_model(const ProblemDev& pb, const Layout& L, const StateDev& st, double2* lp,
-                            const ObsOut& out, double huber, uint32_t* list, int* count, cudaStream_t s) {
+                            const ObsOut& out, double huber, uint32_t* list, int* count, cudaStream_t s,
+                            cudaEvent_t main_done) {
   const int threads = jac_threads();
   const unsigned blocks = static_cast<unsigned>((pb.n_obs + threads - 1) / threads);
   residual_jacobian_kernel<MODEL, JAC, MINB, false><<<blocks, threads, 0, s>>>(pb, L, st, lp, out, huber, list, count,
                                                                                main_eval_budget());
-  if (g_main_done_event) cudaEventRecord(g_main_done_event, s);
+  if (main_done) cudaEventRecord(main_done, s);  // between the main and the straggler pass
 }
 
 template <bool JAC>
@@ -506,26 +506,25 @@ static void launch_rj(int model, const ProblemDev& pb, const Layout& L, const St
                       const ObsOut& out, double huber, uint32_t* list, int* count, cudaStream_t s,
                       cudaEvent_t main_done) {
   if (pb.n_obs == 0) return;
-  g_main_done_event = main_done;
   cudaMemsetAsync(count, 0, sizeof(int), s);
   switch (model) {
     case B200BA_MODEL_CENTRAL_GENERIC:
       switch (jac_minb()) {
-        case 2: launch_rj_model<B200BA_MODEL_CENTRAL_GENERIC, JAC, 2>(pb, L, st, lp, out, huber, list, count, s); break;
-        case 3: launch_rj_model<B200BA_MODEL_CENTRAL_GENERIC, JAC, 3>(pb, L, st, lp, out, huber, list, count, s); break;
-        case 5: launch_rj_model<B200BA_MODEL_CENTRAL_GENERIC, JAC, 5>(pb, L, st, lp, out, huber, list, count, s); break;
-        case 6: launch_rj_model<B200BA_MODEL_CENTRAL_GENERIC, JAC, 6>(pb, L, st, lp, out, huber, list, count, s); break;
-        default: launch_rj_model<B200BA_MODEL_CENTRAL_GENERIC, JAC, 4>(pb, L, st, lp, out, huber, list, count, s);
+        case 2: launch_rj_model<B200BA_MODEL_CENTRAL_GENERIC, JAC, 2>(pb, L, st, lp, out, huber, list, count, s, main_done); break;
+        case 3: launch_rj_model<B200BA_MODEL_CENTRAL_GENERIC, JAC, 3>(pb, L, st, lp, out, huber, list, count, s, main_done); break;
+        case 5: launch_rj_model<B200BA_MODEL_CENTRAL_GENERIC, JAC, 5>(pb, L, st, lp, out, huber, list, count, s, main_done); break;
+        case 6: launch_rj_model<B200BA_MODEL_CENTRAL_GENERIC, JAC, 6>(pb, L, st, lp, out, huber, list, count, s, main_done); break;
+        default: launch_rj_model<B200BA_MODEL_CENTRAL_GENERIC, JAC, 4>(pb, L, st, lp, out, huber, list, count, s, main_done);
       }
       break;
     case B200BA_MODEL_NONCENTRAL_GENERIC:
-      launch_rj_model<B200BA_MODEL_NONCENTRAL_GENERIC, JAC, 3>(pb, L, st, lp, out, huber, list, count, s);
+      launch_rj_model<B200BA_MODEL_NONCENTRAL_GENERIC, JAC, 3>(pb, L, st, lp, out, huber, list, count, s, main_done);
       break;
     case B200BA_MODEL_CENTRAL_OPENCV:
-      launch_rj_model<B200BA_MODEL_CENTRAL_OPENCV, JAC, 4>(pb, L, st, lp, out, huber, list, count, s);
+      launch_rj_model<B200BA_MODEL_CENTRAL_OPENCV, JAC, 4>(pb, L, st, lp, out, huber, list, count, s, main_done);
       break;
     default:
-      launch_rj_model<-1, JAC, 3>(pb, L, st, lp, out, huber, list, count, s);
+      launch_rj_model<-1, JAC, 3>(pb, L, st, lp, out, huber, list, count, s, main_done);
   }
 }
 
@@ -558,7 +557,6 @@ void launch_residual_jacobian(int uniform_model, bool jac, const ProblemDev& pb,
     launch_rj<true>(uniform_model, pb, L, st, last_projection, out, huber, straggler_list, straggler_count, s, main_done);
   else
     launch_rj<false>(uniform_model, pb, L, st, last_projection, out, huber, straggler_list, straggler_count, s, main_done);
-  g_main_done_event = nullptr;
 }
 
 void launch_straggler_pass(int uniform_model, bool jac, const ProblemDev& pb, const Layout& L, const StateDev& st,

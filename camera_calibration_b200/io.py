@@ -137,7 +137,8 @@ def LoadDataset(path: str) -> Optional[Dataset]:
             geoms.append(g)
         ds.known_geometries = geoms
         return ds
-    except struct.error:
+    except (struct.error, ValueError, UnicodeDecodeError):
+        # truncated file / bad filename bytes: the reference's reader returns false
         return None
 
 
@@ -260,26 +261,28 @@ def SavePoses(image_used, poses: np.ndarray, path: str) -> bool:
 
 
 def LoadPoses(path: str):
-    """Returns (image_used list, poses [n, 7]) or None."""
+    """Returns (image_used list, poses [n, 7]) or None (malformed file: the reference returns false)."""
     try:
         node = yaml.load(open(path), Loader=_Loader)
-    except (OSError, yaml.YAMLError):
-        return None
-    n = int(node["pose_count"])
-    used = [False] * n
-    poses = np.tile(np.array([1.0, 0, 0, 0, 0, 0, 0]), (n, 1))
-    items = node.get("poses") or []
-    if not isinstance(items, list):
-        return None
-    for it in items:
-        i = int(it["index"])
-        if i >= n:
+        n = int(node["pose_count"])
+        if n < 0:
             return None
-        used[i] = True
-        q = np.array([it["qw"], it["qx"], it["qy"], it["qz"]], dtype=np.float64)
-        q = q / np.linalg.norm(q)  # SE3::setQuaternion normalises
-        poses[i] = np.concatenate([q, [float(it["tx"]), float(it["ty"]), float(it["tz"])]])
-    return used, poses
+        used = [False] * n
+        poses = np.tile(np.array([1.0, 0, 0, 0, 0, 0, 0]), (n, 1))
+        items = node.get("poses") or []
+        if not isinstance(items, list):
+            return None
+        for it in items:
+            i = int(it["index"])
+            if i < 0 or i >= n:
+                return None
+            used[i] = True
+            q = np.array([it["qw"], it["qx"], it["qy"], it["qz"]], dtype=np.float64)
+            q = q / np.linalg.norm(q)  # SE3::setQuaternion normalises
+            poses[i] = np.concatenate([q, [float(it["tx"]), float(it["ty"]), float(it["tz"])]])
+        return used, poses
+    except (OSError, yaml.YAMLError, TypeError, KeyError, ValueError, AttributeError):
+        return None
 
 
 def SavePointsAndIndexMapping(state: BAState, path: str) -> bool:
@@ -300,13 +303,15 @@ def SavePointsAndIndexMapping(state: BAState, path: str) -> bool:
 def LoadPointsAndIndexMapping(path: str):
     try:
         node = yaml.load(open(path), Loader=_Loader)
-    except (OSError, yaml.YAMLError):
+        pts = np.array(node["points"], dtype=np.float64)
+        if pts.size % 3 != 0:
+            return None
+        mapping = {int(it["feature_id"]): int(it["point_index"]) for it in (node.get("feature_id_to_point_index") or [])}
+        if any(v < 0 or 3 * v >= max(pts.size, 1) for v in mapping.values()):
+            return None
+        return pts.reshape(-1, 3), mapping
+    except (OSError, yaml.YAMLError, TypeError, KeyError, ValueError, AttributeError):
         return None
-    pts = np.array(node["points"], dtype=np.float64)
-    if pts.size % 3 != 0:
-        return None
-    mapping = {int(it["feature_id"]): int(it["point_index"]) for it in (node.get("feature_id_to_point_index") or [])}
-    return pts.reshape(-1, 3), mapping
 
 
 def SaveBAState(base_path: str, state: BAState) -> bool:

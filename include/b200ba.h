@@ -166,6 +166,13 @@ B200BA_API const char* b200ba_last_error(const b200ba_handle* h); /* h may be NU
 B200BA_API int b200ba_set_state(b200ba_handle* h, const b200ba_state* state);
 B200BA_API int b200ba_get_state(b200ba_handle* h, b200ba_state* state);
 
+/* Device-side copy of the optimised state + last_projection held by the handle into a snapshot
+ * slot / back (no host transfer). The reference keeps such a copy implicitly: LMOptimizer works
+ * on `State test_state = *state` (libvis lm_optimizer.h:868) and the product writes a checkpoint
+ * after every iteration (calibration.cc:240-243). */
+B200BA_API int b200ba_snapshot_state(b200ba_handle* h);
+B200BA_API int b200ba_restore_state(b200ba_handle* h);
+
 /* ---- the hot path -------------------------------------------------------- */
 /* Equivalent of OptimizeJointly (joint_optimization.cc:757-953) on the state held
  * by the handle; the state stays resident on the device between calls. */
