@@ -108,6 +108,13 @@ class BundleAdjuster:
         _check(self.lib.b200ba_optimize_host(self._h, C.byref(cs), C.byref(opt), C.byref(rep)), self._h)
         return rep
 
+    def evaluate_device(self, opt: Options, compute_jacobians: bool = False) -> float:
+        """One pass of the cost function whose per-observation outputs stay on the device (it still
+        updates last_projection like the reference mutates the Dataset). Returns the total cost."""
+        total = C.c_double(0)
+        _check(self.lib.b200ba_evaluate(self._h, C.byref(opt), int(compute_jacobians), None, None, C.byref(total)), self._h)
+        return total.value
+
     def evaluate(self, opt: Options, compute_jacobians: bool = False) -> Dict:
         n = self.problem.n_obs
         res = np.zeros((n, 2))

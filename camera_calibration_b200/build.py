@@ -12,7 +12,7 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(CSRC, "libb200ba.so")
-SOURCES = ["ba_kernels.cu", "ba_host.cu"]
+SOURCES = ["ba_kernels.cu", "ba_host.cu", "ba_dense.cu"]
 HEADERS = ["ba_common.h", "ba_device.cuh", "ba_kernels.h", os.path.join("..", "..", "include", "b200ba.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",

@@ -166,6 +166,11 @@ class Timings(C.Structure):
         ("total_ms", C.c_double),
         ("kernel_launches", C.c_int64),
         ("straggler_ms", C.c_double),
+        ("solve_ms", C.c_double),
+        ("contraction_flops", C.c_double),
+        ("factor_flops", C.c_double),
+        ("lm_attempts", C.c_int32),
+        ("build_count", C.c_int32),
     ]
 
 

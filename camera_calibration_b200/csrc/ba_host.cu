@@ -80,7 +80,7 @@ bool load_nccl(std::string* err) {
 
 constexpr int kMaxCholPanels = 1024;
 
-enum Phase { PH_JAC = 0, PH_ACC, PH_SCHUR, PH_FACTOR, PH_TRIAL, PH_UPDATE, PH_ALLREDUCE, PH_STRAGGLER, PH_COUNT };
+enum Phase { PH_JAC = 0, PH_ACC, PH_SCHUR, PH_FACTOR, PH_TRIAL, PH_UPDATE, PH_ALLREDUCE, PH_STRAGGLER, PH_SOLVE, PH_COUNT };
 
 }  // namespace
 
@@ -302,6 +302,7 @@ void resolve_timings(b200ba_handle* h) {
         case PH_UPDATE: h->timings.update_ms += ms; break;
         case PH_ALLREDUCE: h->timings.allreduce_ms += ms; break;
         case PH_STRAGGLER: h->timings.straggler_ms += ms; break;
+        case PH_SOLVE: h->timings.solve_ms += ms; h->timings.factor_ms += ms; break;
       }
     }
     if (p.own_a) h->event_pool.push_back(p.a);
@@ -724,6 +725,7 @@ int solve_system(b200ba_handle* h, double lambda, int* spd) {
       const int nblk = h->group_start[g + 1] - h->group_start[g];
       const int kg = nblk * L.bs, mg = h->group_count[g];
       if (mg == 0 || kg == 0) continue;
+      h->timings.contraction_flops += static_cast<double>(mg) * mg * kg;
       const int b = it & 1;
       double* Wc = h->d_Wc + b * h->wc_stride;
       double* P = h->d_P + b * h->p_stride;
@@ -775,6 +777,7 @@ int solve_system(b200ba_handle* h, double lambda, int* spd) {
       CUDA_TRY(h, cudaMemsetAsync(rhs_tail, 0, L.nd * sizeof(double), h->stream));
       h->timings.kernel_launches += 2;
       if (k_rows > 0 && L.nd > 0) {
+        h->timings.contraction_flops += static_cast<double>(L.nd) * L.nd * k_rows;
         const double zero = 0.0;
         const double* Wr = h->d_W + static_cast<size_t>(L.bs) * p0 * L.nd;
         // row-major W [nbd x nd] is the column-major nd x nbd matrix W^T: S -= W_r^T W_r (lower)
@@ -800,6 +803,10 @@ int solve_system(b200ba_handle* h, double lambda, int* spd) {
   {
     ScopedPhase ph(h, PH_FACTOR);
     if (factor_dense(h)) return 1;
+    h->timings.factor_flops += static_cast<double>(L.nd) * L.nd * L.nd / 3.0;
+  }
+  {
+    ScopedPhase ph(h, PH_SOLVE);
     CUSOLVER_TRY(h, cusolverDnDpotrs(h->cusolver, CUBLAS_FILL_MODE_LOWER, L.nd, 1, h->d_S, L.nd, h->d_x + L.nbd, L.nd,
                                      h->d_info + 1));
   }
@@ -1224,6 +1231,7 @@ int b200ba_optimize(b200ba_handle* h, const b200ba_options* opt, b200ba_report* 
   for (int iteration = 0; iteration < opt->max_iteration_count; ++iteration) {
     double cost = 0, n_valid = 0;
     if (build_system(h, huber, &cost, &n_valid)) return 1;
+    h->timings.build_count += 1;
     stat_valid = h->h_scal[4];
     stat_sumsq = h->h_scal[5];
     have_stats = true;
@@ -1243,6 +1251,7 @@ int b200ba_optimize(b200ba_handle* h, const b200ba_options* opt, b200ba_report* 
     int attempts = 0;
     for (int lm_iteration = 0; lm_iteration < opt->max_lm_attempts; ++lm_iteration) {
       ++attempts;
+      h->timings.lm_attempts += 1;
       int spd = 1;
       if (solve_system(h, lambda, &spd)) return 1;
       if (!spd) {

@@ -58,4 +58,45 @@ void launch_dirfit_update(int G, const double* grid, const double* x, double* ou
 void launch_permute_double2(int64_t n, const uint32_t* perm, const double2* src, double2* dst, bool scatter,
                             cudaStream_t s);
 
+
+// ---- dense phase (ba_dense.cu) ----------------------------------------------------------------
+// Storage map of the reduced system S (n_d x n_d, column-major, lower triangle valid): columns are
+// grouped in blocks of `nb`; block j lives in slot (j % ranks) * blocks_per_rank + j / ranks, so that
+// the column blocks one rank owns in the block-cyclic distribution are CONTIGUOUS (one chunk of a
+// reduce-scatter). With one rank the map is the identity. Rows are never permuted.
+struct DenseMap {
+  int nb;               // column-block width
+  int ranks;            // R
+  int blocks_per_rank;  // ceil(n_blocks / R)
+  int64_t ld;           // leading dimension (>= n_d, even)
+  __host__ __device__ __forceinline__ int slot(int block) const { return (block % ranks) * blocks_per_rank + block / ranks; }
+  __host__ __device__ __forceinline__ int64_t col_offset(int c) const {
+    const int b = c / nb;
+    return (static_cast<int64_t>(slot(b)) * nb + (c - b * nb)) * ld;
+  }
+};
+
+// C (+)= alpha * A B^T; A(i, k) at A[k * lda + i], B(j, k) at B[k * ldb + j], C(i, j) at C[j * ldc + i].
+struct GemmArgs {
+  int M, N, K;
+  const double* A;
+  int64_t lda;
+  const double* B;
+  int64_t ldb;
+  double* C;
+  int64_t ldc;
+  double alpha, beta;
+  bool a_aligned, b_aligned;  // 16-byte copies allowed (set by make_gemm_args)
+  // scatter epilogue: C is the base of S, compact row / column i is dense column cols[i] (ascending)
+  const int* cols;
+  DenseMap map;
+};
+inline bool gemm_operand_aligned(const double* p, int64_t ld) {
+  return (reinterpret_cast<uintptr_t>(p) % 16 == 0) && (ld % 2 == 0);
+}
+// lower: only tiles / entries with i >= j (M == N); scatter: the scatter-subtract epilogue (implies lower).
+int launch_dgemm_nt(const GemmArgs& g, bool lower, bool scatter, cudaStream_t s);
+// Cholesky of a 128 x 128 (live size n) column-major diagonal tile in place + Linv [128 x 128, ld 128].
+int launch_potrf_tile(double* A, int64_t lda, int n, double* Linv, int* info, cudaStream_t s);
+
 }  // namespace b200ba

@@ -274,6 +274,12 @@ typedef struct b200ba_timings {
   int64_t kernel_launches;   /* kernels of this library launched */
   double straggler_ms;       /* straggler passes of the residual/Jacobian kernel (observations whose
                                 projection needs more than the main pass's evaluation budget) */
+  double solve_ms;           /* triangular solves with the dense factor (part of factor_ms) */
+  double contraction_flops;  /* FP64 flops of the Schur contraction S = C - W^T W actually issued (structured:
+                                sum over groups of m_g^2 k_g; dense: n_d^2 * k), summed over LM attempts */
+  double factor_flops;       /* n_d^3 / 3 per factorisation, summed over LM attempts */
+  int32_t lm_attempts;       /* linear solves (LM attempts) of the last b200ba_optimize */
+  int32_t build_count;       /* H / b builds (outer iterations) of the last b200ba_optimize */
 } b200ba_timings;
 B200BA_API int b200ba_get_timings(const b200ba_handle* h, b200ba_timings* t);
 

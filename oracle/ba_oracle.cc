@@ -34,6 +34,8 @@
 #include <limits>
 #include <vector>
 
+#include "ba_dense_fast.h"
+
 namespace {
 
 // ------------------------------------------------------------------------------------
@@ -848,6 +850,17 @@ struct Accumulator {
   int32_t out_K = 0;
   int32_t* out_has_jacobian = nullptr;
 
+  // record mode (threaded evaluation, compute_mt): the add_* calls of ONE observation are captured
+  // instead of applied, and replayed later in the reference's sequential order
+  struct Record {
+    int kind = 0;  // 0 invalid, 1 residual only, 2 residual with Jacobian
+    double rx = 0, ry = 0;
+    int n = 0;
+    int idx[3 + 6 + 6 + 80];
+    double jx[3 + 6 + 6 + 80], jy[3 + 6 + 6 + 80];
+  };
+  Record* rec = nullptr;
+
   ~Accumulator() {
     free(block_diag);
     free(off_diag);
@@ -884,9 +897,19 @@ struct Accumulator {
       b_dense[i - nbd] += v;
   }
   void add_invalid() {
+    if (rec) {
+      rec->kind = 0;
+      return;
+    }
     if (cost_vector) cost_vector->push_back(-1);
   }
   void add_residual(double rx, double ry) {
+    if (rec) {
+      rec->kind = 1;
+      rec->rx = rx;
+      rec->ry = ry;
+      return;
+    }
     const double c = huber_cost_sq(huber, rx * rx + ry * ry);
     cost += c;
     if (cost_vector) cost_vector->push_back(c);
@@ -895,6 +918,16 @@ struct Accumulator {
   // b(i) += w (J_i . r).
   void add_residual_with_jacobian(double rx, double ry, int n, const int* idx, const double* jx,
                                   const double* jy) {
+    if (rec) {
+      rec->kind = 2;
+      rec->rx = rx;
+      rec->ry = ry;
+      rec->n = n;
+      std::copy(idx, idx + n, rec->idx);
+      std::copy(jx, jx + n, rec->jx);
+      std::copy(jy, jy + n, rec->jy);
+      return;
+    }
     add_residual(rx, ry);
     if (!want_matrices) return;
     const double w = huber_weight_sq(huber, rx * rx + ry * ry);
@@ -903,6 +936,14 @@ struct Accumulator {
       for (int k = i; k < n; ++k) addH(idx[i], idx[k], wjx * jx[k] + wjy * jy[k]);
       addB(idx[i], rx * wjx + ry * wjy);
     }
+  }
+  void replay(const Record& r) {
+    if (r.kind == 0)
+      add_invalid();
+    else if (r.kind == 1)
+      add_residual(r.rx, r.ry);
+    else
+      add_residual_with_jacobian(r.rx, r.ry, r.n, r.idx, r.jx, r.jy);
   }
 };
 
@@ -1137,6 +1178,10 @@ struct CostFunction {
     }
     const int64_t o_begin = obs_begin;
     const int64_t o_end = obs_end < 0 ? P.n_obs : obs_end;
+    if (oracle_fast::thread_count() > 1 && !acc->rec) {
+      compute_mt(compute_jacobians, S, acc, tangents, o_begin, o_end);
+      return;
+    }
     int cur_imageset = -1, cur_camera = -1;
     Pose image_tr_global{};
     double R[3][3];
@@ -1153,6 +1198,54 @@ struct CostFunction {
       Cam m{P.cameras[cam], S.intrinsics[cam].data()};
       add_reprojection_residual(compute_jacobians, S, m, tangents[cam], o, iset, cam,
                                 image_tr_global, R, acc);
+    }
+  }
+
+  // Threaded evaluation for the full-size timing runs: the per-observation work (projection and
+  // Jacobians -- in NUMERIC mode 3 + 32 / 80 re-projections with the control points perturbed IN
+  // PLACE, hence one private copy of the state per thread) runs in parallel chunk by chunk; the
+  // accumulation is then replayed sequentially in the reference's observation order, so H, b and
+  // the cost vector are bitwise those of the single-threaded pass.
+  void compute_mt(bool compute_jacobians, State& S, Accumulator* acc, const std::vector<std::vector<Tangents>>& tangents,
+                  int64_t o_begin, int64_t o_end) const {
+    const b200ba_problem& P = *pb;
+    const int nt = oracle_fast::thread_count();
+    const int64_t chunk = 32768;
+    std::vector<Accumulator::Record> recs(static_cast<size_t>(std::min<int64_t>(chunk, std::max<int64_t>(0, o_end - o_begin))));
+    std::vector<State> copies(nt, S);
+    for (int64_t c0 = o_begin; c0 < o_end; c0 += chunk) {
+      const int64_t c1 = std::min(o_end, c0 + chunk);
+#pragma omp parallel num_threads(nt)
+      {
+#ifdef _OPENMP
+        const int tid = omp_get_thread_num();
+#else
+        const int tid = 0;
+#endif
+        State& Sl = copies[tid];
+        Accumulator ta;
+        ta.huber = acc->huber;
+        ta.out_residuals = acc->out_residuals;
+        ta.out_jpoint = acc->out_jpoint;
+        ta.out_jpose = acc->out_jpose;
+        ta.out_jrig = acc->out_jrig;
+        ta.out_jintr = acc->out_jintr;
+        ta.out_intr_index = acc->out_intr_index;
+        ta.out_K = acc->out_K;
+        ta.out_has_jacobian = acc->out_has_jacobian;
+#pragma omp for schedule(dynamic, 256)
+        for (int64_t o = c0; o < c1; ++o) {
+          const int iset = static_cast<int>(P.obs_imageset[o]);
+          const int cam = static_cast<int>(P.obs_camera[o]);
+          const Pose image_tr_global = pose_mul(load_pose(&Sl.camera_tr_rig[7 * cam]), load_pose(&Sl.rig_tr_global[7 * iset]));
+          double R[3][3];
+          qrot(image_tr_global.q, R);
+          Cam m{P.cameras[cam], Sl.intrinsics[cam].data()};
+          ta.rec = &recs[static_cast<size_t>(o - c0)];
+          add_reprojection_residual(compute_jacobians, Sl, m, tangents[cam], o, iset, cam, image_tr_global, R, &ta);
+        }
+      }
+      for (int64_t o = c0; o < c1; ++o) acc->replay(recs[static_cast<size_t>(o - c0)]);
     }
   }
 
@@ -1503,6 +1596,144 @@ void schur_solve(int bs, int nb, int nd, const double* D, const double* B, const
   }
 }
 
+// Full-size variants of ldlt_solve() / schur_solve() on the blocked, threaded kernels of
+// ba_dense_fast.h (same quantities; summation order differs). Used above kFastDenseMinN.
+double now_seconds();
+constexpr int kFastDenseMinN = 768;
+bool g_force_fast_dense = false;
+
+// Lm: n x n row-major, lower triangle = the matrix; overwritten by the factor.
+bool ldlt_solve_lower_fast(int n, double* Lm, const double* b, double* x) {
+  std::vector<double> diag(n);
+  for (int i = 0; i < n; ++i) diag[i] = Lm[size_t(i) * n + i];
+  std::vector<int> transp;
+  oracle_fast::ldlt_pivot_sequence(n, diag, &transp);
+  bool any = false;
+  for (int k = 0; k < n; ++k) any |= transp[k] != k;
+  if (any) {
+    // position -> original index after the whole transposition sequence; A'[i][j] = A[p[i]][p[j]]
+    std::vector<int> p(n);
+    for (int i = 0; i < n; ++i) p[i] = i;
+    for (int k = 0; k < n; ++k) std::swap(p[k], p[transp[k]]);
+    double* T = static_cast<double*>(malloc(size_t(n) * n * sizeof(double)));
+#pragma omp parallel for schedule(dynamic, 16) num_threads(oracle_fast::thread_count())
+    for (int i = 0; i < n; ++i)
+      for (int j = 0; j <= i; ++j) {
+        const int a = std::max(p[i], p[j]), c = std::min(p[i], p[j]);
+        T[size_t(i) * n + j] = Lm[size_t(a) * n + c];
+      }
+#pragma omp parallel for schedule(dynamic, 16) num_threads(oracle_fast::thread_count())
+    for (int i = 0; i < n; ++i) std::copy(T + size_t(i) * n, T + size_t(i) * n + i + 1, Lm + size_t(i) * n);
+    free(T);
+  }
+  oracle_fast::ldlt_factor_blocked(n, Lm);
+  const double tolerance = 1.0 / std::numeric_limits<double>::max();
+  std::vector<double> y(b, b + n);
+  for (int k = 0; k < n; ++k) std::swap(y[k], y[transp[k]]);
+  for (int i = 0; i < n; ++i) {
+    double s = y[i];
+    const double* row = &Lm[size_t(i) * n];
+    for (int j = 0; j < i; ++j) s -= row[j] * y[j];
+    y[i] = s;
+  }
+  for (int i = 0; i < n; ++i) {
+    const double d = Lm[size_t(i) * n + i];
+    y[i] = (std::fabs(d) > tolerance) ? y[i] / d : 0.0;
+  }
+  for (int i = n - 1; i >= 0; --i) {
+    const double yi = y[i];
+    const double* row = &Lm[size_t(i) * n];
+    for (int j = 0; j < i; ++j) y[j] -= row[j] * yi;
+  }
+  for (int k = n - 1; k >= 0; --k) std::swap(y[k], y[transp[k]]);
+  std::copy(y.begin(), y.end(), x);
+  return true;
+}
+
+void schur_solve_fast(int bs, int nb, int nd, const double* D, const double* B, const double* C,
+                      const double* b1, const double* b2, double* x) {
+  const int nbd = bs * nb;
+  const int nt = oracle_fast::thread_count();
+  // D^-1 b and (D^-1 B)^T, B^T: column i of B becomes row i (k contiguous). Tiled over the dense
+  // columns so that both the row-major reads of B and the transposed writes stay cache-resident.
+  const bool verbose = getenv("ORACLE_VERBOSE") != nullptr;
+  double tp = now_seconds();
+  std::vector<double> Dinvb(nbd), Hinv(size_t(nb) * bs * bs);
+  double* Bt = static_cast<double*>(malloc(std::max<size_t>(1, size_t(nd) * nbd) * sizeof(double)));
+  double* Xt = static_cast<double*>(malloc(std::max<size_t>(1, size_t(nd) * nbd) * sizeof(double)));
+#pragma omp parallel for schedule(static) num_threads(nt)
+  for (int blk = 0; blk < nb; ++blk) {
+    std::vector<double> I(size_t(bs) * bs, 0.0);
+    for (int i = 0; i < bs; ++i) I[size_t(i) * bs + i] = 1;
+    double* Hb = &Hinv[size_t(blk) * bs * bs];
+    const int base = blk * bs;
+    ldlt_solve(bs, D + size_t(blk) * bs * bs, bs, I.data(), bs, bs, Hb, bs);  // :1289
+    for (int row = 0; row < bs; ++row) {
+      double r = 0;
+      for (int k = 0; k < bs; ++k) r += Hb[size_t(row) * bs + k] * b1[base + k];
+      Dinvb[base + row] = r;
+    }
+  }
+  constexpr int CT = 64;
+  const int nct = (nd + CT - 1) / CT;
+#pragma omp parallel for schedule(dynamic, 1) num_threads(nt)
+  for (int ct = 0; ct < nct; ++ct) {
+    const int c0 = ct * CT, c1 = std::min(nd, c0 + CT);
+    for (int blk = 0; blk < nb; ++blk) {
+      const int base = blk * bs;
+      const double* Hb = &Hinv[size_t(blk) * bs * bs];
+      for (int col = c0; col < c1; ++col) {
+        for (int row = 0; row < bs; ++row) {
+          double rr = 0;
+          for (int k = 0; k < bs; ++k) rr += Hb[size_t(row) * bs + k] * B[size_t(base + k) * nd + col];
+          Xt[size_t(col) * nbd + base + row] = rr;
+          Bt[size_t(col) * nbd + base + row] = B[size_t(base + row) * nd + col];
+        }
+      }
+    }
+  }
+  if (verbose) fprintf(stderr, "[oracle] schur: D^-1 B + transposes %.2f s\n", now_seconds() - tp), tp = now_seconds();
+  std::vector<double> sb(nd);
+#pragma omp parallel for schedule(static) num_threads(nt)
+  for (int i = 0; i < nd; ++i) {
+    double r = 0;
+    const double* bt = Bt + size_t(i) * nbd;
+    for (int k = 0; k < nbd; ++k) r += bt[k] * Dinvb[k];
+    sb[i] = b2[i] - r;
+  }
+  // lower-triangular S: S[j][i] = C_upper[i][j] - sum_k Xt[j][k] Bt[i][k], i <= j   (:1328, :1334-1335)
+  double* Sl = static_cast<double*>(malloc(std::max<size_t>(1, size_t(nd) * nd) * sizeof(double)));
+  {
+    constexpr int TT = 64;  // tiled transpose of the upper triangle of C
+    const int ntt = (nd + TT - 1) / TT;
+#pragma omp parallel for schedule(dynamic, 1) num_threads(nt)
+    for (int tj = 0; tj < ntt; ++tj)
+      for (int ti = 0; ti <= tj; ++ti) {
+        const int j1 = std::min(nd, (tj + 1) * TT), i1 = std::min(nd, (ti + 1) * TT);
+        for (int i = ti * TT; i < i1; ++i)
+          for (int j = std::max(i, tj * TT); j < j1; ++j) Sl[size_t(j) * nd + i] = C[size_t(i) * nd + j];
+      }
+  }
+  if (verbose) fprintf(stderr, "[oracle] schur: S <- C^T %.2f s\n", now_seconds() - tp), tp = now_seconds();
+  oracle_fast::gemm_nt_lower(nd, nd, nbd, -1.0, Xt, nbd, Bt, nbd, Sl, nd, 0);
+  if (verbose) fprintf(stderr, "[oracle] schur: contraction %.2f s (%.1f GF/s)\n", now_seconds() - tp, double(nd) * nd * nbd / (now_seconds() - tp) / 1e9), tp = now_seconds();
+  std::vector<double> xd(nd);
+  ldlt_solve_lower_fast(nd, Sl, sb.data(), xd.data());  // :1361
+  if (verbose) fprintf(stderr, "[oracle] schur: LDLT + solve %.2f s (%.1f GF/s)\n", now_seconds() - tp, double(nd) * nd * nd / 3 / (now_seconds() - tp) / 1e9), tp = now_seconds();
+  free(Sl);
+  free(Bt);
+  for (int i = 0; i < nd; ++i) x[nbd + i] = xd[i];
+  // back-substitution (:1366-1367): x_b = D^-1 b - (D^-1 B) x_d
+  std::vector<double> t(nbd, 0.0);
+  for (int j = 0; j < nd; ++j) {
+    const double xj = xd[j];
+    const double* xt = &Xt[size_t(j) * nbd];
+    for (int k = 0; k < nbd; ++k) t[k] += xt[k] * xj;
+  }
+  for (int k = 0; k < nbd; ++k) x[k] = Dinvb[k] - t[k];
+  free(Xt);
+}
+
 // CostIsSmallerThan (LV/lm_optimizer.h:993-1011)
 bool cost_is_smaller_than(const std::vector<double>& left, const std::vector<double>& right) {
   double ls = 0, rs = 0;
@@ -1616,7 +1847,10 @@ int oracle_optimize(const b200ba_problem* pb, b200ba_state* state, const b200ba_
             acc.block_diag[(size_t(b) * L.block_size + k) * L.block_size + k] = orig_diag[di++] + lambda;
         for (int i = 0; i < nd; ++i) acc.dense[size_t(i) * nd + i] = orig_diag[di++] + lambda;
       }
-      if (nbd > 0) {
+      if (nbd > 0 && (nd >= kFastDenseMinN || g_force_fast_dense)) {
+        schur_solve_fast(L.block_size, L.num_blocks, nd, acc.block_diag, acc.off_diag, acc.dense,
+                         acc.b_block.data(), acc.b_dense.data(), x.data());
+      } else if (nbd > 0) {
         schur_solve(L.block_size, L.num_blocks, nd, acc.block_diag, acc.off_diag, acc.dense,
                     acc.b_block.data(), acc.b_dense.data(), x.data());
       } else {
@@ -2117,6 +2351,27 @@ double oracle_time_ldlt(int32_t n) {
   const double t0 = now_seconds();
   ldlt_solve(n, A.data(), n, b.data(), 1, 1, x.data(), 1);
   return now_seconds() - t0;
+}
+
+// Host threads used by the full-size kernels (compute_mt, ba_dense_fast.h); 1 = the reference's
+// single-threaded behaviour. Returns the value in effect.
+int oracle_set_threads(int n) {
+#ifdef _OPENMP
+  if (n <= 0) n = omp_get_num_procs();
+  oracle_fast::thread_count() = std::max(1, n);
+#else
+  (void)n;
+  oracle_fast::thread_count() = 1;
+#endif
+  return oracle_fast::thread_count();
+}
+// Forces the blocked dense kernels also below kFastDenseMinN (agreement tests).
+void oracle_force_fast_dense(int on) { g_force_fast_dense = on != 0; }
+// Stand-alone blocked Schur solve (same interface as oracle_schur_solve).
+int oracle_schur_solve_fast(int32_t bs, int32_t nb, int32_t nd, const double* D, const double* B,
+                            const double* C, const double* b1, const double* b2, double* x) {
+  schur_solve_fast(bs, nb, nd, D, B, C, b1, b2, x);
+  return 0;
 }
 
 }  // extern "C"

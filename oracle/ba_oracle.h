@@ -91,6 +91,14 @@ double oracle_time_jacobian(const b200ba_problem* problem, b200ba_state* state,
 double oracle_time_contraction(int32_t n_rows, int32_t n_cols);
 double oracle_time_ldlt(int32_t n);
 
+/* Full-size runs (bench.py --impl reference / cpu_baseline): host threads for the per-observation
+ * pass and the blocked dense kernels (0 = all cores; 1 = single-threaded like the reference). */
+int oracle_set_threads(int n);
+void oracle_force_fast_dense(int on);
+int oracle_schur_solve_fast(int32_t block_size, int32_t n_blocks, int32_t n_dense, const double* D,
+                            const double* B, const double* C, const double* b1, const double* b2, double* x);
+
+
 #ifdef __cplusplus
 }
 #endif

@@ -17,19 +17,36 @@ from camera_calibration_b200.cabi import Camera, FlatProblem, FlatState, Options
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "_build", "libba_oracle.so")
+NATIVE_LIB_PATH = os.path.join(_HERE, "_build", "libba_oracle_native.so")
 _LIB = None
 _D = C.POINTER(C.c_double)
 _I32 = C.POINTER(C.c_int32)
 
 
-def build(force: bool = False) -> str:
-    """Compile the oracle with the committed Makefile (g++, no dependencies)."""
-    src = os.path.join(_HERE, "ba_oracle.cc")
-    if force or not os.path.exists(LIB_PATH) or os.path.getmtime(LIB_PATH) < max(
-            os.path.getmtime(src), os.path.getmtime(os.path.join(_HERE, "ba_oracle.h")),
-            os.path.getmtime(os.path.join(_HERE, "..", "include", "b200ba.h"))):
-        subprocess.check_call(["make", "-C", _HERE, "-B" if force else "-s"], stdout=subprocess.DEVNULL)
-    return LIB_PATH
+def build(force: bool = False, native: bool = False) -> str:
+    """Compile the oracle with the committed Makefile (g++, no dependencies). ``native=True``
+    builds the -march=native variant used by the timing legs of bench.py (on the box it runs on)."""
+    target = NATIVE_LIB_PATH if native else LIB_PATH
+    srcs = [os.path.join(_HERE, f) for f in ("ba_oracle.cc", "ba_oracle.h", "ba_dense_fast.h")] + [
+        os.path.join(_HERE, "..", "include", "b200ba.h")]
+    if force or not os.path.exists(target) or os.path.getmtime(target) < max(os.path.getmtime(f) for f in srcs):
+        cmd = ["make", "-C", _HERE, "-s"] + (["-B"] if force else []) + (["native"] if native else [])
+        subprocess.check_call(cmd, stdout=subprocess.DEVNULL)
+    return target
+
+
+def use_native(threads: int = 0) -> int:
+    """Switch this process to the -march=native build (rebuilt here if stale) and set the host
+    thread count of the full-size kernels (0 = all cores). Returns the thread count in effect."""
+    global _LIB, LIB_PATH
+    build(native=True, force=True)  # the .so may have travelled from another CPU: always rebuild on this box
+    LIB_PATH = NATIVE_LIB_PATH
+    _LIB = None
+    return set_threads(threads)
+
+
+def set_threads(n: int) -> int:
+    return int(lib().oracle_set_threads(int(n)))
 
 
 def lib():
@@ -71,6 +88,12 @@ def lib():
         l.oracle_time_contraction.argtypes = [C.c_int32, C.c_int32]
         l.oracle_time_ldlt.restype = C.c_double
         l.oracle_time_ldlt.argtypes = [C.c_int32]
+        l.oracle_set_threads.restype = C.c_int
+        l.oracle_set_threads.argtypes = [C.c_int]
+        l.oracle_force_fast_dense.restype = None
+        l.oracle_force_fast_dense.argtypes = [C.c_int]
+        l.oracle_schur_solve_fast.restype = C.c_int
+        l.oracle_schur_solve_fast.argtypes = [C.c_int32, C.c_int32, C.c_int32, _D, _D, _D, _D, _D, _D]
         _LIB = l
     return _LIB
 
