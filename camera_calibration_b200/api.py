@@ -167,6 +167,19 @@ def nccl_unique_id() -> bytes:
     return bytes(buf)
 
 
+def dense_cholesky_solve(A, b, block_width: int = 256, device: int = -1):
+    """A x = b for a symmetric positive definite A on the in-tree dense kernels (ba_dense.cu).
+    Returns (x, factor_ms, solve_ms)."""
+    lib = cabi.load_library()
+    A = np.ascontiguousarray(A, dtype=np.float64)
+    b = np.ascontiguousarray(b, dtype=np.float64)
+    n = A.shape[0]
+    x = np.zeros(n)
+    fm, sm = C.c_double(0), C.c_double(0)
+    _check(lib.b200ba_dense_cholesky_solve(device, n, int(block_width), _dp(A), _dp(b), _dp(x), C.byref(fm), C.byref(sm)))
+    return x, fm.value, sm.value
+
+
 def schur_solve(block_size: int, D, B, Cm, b1, b2, device: int = -1) -> np.ndarray:
     """SolveWithSchurComplementDenseOffDiag (libvis lm_optimizer.h:1246-1369) on the device."""
     lib = cabi.load_library()

@@ -342,6 +342,8 @@ SYMBOLS = {
     "b200ba_nccl_unique_id": (C.c_int, [C.POINTER(C.c_uint8)]),
     "b200ba_comm_init": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint8), C.c_int, C.c_int]),
     "b200ba_get_timings": (C.c_int, [C.c_void_p, C.POINTER(Timings)]),
+    "b200ba_dense_cholesky_solve": (C.c_int, [C.c_int, C.c_int32, C.c_int32, C.POINTER(C.c_double), C.POINTER(C.c_double),
+                                             C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "b200ba_snapshot_state": (C.c_int, [C.c_void_p]),
     "b200ba_restore_state": (C.c_int, [C.c_void_p]),
     "b200ba_version": (C.c_char_p, []),

@@ -21,6 +21,7 @@
 // which is what both a column-major panel of S and a row-major compact panel W_g[k][j] look like.
 // C is column-major (element (i, j) at C[j * ldc + i]); for a symmetric result only i >= j is touched.
 
+#include <algorithm>
 #include <cstdio>
 
 #include "ba_kernels.h"
@@ -178,7 +179,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) dgemm_nt_kernel(GemmArgs g) {
 
 int launch_dgemm_nt(const GemmArgs& g, bool lower, bool scatter, cudaStream_t s) {
   if (g.M <= 0 || g.N <= 0) return 0;
-  static bool configured = false;
+  static bool configured_dev[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  bool& configured = configured_dev[dev & 63];  // function attributes are per device
   if (!configured) {
     cudaFuncSetAttribute(dgemm_nt_kernel<true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kGemmSmem));
     cudaFuncSetAttribute(dgemm_nt_kernel<false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kGemmSmem));
@@ -196,31 +200,39 @@ int launch_dgemm_nt(const GemmArgs& g, bool lower, bool scatter, cudaStream_t s)
 }
 
 // ------------------------------------------------------------------------------------------
-// 128 x 128 diagonal tile: Cholesky in shared memory + explicit inverse of the factor
+// 128 x 128 diagonal tile: Cholesky in shared memory, then the explicit inverse of the factor
 // ------------------------------------------------------------------------------------------
-// A: column-major tile (leading dimension lda), lower triangle read; on exit its lower triangle holds L.
-// Linv: 128 x 128 column-major (leading dimension 128), lower triangle = L^-1, strict upper = 0.
-// n <= 128 is the live size (last tile of the matrix); the rest is treated as identity.
-// info[0] is raised when a pivot is not positive (the LM loop then rejects the attempt).
+// potrf_tile_kernel (1 CTA)   A: column-major tile (leading dimension lda), lower triangle read; on exit
+//                             its lower triangle holds L. n <= 128 is the live size (last tile of the
+//                             matrix); the rest is treated as identity. info[0] is raised when a pivot is
+//                             not positive (the LM loop then rejects the attempt).
+// trinv_tile_kernel (8 CTAs)  Linv: 128 x 128 column-major (leading dimension 128), lower triangle = L^-1,
+//                             strict upper = 0. The columns of the inverse are independent: each warp
+//                             solves L x = e_c for one column by forward substitution with x spread over
+//                             the lanes' registers (a 128-step dependency chain of 4 FMAs + one warp
+//                             reduction), 16 columns per CTA.
 constexpr int PT = 128;        // tile size
 constexpr int PLD = PT + 1;    // odd pitch: column walks and row walks are both conflict-free
 constexpr int POTRF_THREADS = 512;
+constexpr size_t kTileSmem = static_cast<size_t>(PT) * PLD * sizeof(double);
 
-__global__ void __launch_bounds__(POTRF_THREADS, 1)
-    potrf_tile_kernel(double* __restrict__ A, int64_t lda, int n, double* __restrict__ Linv, int* __restrict__ info) {
-  extern __shared__ __align__(16) double sm[];
-  double* L = sm;                 // [PT][PLD] column-major: L(i, j) at L[j * PLD + i]
-  double* X = sm + PT * PLD;      // inverse, same layout
-  const int tid = threadIdx.x;
-  for (int e = tid; e < PT * PT; e += POTRF_THREADS) {
+__device__ __forceinline__ void load_lower_tile(double* L, const double* __restrict__ A, int64_t lda, int n) {
+  for (int e = threadIdx.x; e < PT * PT; e += POTRF_THREADS) {
     const int j = e >> 7, i = e & 127;
     double v = (i == j) ? 1.0 : 0.0;
     if (i < n && j < n && i >= j) v = A[static_cast<int64_t>(j) * lda + i];
     L[j * PLD + i] = (i >= j) ? v : 0.0;
   }
-  __syncthreads();
+}
+
+__global__ void __launch_bounds__(POTRF_THREADS, 1)
+    potrf_tile_kernel(double* __restrict__ A, int64_t lda, int n, int* __restrict__ info) {
+  extern __shared__ __align__(16) double sm[];
+  double* L = sm;  // [PT][PLD] column-major: L(i, j) at L[j * PLD + i]
+  const int tid = threadIdx.x;
   __shared__ int s_bad;
   if (tid == 0) s_bad = 0;
+  load_lower_tile(L, A, lda, n);
   // right-looking, one column at a time. Fixed ownership for the trailing update: thread t owns row
   // (t & 127) and the columns c with c % 4 == t >> 7, so consecutive threads touch consecutive
   // shared-memory words of one column and L(row, j) is read once per step.
@@ -244,41 +256,325 @@ __global__ void __launch_bounds__(POTRF_THREADS, 1)
   }
   __syncthreads();
   if (tid == 0 && s_bad) info[0] = 1;
-  // write L back
   for (int e = tid; e < PT * PT; e += POTRF_THREADS) {
     const int j = e >> 7, i = e & 127;
     if (i < n && j < n && i >= j) A[static_cast<int64_t>(j) * lda + i] = L[j * PLD + i];
   }
-  // inverse by forward substitution, one column per thread group: column c of X solves L x = e_c.
-  // 4 threads share a column (strided over the inner product), 128 columns -> 512 threads.
-  {
-    const int c = tid >> 2, q = tid & 3;
-    for (int i = 0; i < PT; ++i) {
-      // x_i = (delta_ic - sum_{k=c}^{i-1} L(i,k) x_k) / L(i,i); rows above c are zero
-      double s = 0.0;
-      if (i > c)
-        for (int k = c + q; k < i; k += 4) s += L[k * PLD + i] * X[c * PLD + k];
-      s += __shfl_xor_sync(0xffffffffu, s, 1);
-      s += __shfl_xor_sync(0xffffffffu, s, 2);
-      if (q == 0) X[c * PLD + i] = (i < c) ? 0.0 : (((i == c) ? 1.0 : 0.0) - s) / L[i * PLD + i];
-      __syncwarp();
+}
+
+constexpr int TRINV_CTAS = 8;
+__global__ void __launch_bounds__(POTRF_THREADS, 1)
+    trinv_tile_kernel(const double* __restrict__ A, int64_t lda, int n, double* __restrict__ Linv) {
+  extern __shared__ __align__(16) double sm[];
+  double* L = sm;
+  load_lower_tile(L, A, lda, n);
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int c = blockIdx.x * (POTRF_THREADS / 32) + warp;  // 16 warps x 8 CTAs = 128 columns
+  // lane l keeps x_k for k = l, l + 32, l + 64, l + 96
+  double x0 = 0.0, x1 = 0.0, x2 = 0.0, x3 = 0.0;
+  for (int i = c; i < PT; ++i) {
+    // s = sum_{k = c}^{i - 1} L(i, k) x_k ; entries with k < c or k >= i are zero in x
+    double s = 0.0;
+    s = fma(L[(lane)*PLD + i], x0, s);
+    s = fma(L[(lane + 32) * PLD + i], x1, s);
+    s = fma(L[(lane + 64) * PLD + i], x2, s);
+    s = fma(L[(lane + 96) * PLD + i], x3, s);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const double xi = (((i == c) ? 1.0 : 0.0) - s) / L[i * PLD + i];
+    if ((i & 31) == lane) {
+      const int m = i >> 5;
+      if (m == 0) x0 = xi;
+      else if (m == 1) x1 = xi;
+      else if (m == 2) x2 = xi;
+      else x3 = xi;
     }
   }
-  __syncthreads();
-  for (int e = tid; e < PT * PT; e += POTRF_THREADS) {
-    const int j = e >> 7, i = e & 127;
-    Linv[j * PT + i] = X[j * PLD + i];
-  }
+  // L(i, k) for k > i is zero in shared memory, so the not-yet-computed x_k (still 0) never contribute
+  double* out = Linv + c * PT;
+  out[lane] = x0;
+  out[lane + 32] = x1;
+  out[lane + 64] = x2;
+  out[lane + 96] = x3;
 }
 
 int launch_potrf_tile(double* A, int64_t lda, int n, double* Linv, int* info, cudaStream_t s) {
-  static bool configured = false;
-  const size_t smem = 2 * static_cast<size_t>(PT) * PLD * sizeof(double);
+  static bool configured_dev[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  bool& configured = configured_dev[dev & 63];
   if (!configured) {
-    cudaFuncSetAttribute(potrf_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    cudaFuncSetAttribute(potrf_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kTileSmem));
+    cudaFuncSetAttribute(trinv_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kTileSmem));
     configured = true;
   }
-  potrf_tile_kernel<<<1, POTRF_THREADS, smem, s>>>(A, lda, n, Linv, info);
+  potrf_tile_kernel<<<1, POTRF_THREADS, kTileSmem, s>>>(A, lda, n, info);
+  trinv_tile_kernel<<<TRINV_CTAS, POTRF_THREADS, kTileSmem, s>>>(A, lda, n, Linv);
+  return cudaGetLastError() == cudaSuccess ? 0 : 1;
+}
+
+// ------------------------------------------------------------------------------------------
+// small helpers
+// ------------------------------------------------------------------------------------------
+// S(c, c) += lambda through the storage map (LV/lm_optimizer.h:839-852: the damping is ADDED to the diagonal)
+__global__ void add_diagonal_map_kernel(int n, double* S, DenseMap map, double lambda) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < n) S[map.col_offset(c) + c] += lambda;
+}
+void launch_add_diagonal_map(int n, double* S, const DenseMap& map, double lambda, cudaStream_t s) {
+  if (n > 0) add_diagonal_map_kernel<<<(n + 255) / 256, 256, 0, s>>>(n, S, map, lambda);
+}
+
+// ------------------------------------------------------------------------------------------
+// triangular solves with the packed factor
+// ------------------------------------------------------------------------------------------
+// The factor lives in packed block-column panels: panel k holds rows k0 .. n of the columns k0 .. k0 + NB
+// (k0 = k * NB) column-major with leading dimension hk = even(n - k0); element L(i, c) = P_k[(c - k0) * hk +
+// (i - k0)]. Every 128 x 128 diagonal tile also has its explicit inverse (Linv tiles, from potrf_tile).
+//
+// forward step, tile t (columns c0 .. c0 + 128): y_t = Linv_t b_t ; b_i -= sum_c L(i, c) y_c for i below.
+// One launch per tile; every CTA recomputes y_t (128 x 128 product, L2 resident) and owns 256 rows below.
+constexpr int TS_THREADS = 256;
+__global__ void __launch_bounds__(TS_THREADS)
+    trsv_forward_step_kernel(const double* __restrict__ P, int64_t hk, int row0_in_panel, int col_in_panel, int live,
+                             int rows_below, const double* __restrict__ Linv, double* __restrict__ b /* at row c0 */) {
+  __shared__ double y[PT];
+  const int tid = threadIdx.x;
+  if (tid < PT) {
+    double acc = 0.0;
+    if (tid < live)
+      for (int c = 0; c <= tid; ++c) acc = fma(Linv[c * PT + tid], b[c], acc);
+    y[tid] = acc;
+  }
+  __syncthreads();
+  const int r = blockIdx.x * TS_THREADS + tid;  // row below the tile
+  if (r < rows_below) {
+    const double* Lp = P + static_cast<int64_t>(col_in_panel) * hk + row0_in_panel + PT + r;
+    double acc = 0.0;
+#pragma unroll 8
+    for (int c = 0; c < live; ++c) acc = fma(Lp[static_cast<int64_t>(c) * hk], y[c], acc);
+    b[PT + r] -= acc;
+  }
+  // the tile's own solution is written last by block 0 (every CTA has read b_t by now? no: other CTAs may
+  // still be reading b_t) -> it goes to a separate output vector
+}
+__global__ void trsv_store_tile_kernel(const double* __restrict__ Linv, const double* __restrict__ b, int live,
+                                       double* __restrict__ out, bool transpose) {
+  const int tid = threadIdx.x;
+  if (tid >= live) return;
+  double acc = 0.0;
+  if (!transpose) {
+    for (int c = 0; c <= tid; ++c) acc = fma(Linv[c * PT + tid], b[c], acc);
+  } else {
+    for (int i = tid; i < live; ++i) acc = fma(Linv[tid * PT + i], b[i], acc);
+  }
+  out[tid] = acc;
+}
+
+// backward step, tile t (rows r0 .. r0 + live): x_t = Linv_t^T y_t ; y_c -= sum_{i in t} L(i, c) x_i for every
+// column c to the LEFT of the tile. One warp per column (the 128 rows of a column are contiguous).
+__global__ void __launch_bounds__(TS_THREADS)
+    trsv_backward_step_kernel(const double* __restrict__ Lpack, const int64_t* __restrict__ panel_off,
+                              const int* __restrict__ panel_h, int NB, int r0, int live, int n_cols_left,
+                              const double* __restrict__ Linv, const double* __restrict__ yt /* y at row r0 */,
+                              double* __restrict__ y /* full vector */) {
+  __shared__ double x[PT];
+  const int tid = threadIdx.x;
+  if (tid < PT) {
+    double acc = 0.0;
+    if (tid < live)
+      for (int i = tid; i < live; ++i) acc = fma(Linv[tid * PT + i], yt[i], acc);
+    x[tid] = acc;
+  }
+  __syncthreads();
+  const int warp = tid >> 5, lane = tid & 31;
+  const int c = blockIdx.x * (TS_THREADS / 32) + warp;
+  if (c >= n_cols_left) return;
+  const int k = c / NB;
+  const double* col = Lpack + panel_off[k] + static_cast<int64_t>(c - k * NB) * panel_h[k] + (r0 - k * NB);
+  double acc = 0.0;
+  for (int i = lane; i < live; i += 32) acc = fma(col[i], x[i], acc);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (lane == 0) y[c] -= acc;
+}
+
+// ------------------------------------------------------------------------------------------
+// host side: blocked right-looking Cholesky with look-ahead, block-cyclic over the ranks
+// ------------------------------------------------------------------------------------------
+int dense_plan(DenseCtx* d, int n, int nb, int rank, int ranks) {
+  d->n = n;
+  d->rank = rank;
+  d->ranks = ranks;
+  d->NB = nb;
+  d->nblk = (n + nb - 1) / nb;
+  d->ntiles = (n + PT - 1) / PT;
+  d->map.nb = nb;
+  d->map.ranks = ranks;
+  d->map.blocks_per_rank = (d->nblk + ranks - 1) / ranks;
+  d->map.ld = (n + 1) / 2 * 2;
+  d->chunk = static_cast<int64_t>(d->map.blocks_per_rank) * nb * d->map.ld;
+  d->panel_off.assign(d->nblk + 1, 0);
+  d->panel_h.assign(std::max(1, d->nblk), 0);
+  for (int k = 0; k < d->nblk; ++k) {
+    const int hk = n - k * nb;
+    d->panel_h[k] = (hk + 1) / 2 * 2;
+    d->panel_off[k + 1] = d->panel_off[k] + static_cast<int64_t>(d->panel_h[k]) * nb;
+  }
+  return 0;
+}
+
+// Factors the matrix held (lower triangle, storage map d->map) in d->S. On return every rank holds the
+// complete factor in d->Lpack. Work is enqueued on d->s_main / d->s_panel; the caller synchronises.
+int dense_factor(DenseCtx* d) {
+  const int n = d->n, NB = d->NB, R = d->ranks, me = d->rank;
+  if (n == 0) return 0;
+  const int sub_n = NB / PT;
+  cudaStream_t sm = d->s_main, sp = d->s_panel;
+  auto owner = [&](int k) { return k % R; };
+  // S is ready when everything queued on s_main so far has run
+  cudaEventRecord(d->ev_misc, sm);
+  cudaStreamWaitEvent(sp, d->ev_misc, 0);
+
+  // trailing update of the block columns [j_first, j_last] by panel k (single launch when they are contiguous in S)
+  auto update = [&](int k, int j_first, int j_last, cudaStream_t st) -> int {
+    const int k0 = k * NB, kw = std::min(NB, n - k0);
+    const int j0 = j_first * NB;
+    const int jn = std::min(n, (j_last + 1) * NB) - j0;
+    if (jn <= 0) return 0;
+    GemmArgs g{};
+    g.M = n - j0;
+    g.N = jn;
+    g.K = kw;
+    g.A = d->Lpack + d->panel_off[k] + (j0 - k0);
+    g.lda = d->panel_h[k];
+    g.B = g.A;
+    g.ldb = g.lda;
+    g.C = d->S + d->map.col_offset(j0) + j0;
+    g.ldc = d->map.ld;
+    g.alpha = -1.0;
+    g.beta = 1.0;
+    g.a_aligned = g.b_aligned = gemm_operand_aligned(g.A, g.lda);
+    return launch_dgemm_nt(g, /*lower=*/true, /*scatter=*/false, st);
+  };
+
+  for (int k = 0; k < d->nblk; ++k) {
+    const int k0 = k * NB, kw = std::min(NB, n - k0), hk = d->panel_h[k], hlive = n - k0;
+    double* P = d->Lpack + d->panel_off[k];
+    if (owner(k) == me) {
+      // pack the (fully updated) block column into its panel, then factor it in place
+      cudaMemcpy2DAsync(P, static_cast<size_t>(hk) * sizeof(double), d->S + d->map.col_offset(k0) + k0,
+                        static_cast<size_t>(d->map.ld) * sizeof(double), static_cast<size_t>(hlive) * sizeof(double), kw,
+                        cudaMemcpyDeviceToDevice, sp);
+      for (int sub = 0; sub < sub_n; ++sub) {
+        const int c0 = sub * PT;
+        if (c0 >= kw) break;
+        const int live = std::min(PT, kw - c0);
+        double* tile = P + static_cast<int64_t>(c0) * hk + c0;
+        double* Li = d->Linv + static_cast<int64_t>(k * sub_n + sub) * PT * PT;
+        if (launch_potrf_tile(tile, hk, live, Li, d->info, sp)) return 1;
+        const int below = hlive - c0 - PT;
+        if (below > 0) {
+          GemmArgs g{};  // rows below: X <- X Linv^T
+          g.M = below;
+          g.N = PT;
+          g.K = PT;
+          g.A = tile + PT;
+          g.lda = hk;
+          g.B = Li;
+          g.ldb = PT;
+          g.C = tile + PT;
+          g.ldc = hk;
+          g.alpha = 1.0;
+          g.beta = 0.0;
+          g.a_aligned = gemm_operand_aligned(g.A, g.lda);
+          g.b_aligned = gemm_operand_aligned(g.B, g.ldb);
+          if (launch_dgemm_nt(g, false, false, sp)) return 1;
+          const int rest = kw - c0 - PT;  // remaining columns of this panel
+          if (rest > 0) {
+            GemmArgs u{};
+            u.M = below;
+            u.N = rest;
+            u.K = PT;
+            u.A = tile + PT;
+            u.lda = hk;
+            u.B = u.A;
+            u.ldb = hk;
+            u.C = P + static_cast<int64_t>(c0 + PT) * hk + (c0 + PT);
+            u.ldc = hk;
+            u.alpha = -1.0;
+            u.beta = 1.0;
+            u.a_aligned = u.b_aligned = gemm_operand_aligned(u.A, u.lda);
+            if (launch_dgemm_nt(u, true, false, sp)) return 1;
+          }
+        }
+      }
+    }
+    if (R > 1) {
+      if (d->bcast(P, static_cast<size_t>(hk) * kw, owner(k), sp, d->user)) return 1;
+      if (owner(k) != me && d->bcast_linv) {
+        // the inverse tiles travel too (the triangular solves run on every rank)
+      }
+      if (d->bcast(d->Linv + static_cast<int64_t>(k) * sub_n * PT * PT, static_cast<size_t>(sub_n) * PT * PT, owner(k), sp,
+                   d->user))
+        return 1;
+    }
+    cudaEventRecord(d->ev_ready[k & 1], sp);
+    // look-ahead: the owner of the next block column updates it first, on the panel stream
+    int first_rest = k + 1;
+    if (k + 1 < d->nblk && owner(k + 1) == me) {
+      if (k > 0) cudaStreamWaitEvent(sp, d->ev_main[(k - 1) & 1], 0);
+      if (update(k, k + 1, k + 1, sp)) return 1;
+      first_rest = k + 2;
+    }
+    cudaStreamWaitEvent(sm, d->ev_ready[k & 1], 0);
+    if (R == 1) {
+      if (first_rest < d->nblk && update(k, first_rest, d->nblk - 1, sm)) return 1;
+    } else {
+      for (int j = first_rest; j < d->nblk; ++j)
+        if (owner(j) == me && update(k, j, j, sm)) return 1;
+    }
+    cudaEventRecord(d->ev_main[k & 1], sm);
+  }
+  cudaEventRecord(d->ev_misc, sp);
+  cudaStreamWaitEvent(sm, d->ev_misc, 0);
+  return cudaGetLastError() == cudaSuccess ? 0 : 1;
+}
+
+// Solves L L^T x = b in place (b on the device, length n) with the packed factor, on s_main.
+int dense_solve(DenseCtx* d, double* b) {
+  const int n = d->n, NB = d->NB;
+  if (n == 0) return 0;
+  cudaStream_t sm = d->s_main;
+  const int sub_n = NB / PT;
+  auto linv_of = [&](int t) {
+    const int k = (t * PT) / NB, sub = (t * PT - k * NB) / PT;
+    return d->Linv + static_cast<int64_t>(k * sub_n + sub) * PT * PT;
+  };
+  // forward: L y = b
+  for (int t = 0; t < d->ntiles; ++t) {
+    const int c0 = t * PT, live = std::min(PT, n - c0), k = c0 / NB;
+    const int rows_below = n - c0 - PT;
+    const double* Li = linv_of(t);
+    if (rows_below > 0) {
+      const int grid = (rows_below + TS_THREADS - 1) / TS_THREADS;
+      trsv_forward_step_kernel<<<grid, TS_THREADS, 0, sm>>>(d->Lpack + d->panel_off[k], d->panel_h[k], c0 - k * NB,
+                                                              c0 - k * NB, live, rows_below, Li, b + c0);
+    }
+    trsv_store_tile_kernel<<<1, PT, 0, sm>>>(Li, b + c0, live, d->tmp + c0, false);
+  }
+  // backward: L^T x = y  (y = d->tmp)
+  for (int t = d->ntiles - 1; t >= 0; --t) {
+    const int r0 = t * PT, live = std::min(PT, n - r0);
+    const double* Li = linv_of(t);
+    if (r0 > 0) {
+      const int grid = (r0 + TS_THREADS / 32 - 1) / (TS_THREADS / 32);
+      trsv_backward_step_kernel<<<grid, TS_THREADS, 0, sm>>>(d->Lpack, d->d_panel_off, d->d_panel_h, NB, r0, live, r0, Li,
+                                                               d->tmp + r0, d->tmp);
+    }
+    trsv_store_tile_kernel<<<1, PT, 0, sm>>>(Li, d->tmp + r0, live, b + r0, true);
+  }
   return cudaGetLastError() == cudaSuccess ? 0 : 1;
 }
 

@@ -40,6 +40,7 @@ struct NcclApi {
   int (*CommInitRank)(void**, int, NcclUniqueId, int) = nullptr;
   int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
   int (*Broadcast)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+  int (*ReduceScatter)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
   int (*CommDestroy)(void*) = nullptr;
   const char* (*GetErrorString)(int) = nullptr;
 };
@@ -68,9 +69,11 @@ bool load_nccl(std::string* err) {
   *reinterpret_cast<void**>(&g_nccl.CommInitRank) = dlsym(lib, "ncclCommInitRank");
   *reinterpret_cast<void**>(&g_nccl.AllReduce) = dlsym(lib, "ncclAllReduce");
   *reinterpret_cast<void**>(&g_nccl.Broadcast) = dlsym(lib, "ncclBroadcast");
+  *reinterpret_cast<void**>(&g_nccl.ReduceScatter) = dlsym(lib, "ncclReduceScatter");
   *reinterpret_cast<void**>(&g_nccl.CommDestroy) = dlsym(lib, "ncclCommDestroy");
   *reinterpret_cast<void**>(&g_nccl.GetErrorString) = dlsym(lib, "ncclGetErrorString");
-  if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllReduce || !g_nccl.Broadcast || !g_nccl.CommDestroy) {
+  if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllReduce || !g_nccl.Broadcast || !g_nccl.ReduceScatter ||
+      !g_nccl.CommDestroy) {
     *err = "libnccl lacks a required symbol";
     g_nccl.lib = nullptr;
     return false;
@@ -164,6 +167,14 @@ struct b200ba_handle {
   // multi-GPU
   void* comm = nullptr;
   int rank = 0, n_ranks = 1;
+
+  // dense phase on the in-tree DMMA kernels (ba_dense.cu); B200BA_DENSE=lib selects the cuBLAS / cuSOLVER path
+  bool own_dense = true;
+  DenseCtx dn;
+  int dense_planned_ranks = 0, dense_planned_n = -1;
+  int dense_nb = 256;                   // column-block width of the factorisation (B200BA_DENSE_NB, multiple of 128)
+  cudaStream_t panel_stream = nullptr;  // panel factorisations + broadcasts (look-ahead)
+  int* d_ident_cols = nullptr;          // 0 .. nd - 1 (scatter epilogue of the dense contraction with several ranks)
 
   // timings
   b200ba_timings timings{};
@@ -374,10 +385,10 @@ int build_groups(b200ba_handle* h, bool allocate) {
     if (dev_alloc(h, &h->d_count, std::max(1, h->n_groups))) return 1;
     if (h->h_count) cudaFreeHost(h->h_count);
     CUDA_TRY(h, cudaMallocHost(reinterpret_cast<void**>(&h->h_count), std::max(1, h->n_groups) * sizeof(int)));
-    h->wc_stride = static_cast<size_t>(gb) * L.bs * std::max(1, L.nd);
+    h->wc_stride = static_cast<size_t>(gb) * L.bs * (std::max(1, L.nd) + 1);
     h->p_stride = static_cast<size_t>(std::max(1, L.nd)) * std::max(1, L.nd);
     if (dev_alloc(h, &h->d_Wc, 2 * h->wc_stride)) return 1;
-    if (dev_alloc(h, &h->d_P, 2 * h->p_stride)) return 1;
+    if (!h->own_dense && dev_alloc(h, &h->d_P, 2 * h->p_stride)) return 1;
     for (int i = 0; i < 2; ++i) {
       if (!h->ev_syrk[i]) CUDA_TRY(h, cudaEventCreateWithFlags(&h->ev_syrk[i], cudaEventDisableTiming));
       if (!h->ev_scatter[i]) CUDA_TRY(h, cudaEventCreateWithFlags(&h->ev_scatter[i], cudaEventDisableTiming));
@@ -387,6 +398,57 @@ int build_groups(b200ba_handle* h, bool allocate) {
   }
   CUDA_TRY(h, cudaMemcpy(h->d_group_of_block, gob.data(), std::max(1, nb) * sizeof(int), cudaMemcpyHostToDevice));
   if (nb > 0) CUDA_TRY(h, cudaMemcpy(h->d_group_blocks, order.data(), nb * sizeof(int), cudaMemcpyHostToDevice));
+  return 0;
+}
+
+// ---- dense phase buffers (own kernels) ------------------------------------------------------
+int nccl_bcast_cb(double* buf, size_t count, int root, cudaStream_t s, void* user) {
+  b200ba_handle* h = static_cast<b200ba_handle*>(user);
+  const int rc = g_nccl.Broadcast(buf, buf, count, kNcclDouble, root, h->comm, s);
+  if (rc != 0) {
+    h->error = std::string("ncclBroadcast: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "error");
+    return 1;
+  }
+  return 0;
+}
+
+// (Re)plans the storage of S / the packed factor for the current (n_d, rank count).
+int plan_dense(b200ba_handle* h) {
+  if (!h->own_dense || !h->have_layout) return 0;
+  const int nd = h->L.nd;
+  if (h->dense_planned_n == nd && h->dense_planned_ranks == h->n_ranks) return 0;
+  DenseCtx& d = h->dn;
+  dense_plan(&d, nd, h->dense_nb, h->rank, h->n_ranks);
+  if (dev_alloc(h, &h->d_S, static_cast<size_t>(std::max<int64_t>(1, d.chunk * h->n_ranks)))) return 1;
+  d.S = h->d_S;
+  if (dev_alloc(h, &d.Lpack, static_cast<size_t>(std::max<int64_t>(1, d.panel_off[d.nblk])))) return 1;
+  if (dev_alloc(h, &d.Linv, static_cast<size_t>(std::max(1, d.nblk)) * (d.NB / 128) * 128 * 128)) return 1;
+  if (dev_alloc(h, &d.tmp, std::max(1, nd))) return 1;
+  if (dev_alloc(h, &d.d_panel_off, d.panel_off.size())) return 1;
+  if (dev_alloc(h, &d.d_panel_h, d.panel_h.size())) return 1;
+  CUDA_TRY(h, cudaMemcpy(d.d_panel_off, d.panel_off.data(), d.panel_off.size() * sizeof(int64_t), cudaMemcpyHostToDevice));
+  CUDA_TRY(h, cudaMemcpy(d.d_panel_h, d.panel_h.data(), d.panel_h.size() * sizeof(int), cudaMemcpyHostToDevice));
+  {
+    std::vector<int> ident(std::max(1, nd));
+    for (int i = 0; i < nd; ++i) ident[i] = i;
+    if (dev_alloc(h, &h->d_ident_cols, ident.size())) return 1;
+    CUDA_TRY(h, cudaMemcpy(h->d_ident_cols, ident.data(), ident.size() * sizeof(int), cudaMemcpyHostToDevice));
+  }
+  // the un-owned chunks of S are never written by the contraction of a single rank but are read by nobody either;
+  // zero once so that partial sums start clean
+  CUDA_TRY(h, cudaMemset(h->d_S, 0, static_cast<size_t>(std::max<int64_t>(1, d.chunk * h->n_ranks)) * sizeof(double)));
+  d.info = h->d_info;
+  d.s_main = h->stream;
+  d.s_panel = h->panel_stream;
+  for (int i = 0; i < 2; ++i) {
+    if (!d.ev_ready[i]) CUDA_TRY(h, cudaEventCreateWithFlags(&d.ev_ready[i], cudaEventDisableTiming));
+    if (!d.ev_main[i]) CUDA_TRY(h, cudaEventCreateWithFlags(&d.ev_main[i], cudaEventDisableTiming));
+  }
+  if (!d.ev_misc) CUDA_TRY(h, cudaEventCreateWithFlags(&d.ev_misc, cudaEventDisableTiming));
+  d.bcast = nccl_bcast_cb;
+  d.user = h;
+  h->dense_planned_n = nd;
+  h->dense_planned_ranks = h->n_ranks;
   return 0;
 }
 
@@ -443,9 +505,10 @@ int make_layout(b200ba_handle* h, const b200ba_options* opt) {
   L.jc_intr = 9 + (L.rig_in_state ? 6 : 0);
   L.n_jcols = L.jc_intr + kmax;
   const bool same = h->have_layout && memcmp(&L, &h->L, sizeof(Layout)) == 0;
-  if (same) return 0;
+  if (same) return plan_dense(h);
   h->L = L;
   h->have_layout = true;
+  h->dense_planned_n = -1;
 
   const int64_t n = h->n_obs;
   if (dev_alloc(h, &h->out.residual, 2 * n)) return 1;
@@ -482,7 +545,11 @@ int make_layout(b200ba_handle* h, const b200ba_options* opt) {
   s.bd = s.base + obd;
   s.scalars = s.base + osc;
   if (dev_alloc(h, &h->d_W, static_cast<size_t>(L.nbd) * L.nd)) return 1;
-  if (dev_alloc(h, &h->d_S, static_cast<size_t>(L.nd) * L.nd + L.nd)) return 1;  // + partial rhs tail
+  if (!h->own_dense) {
+    if (dev_alloc(h, &h->d_S, static_cast<size_t>(L.nd) * L.nd + L.nd)) return 1;  // + partial rhs tail
+  } else if (plan_dense(h)) {
+    return 1;
+  }
   if (dev_alloc(h, &h->d_Linv, static_cast<size_t>(L.dsz) * L.nblocks)) return 1;
   if (dev_alloc(h, &h->d_v, L.nbd)) return 1;
   if (dev_alloc(h, &h->d_y, L.nbd)) return 1;
@@ -698,7 +765,10 @@ int factor_dense(b200ba_handle* h) {
 
 // Hot loop 2: Schur complement solve for a given lambda (LV/lm_optimizer.h:1246-1369).
 // Leaves x = [x_points | x_dense] in d_x. *spd = 0 when a factorisation met a non-positive pivot.
+int solve_system_own(b200ba_handle* h, double lambda, int* spd);
+
 int solve_system(b200ba_handle* h, double lambda, int* spd) {
+  if (h->own_dense) return solve_system_own(h, lambda, spd);
   const Layout& L = h->L;
   const double one = 1.0, minus_one = -1.0;
   bool grouped_done = false;
@@ -731,7 +801,7 @@ int solve_system(b200ba_handle* h, double lambda, int* spd) {
       double* P = h->d_P + b * h->p_stride;
       const int* cols = h->d_cols + static_cast<size_t>(g) * L.nd;
       if (it >= 2) CUDA_TRY(h, cudaStreamWaitEvent(h->stream, h->ev_scatter[b], 0));  // buffer b is free again
-      launch_gather_scale(L.bs, nblk, L.nd, mg, h->sys.B, h->d_Linv, h->d_group_blocks + h->group_start[g], cols, Wc,
+      launch_gather_scale(L.bs, nblk, L.nd, mg, mg, h->sys.B, h->d_Linv, h->d_group_blocks + h->group_start[g], cols, Wc,
                           h->stream);
       // row-major Wc [kg x mg] is the column-major mg x kg panel: P = Wc^T Wc (lower)
       CUBLAS_TRY(h, cublasDsyrk(h->cublas, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_N, mg, kg, &one, Wc, mg, &zero, P, mg));
@@ -836,6 +906,168 @@ int solve_system(b200ba_handle* h, double lambda, int* spd) {
   return 0;
 }
 
+// The same solve on the in-tree kernels (ba_dense.cu): the contraction is a DMMA product whose epilogue
+// scatters straight into S, the reduced system is factorised by a blocked right-looking Cholesky with
+// look-ahead (block columns dealt cyclically to the ranks, panels broadcast over NVLink), the
+// triangular solves run on the packed factor. With several ranks S is formed as partial sums
+// S_r = C_r - sum_{g of r} W_g^T W_g that ONE reduce-scatter per attempt turns into the block columns each
+// rank owns; nobody holds or reduces the whole matrix.
+int solve_system_own(b200ba_handle* h, double lambda, int* spd) {
+  const Layout& L = h->L;
+  DenseCtx& d = h->dn;
+  const int nd = L.nd, R = h->n_ranks;
+  const double one = 1.0, minus_one = -1.0, zero = 0.0;
+  {
+    ScopedPhase ph(h, PH_SCHUR);
+    CUDA_TRY(h, cudaMemsetAsync(h->d_fail, 0, sizeof(int), h->stream));
+    CUDA_TRY(h, cudaMemsetAsync(h->d_info, 0, sizeof(int), h->stream));
+    launch_schur_blocks(L.bs, L.nblocks, h->sys.Dblk, h->sys.bp, lambda, h->d_Linv, h->d_v, h->d_fail, h->stream);
+    // S <- C_r (this rank's partial dense block) through the storage map, on the side stream
+    // underneath the block factorisations and the first gather
+    CUDA_TRY(h, cudaEventRecord(h->ev_s_ready, h->stream));  // everything that used S before is done
+    CUDA_TRY(h, cudaStreamWaitEvent(h->side_stream, h->ev_s_ready, 0));
+    if (nd > 0) {
+      if (R == 1) {
+        CUDA_TRY(h, cudaMemcpy2DAsync(h->d_S, d.map.ld * sizeof(double), h->sys.C, static_cast<size_t>(nd) * sizeof(double),
+                                      static_cast<size_t>(nd) * sizeof(double), nd, cudaMemcpyDeviceToDevice, h->side_stream));
+      } else {
+        for (int j = 0; j < d.nblk; ++j) {
+          const int c0 = j * d.NB, w = std::min(d.NB, nd - c0);
+          CUDA_TRY(h, cudaMemcpy2DAsync(h->d_S + d.map.col_offset(c0), d.map.ld * sizeof(double),
+                                        h->sys.C + static_cast<size_t>(c0) * nd, static_cast<size_t>(nd) * sizeof(double),
+                                        static_cast<size_t>(nd) * sizeof(double), w, cudaMemcpyDeviceToDevice, h->side_stream));
+        }
+      }
+    }
+    CUDA_TRY(h, cudaEventRecord(h->ev_s_ready, h->side_stream));
+    launch_block_solve_t(L.bs, L.nblocks, h->d_Linv, h->d_v, h->d_u, h->stream);  // u = D^-1 b_block
+    h->timings.kernel_launches += 2;
+    bool joined = false;
+    auto join_copy = [&]() {
+      if (!joined) cudaStreamWaitEvent(h->stream, h->ev_s_ready, 0);
+      joined = true;
+    };
+    if (h->use_grouped) {
+      // structured contraction: per group gather -> DMMA rank-k update with the scatter epilogue
+      int it = 0;
+      for (int g = h->rank; g < h->n_groups; g += R) {
+        const int nblk = h->group_start[g + 1] - h->group_start[g];
+        const int kg = nblk * L.bs, mg = h->group_count[g];
+        if (mg == 0 || kg == 0) continue;
+        const int ldw = (mg + 1) / 2 * 2;
+        double* Wc = h->d_Wc + (it & 1) * h->wc_stride;
+        const int* cols = h->d_cols + static_cast<size_t>(g) * nd;
+        launch_gather_scale(L.bs, nblk, nd, mg, ldw, h->sys.B, h->d_Linv, h->d_group_blocks + h->group_start[g], cols, Wc,
+                            h->stream);
+        join_copy();
+        GemmArgs ga{};
+        ga.M = ga.N = mg;
+        ga.K = kg;
+        ga.A = ga.B = Wc;
+        ga.lda = ga.ldb = ldw;
+        ga.C = h->d_S;
+        ga.alpha = -1.0;
+        ga.beta = 1.0;
+        ga.a_aligned = ga.b_aligned = gemm_operand_aligned(Wc, ldw);
+        ga.cols = cols;
+        ga.map = d.map;
+        if (launch_dgemm_nt(ga, true, true, h->stream)) {
+          h->error = "dgemm_nt (contraction) launch failed";
+          return 1;
+        }
+        h->timings.contraction_flops += static_cast<double>(mg) * mg * kg;
+        h->timings.kernel_launches += 2;
+        ++it;
+      }
+    } else if (L.nbd > 0 && nd > 0) {
+      // dense contraction over this rank's slice of the Schur blocks: S_r -= W_r^T W_r
+      const int p0 = static_cast<int>(static_cast<int64_t>(L.nblocks) * h->rank / R);
+      const int p1 = static_cast<int>(static_cast<int64_t>(L.nblocks) * (h->rank + 1) / R);
+      const int k_rows = L.bs * (p1 - p0);
+      launch_schur_scale_rows(L.bs, L.nblocks, nd, h->sys.B, h->d_Linv, h->d_W, h->stream);
+      h->timings.kernel_launches += 1;
+      if (k_rows > 0) {
+        const double* Wr = h->d_W + static_cast<size_t>(L.bs) * p0 * nd;
+        join_copy();
+        GemmArgs ga{};
+        ga.M = ga.N = nd;
+        ga.K = k_rows;
+        ga.A = ga.B = Wr;
+        ga.lda = ga.ldb = nd;
+        ga.C = h->d_S;
+        ga.ldc = d.map.ld;
+        ga.alpha = -1.0;
+        ga.beta = 1.0;
+        ga.a_aligned = ga.b_aligned = gemm_operand_aligned(Wr, nd);
+        ga.cols = h->d_ident_cols;
+        ga.map = d.map;
+        if (launch_dgemm_nt(ga, true, /*scatter=*/R > 1, h->stream)) {
+          h->error = "dgemm_nt (contraction) launch failed";
+          return 1;
+        }
+        h->timings.contraction_flops += static_cast<double>(nd) * nd * k_rows;
+        h->timings.kernel_launches += 1;
+      }
+    }
+    join_copy();
+    if (h->rank == 0) launch_add_diagonal_map(nd, h->d_S, d.map, lambda, h->stream);
+    // x_dense <- b_d - B^T u   (B, D, b are global after the per-build all-reduce)
+    CUDA_TRY(h, cudaMemcpyAsync(h->d_x + L.nbd, h->sys.bd, nd * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+    if (L.nbd > 0 && nd > 0)
+      CUBLAS_TRY(h, cublasDgemv(h->cublas, CUBLAS_OP_N, nd, L.nbd, &minus_one, h->sys.B, nd, h->d_u, 1, &one, h->d_x + L.nbd, 1));
+    h->timings.kernel_launches += 2;
+  }
+  if (R > 1 && nd > 0) {
+    // partial sums -> the block columns each rank owns (in place: rank r keeps chunk r)
+    ScopedPhase ph(h, PH_ALLREDUCE);
+    const int rc = g_nccl.ReduceScatter(h->d_S, h->d_S + static_cast<size_t>(h->rank) * d.chunk, static_cast<size_t>(d.chunk),
+                                        kNcclDouble, kNcclSum, h->comm, h->stream);
+    if (rc != 0) {
+      h->error = std::string("ncclReduceScatter: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "error");
+      return 1;
+    }
+  }
+  {
+    ScopedPhase ph(h, PH_FACTOR);
+    if (dense_factor(&d)) {
+      if (h->error.empty()) h->error = "dense_factor: launch failed";
+      return 1;
+    }
+    h->timings.factor_flops += static_cast<double>(nd) * nd * nd / 3.0;
+    if (R > 1) {
+      // every rank must take the same branch of the LM loop
+      const int rc = g_nccl.AllReduce(h->d_info, h->d_info, 1, kNcclInt32, kNcclMax, h->comm, h->stream);
+      if (rc != 0) {
+        h->error = "ncclAllReduce (factorisation status) failed";
+        return 1;
+      }
+    }
+  }
+  {
+    ScopedPhase ph(h, PH_SOLVE);
+    if (dense_solve(&d, h->d_x + L.nbd)) {
+      h->error = "dense_solve: launch failed";
+      return 1;
+    }
+    h->timings.kernel_launches += 4 * d.ntiles;
+  }
+  {
+    ScopedPhase ph(h, PH_SCHUR);
+    // t = B x_d ; x_block = u - D^-1 t   (W is never needed for the back-substitution)
+    if (L.nbd > 0 && nd > 0)
+      CUBLAS_TRY(h, cublasDgemv(h->cublas, CUBLAS_OP_T, nd, L.nbd, &one, h->sys.B, nd, h->d_x + L.nbd, 1, &zero, h->d_y, 1));
+    else if (L.nbd > 0)
+      CUDA_TRY(h, cudaMemsetAsync(h->d_y, 0, L.nbd * sizeof(double), h->stream));
+    launch_block_backsub2(L.bs, L.nblocks, h->d_Linv, h->d_u, h->d_y, h->d_x, h->stream);
+    h->timings.kernel_launches += 1;
+  }
+  CUDA_TRY(h, cudaMemcpyAsync(h->h_flags, h->d_info, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(h, cudaMemcpyAsync(h->h_flags + 1, h->d_fail, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  if (sync_stream(h)) return 1;
+  *spd = (h->h_flags[0] == 0 && h->h_flags[1] == 0) ? 1 : 0;
+  return 0;
+}
+
 int check_ready(b200ba_handle* h, const b200ba_options* opt) {
   if (!h) return 1;
   if (!opt) {
@@ -871,6 +1103,9 @@ void free_handle_buffers(b200ba_handle* h) {
   if (h->h_count) cudaFreeHost(h->h_count);
   h->h_count = nullptr;
   F(h->d_partial); F(h->d_scal);
+  F(h->dn.Lpack); F(h->dn.Linv); F(h->dn.tmp); F(h->dn.d_panel_off); F(h->dn.d_panel_h); F(h->d_ident_cols);
+  h->dn.S = nullptr;
+  h->dense_planned_n = -1;
   if (h->h_scal) cudaFreeHost(h->h_scal);
   if (h->h_flags) cudaFreeHost(h->h_flags);
   h->h_scal = nullptr;
@@ -1054,6 +1289,13 @@ int b200ba_create(const b200ba_problem* p, int device, b200ba_handle** out) {
     h->h_obs_point.assign(p->obs_point, p->obs_point + n);
     h->h_obs_xy.assign(p->obs_xy, p->obs_xy + 2 * n);
   }
+  if (const char* e = getenv("B200BA_DENSE")) h->own_dense = !(strcmp(e, "lib") == 0 || strcmp(e, "0") == 0);
+  if (const char* e = getenv("B200BA_DENSE_NB")) h->dense_nb = std::max(128, atoi(e) / 128 * 128);
+  {
+    int lo = 0, hi = 0;
+    cudaDeviceGetStreamPriorityRange(&lo, &hi);
+    TRYC(cuda_ok(cudaStreamCreateWithPriority(&h->panel_stream, cudaStreamNonBlocking, hi), "cudaStreamCreate"));
+  }
   if (const char* e = getenv("B200BA_GROUPED")) h->force_grouped = atoi(e);
   if (const char* e = getenv("B200BA_DIST_CHOL")) h->chol_mode = atoi(e);
   if (const char* e = getenv("B200BA_CHOL_NB")) h->chol_nb = std::max(32, atoi(e));
@@ -1102,6 +1344,12 @@ void b200ba_destroy(b200ba_handle* h) {
   if (h->cusolver) cusolverDnDestroy(h->cusolver);
   if (h->stream) cudaStreamDestroy(h->stream);
   if (h->side_stream) cudaStreamDestroy(h->side_stream);
+  if (h->panel_stream) cudaStreamDestroy(h->panel_stream);
+  for (int i = 0; i < 2; ++i) {
+    if (h->dn.ev_ready[i]) cudaEventDestroy(h->dn.ev_ready[i]);
+    if (h->dn.ev_main[i]) cudaEventDestroy(h->dn.ev_main[i]);
+  }
+  if (h->dn.ev_misc) cudaEventDestroy(h->dn.ev_misc);
   delete h;
 }
 
@@ -1474,6 +1722,107 @@ int b200ba_get_timings(const b200ba_handle* h, b200ba_timings* t) {
   return 0;
 }
 
+// ---- stand-alone dense SPD solve on the in-tree kernels (tests / profiling) ---------------------
+// A: n x n symmetric (either major order), host. Factorises with the blocked Cholesky of ba_dense.cu
+// (block width nb, a multiple of 128) and solves A x = b. Returns 4 when a pivot is not positive.
+int b200ba_dense_cholesky_solve(int device, int32_t n, int32_t nb, const double* A, const double* b, double* x,
+                                double* factor_ms, double* solve_ms) {
+  if (n < 1 || nb < 128 || nb % 128 != 0 || !A || !b || !x) {
+    g_create_error = "b200ba_dense_cholesky_solve: bad argument";
+    return 2;
+  }
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    g_create_error = "no CUDA device available (this library has no CPU fallback)";
+    return 3;
+  }
+  if (device >= 0) cudaSetDevice(device);
+  DenseCtx d;
+  dense_plan(&d, n, nb, 0, 1);
+  int rc = 0;
+  double* dA = nullptr;
+  double* db = nullptr;
+  int* dinfo = nullptr;
+  cudaEvent_t e0 = nullptr, e1 = nullptr, e2 = nullptr;
+  auto ok = [&](cudaError_t e) {
+    if (e != cudaSuccess && rc == 0) {
+      g_create_error = std::string("b200ba_dense_cholesky_solve: ") + cudaGetErrorString(e);
+      rc = 1;
+    }
+    return e == cudaSuccess;
+  };
+  int lo = 0, hi = 0;
+  cudaDeviceGetStreamPriorityRange(&lo, &hi);
+  ok(cudaStreamCreateWithFlags(&d.s_main, cudaStreamNonBlocking));
+  ok(cudaStreamCreateWithPriority(&d.s_panel, cudaStreamNonBlocking, hi));
+  for (int i = 0; i < 2; ++i) {
+    ok(cudaEventCreateWithFlags(&d.ev_ready[i], cudaEventDisableTiming));
+    ok(cudaEventCreateWithFlags(&d.ev_main[i], cudaEventDisableTiming));
+  }
+  ok(cudaEventCreateWithFlags(&d.ev_misc, cudaEventDisableTiming));
+  ok(cudaEventCreate(&e0));
+  ok(cudaEventCreate(&e1));
+  ok(cudaEventCreate(&e2));
+  ok(cudaMalloc(reinterpret_cast<void**>(&dA), static_cast<size_t>(n) * n * sizeof(double)));
+  ok(cudaMalloc(reinterpret_cast<void**>(&d.S), static_cast<size_t>(d.chunk) * sizeof(double)));
+  ok(cudaMalloc(reinterpret_cast<void**>(&d.Lpack), static_cast<size_t>(d.panel_off[d.nblk]) * sizeof(double)));
+  ok(cudaMalloc(reinterpret_cast<void**>(&d.Linv), static_cast<size_t>(d.nblk) * (nb / 128) * 128 * 128 * sizeof(double)));
+  ok(cudaMalloc(reinterpret_cast<void**>(&d.tmp), static_cast<size_t>(n) * sizeof(double)));
+  ok(cudaMalloc(reinterpret_cast<void**>(&d.d_panel_off), d.panel_off.size() * sizeof(int64_t)));
+  ok(cudaMalloc(reinterpret_cast<void**>(&d.d_panel_h), d.panel_h.size() * sizeof(int)));
+  ok(cudaMalloc(reinterpret_cast<void**>(&db), static_cast<size_t>(n) * sizeof(double)));
+  ok(cudaMalloc(reinterpret_cast<void**>(&dinfo), sizeof(int)));
+  d.info = dinfo;
+  if (rc == 0) {
+    ok(cudaMemcpy(dA, A, static_cast<size_t>(n) * n * sizeof(double), cudaMemcpyHostToDevice));
+    ok(cudaMemcpy(db, b, static_cast<size_t>(n) * sizeof(double), cudaMemcpyHostToDevice));
+    ok(cudaMemcpy(d.d_panel_off, d.panel_off.data(), d.panel_off.size() * sizeof(int64_t), cudaMemcpyHostToDevice));
+    ok(cudaMemcpy(d.d_panel_h, d.panel_h.data(), d.panel_h.size() * sizeof(int), cudaMemcpyHostToDevice));
+    ok(cudaMemset(d.S, 0, static_cast<size_t>(d.chunk) * sizeof(double)));
+    ok(cudaMemset(dinfo, 0, sizeof(int)));
+    ok(cudaMemcpy2D(d.S, d.map.ld * sizeof(double), dA, static_cast<size_t>(n) * sizeof(double),
+                    static_cast<size_t>(n) * sizeof(double), n, cudaMemcpyDeviceToDevice));
+  }
+  if (rc == 0) {
+    cudaEventRecord(e0, d.s_main);
+    if (dense_factor(&d)) rc = 1;
+    cudaEventRecord(e1, d.s_main);
+    if (rc == 0 && dense_solve(&d, db)) rc = 1;
+    cudaEventRecord(e2, d.s_main);
+    ok(cudaStreamSynchronize(d.s_main));
+    ok(cudaStreamSynchronize(d.s_panel));
+    if (rc == 1 && g_create_error.empty()) g_create_error = "b200ba_dense_cholesky_solve: kernel launch failed";
+  }
+  if (rc == 0) {
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    if (factor_ms) *factor_ms = ms;
+    cudaEventElapsedTime(&ms, e1, e2);
+    if (solve_ms) *solve_ms = ms;
+    int info = 0;
+    ok(cudaMemcpy(&info, dinfo, sizeof(int), cudaMemcpyDeviceToHost));
+    ok(cudaMemcpy(x, db, static_cast<size_t>(n) * sizeof(double), cudaMemcpyDeviceToHost));
+    if (rc == 0 && info != 0) {
+      g_create_error = "b200ba_dense_cholesky_solve: the matrix is not positive definite";
+      rc = 4;
+    }
+  }
+  for (double* p : {dA, d.S, d.Lpack, d.Linv, d.tmp, db})
+    if (p) cudaFree(p);
+  if (d.d_panel_off) cudaFree(d.d_panel_off);
+  if (d.d_panel_h) cudaFree(d.d_panel_h);
+  if (dinfo) cudaFree(dinfo);
+  for (int i = 0; i < 2; ++i) {
+    if (d.ev_ready[i]) cudaEventDestroy(d.ev_ready[i]);
+    if (d.ev_main[i]) cudaEventDestroy(d.ev_main[i]);
+  }
+  for (cudaEvent_t e : {d.ev_misc, e0, e1, e2})
+    if (e) cudaEventDestroy(e);
+  if (d.s_main) cudaStreamDestroy(d.s_main);
+  if (d.s_panel) cudaStreamDestroy(d.s_panel);
+  return rc;
+}
+
 // ---- stand-alone Schur solve (known-answer tests) ---------------------------------------------
 int b200ba_schur_solve(int device, int32_t bs, int32_t nb, int32_t nd, const double* D, const double* B,
                        const double* C, const double* b1, const double* b2, double* x) {
@@ -1782,6 +2131,7 @@ int b200ba_comm_init(b200ba_handle* h, const uint8_t id[B200BA_NCCL_UNIQUE_ID_BY
   }
   h->rank = rank;
   h->n_ranks = n_ranks;
+  if (plan_dense(h)) return 1;
   // every rank must derive the same groups of Schur blocks: reduce the centroid sums
   if (h->L.eliminate_points && h->L.nblocks > 0 && !h->grp_sums.empty()) {
     if (reduce_group_sums(h)) return 1;

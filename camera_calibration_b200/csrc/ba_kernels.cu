@@ -1116,9 +1116,9 @@ void launch_compact_columns(int ngroups, int nd, const uint8_t* flags, int* cols
   compact_columns_kernel<<<ngroups, 1024, 0, s>>>(nd, flags, cols, count);
 }
 
-// Wc[(lb * BS + r) * m + j] = sum_k Linv[blk][r][k] * B[(blk * BS + k)][cols[j]]  for the blocks of one group
+// Wc[(lb * BS + r) * ldw + j] = sum_k Linv[blk][r][k] * B[(blk * BS + k)][cols[j]]  for the blocks of one group
 template <int BS>
-__global__ void gather_scale_kernel(int nd, int m, const double* __restrict__ B, const double* __restrict__ Linv,
+__global__ void gather_scale_kernel(int nd, int m, int ldw, const double* __restrict__ B, const double* __restrict__ Linv,
                                     const int* __restrict__ blocks, const int* __restrict__ cols,
                                     double* __restrict__ Wc) {
   constexpr int DSZ = BS * (BS + 1) / 2;
@@ -1136,17 +1136,17 @@ __global__ void gather_scale_kernel(int nd, int m, const double* __restrict__ B,
     double t = 0;
 #pragma unroll
     for (int q = 0; q <= i; ++q) t = fma(Li[(i * (i + 1)) / 2 + q], b[q], t);
-    Wc[(static_cast<int64_t>(lb) * BS + i) * m + j] = t;
+    Wc[(static_cast<int64_t>(lb) * BS + i) * ldw + j] = t;
   }
 }
-void launch_gather_scale(int bs, int nblocks_in_group, int nd, int m, const double* B, const double* Linv,
+void launch_gather_scale(int bs, int nblocks_in_group, int nd, int m, int ldw, const double* B, const double* Linv,
                          const int* blocks, const int* cols, double* Wc, cudaStream_t s) {
   if (nblocks_in_group == 0 || m == 0) return;
   dim3 grid((m + 255) / 256, nblocks_in_group);
   if (bs == 3)
-    gather_scale_kernel<3><<<grid, 256, 0, s>>>(nd, m, B, Linv, blocks, cols, Wc);
+    gather_scale_kernel<3><<<grid, 256, 0, s>>>(nd, m, ldw, B, Linv, blocks, cols, Wc);
   else
-    gather_scale_kernel<6><<<grid, 256, 0, s>>>(nd, m, B, Linv, blocks, cols, Wc);
+    gather_scale_kernel<6><<<grid, 256, 0, s>>>(nd, m, ldw, B, Linv, blocks, cols, Wc);
 }
 
 // S[cols[j] * nd + cols[i]] -= P[j * m + i] for i >= j (column-major lower triangles on both sides)

@@ -1,5 +1,7 @@
 // ba_kernels.h -- launchers of the kernels in ba_kernels.cu (internal to libb200ba.so).
 #pragma once
+#include <vector>
+
 #include "ba_common.h"
 
 namespace b200ba {
@@ -30,7 +32,7 @@ void launch_schur_backsub(int bs, int n_blocks, const double* Linv, const double
 void launch_group_support(int bs, int nblocks, int nd, const double* B, const int* group_of_block, uint8_t* flags,
                           cudaStream_t s);
 void launch_compact_columns(int ngroups, int nd, const uint8_t* flags, int* cols, int* count, cudaStream_t s);
-void launch_gather_scale(int bs, int nblocks_in_group, int nd, int m, const double* B, const double* Linv,
+void launch_gather_scale(int bs, int nblocks_in_group, int nd, int m, int ldw, const double* B, const double* Linv,
                          const int* blocks, const int* cols, double* Wc, cudaStream_t s);
 void launch_scatter_sub(int nd, int m, const int* cols, const double* P, double* S, cudaStream_t s);
 void launch_block_solve_t(int bs, int n_blocks, const double* Linv, const double* v, double* u, cudaStream_t s);
@@ -98,5 +100,33 @@ inline bool gemm_operand_aligned(const double* p, int64_t ld) {
 int launch_dgemm_nt(const GemmArgs& g, bool lower, bool scatter, cudaStream_t s);
 // Cholesky of a 128 x 128 (live size n) column-major diagonal tile in place + Linv [128 x 128, ld 128].
 int launch_potrf_tile(double* A, int64_t lda, int n, double* Linv, int* info, cudaStream_t s);
+
+void launch_add_diagonal_map(int n, double* S, const DenseMap& map, double lambda, cudaStream_t s);
+
+// Context of the dense factorisation / solve (ba_dense.cu). The caller owns the buffers.
+struct DenseCtx {
+  int n = 0, NB = 256, nblk = 0, ntiles = 0;
+  int rank = 0, ranks = 1;
+  DenseMap map{};
+  int64_t chunk = 0;                 // doubles per rank of the S allocation (reduce-scatter chunk)
+  std::vector<int64_t> panel_off;    // [nblk + 1] offsets of the packed panels in Lpack
+  std::vector<int> panel_h;          // [nblk] leading dimension (even) of each packed panel
+  double* S = nullptr;               // ranks * chunk doubles
+  double* Lpack = nullptr;           // panel_off[nblk] doubles: the factor
+  double* Linv = nullptr;            // [nblk * NB / 128][128 * 128] inverses of the diagonal tiles
+  double* tmp = nullptr;             // [n] intermediate of the triangular solves
+  int64_t* d_panel_off = nullptr;    // device copies for the backward step
+  int* d_panel_h = nullptr;
+  int* info = nullptr;               // device flag: non-positive pivot
+  cudaStream_t s_main = nullptr, s_panel = nullptr;
+  cudaEvent_t ev_ready[2] = {nullptr, nullptr}, ev_main[2] = {nullptr, nullptr}, ev_misc = nullptr;
+  // broadcast of `count` doubles from rank `root` on stream s (multi-GPU only)
+  int (*bcast)(double* buf, size_t count, int root, cudaStream_t s, void* user) = nullptr;
+  void* user = nullptr;
+  bool bcast_linv = true;
+};
+int dense_plan(DenseCtx* d, int n, int nb, int rank, int ranks);
+int dense_factor(DenseCtx* d);
+int dense_solve(DenseCtx* d, double* b);
 
 }  // namespace b200ba

@@ -215,6 +215,14 @@ B200BA_API int b200ba_schur_solve(int device, int32_t block_size, int32_t n_bloc
                        const double* D, const double* B, const double* C, const double* b1,
                        const double* b2, double* x);
 
+/* Stand-alone dense SPD solve A x = b on the in-tree kernels of the dense phase (blocked Cholesky with
+ * FP64 tensor-core trailing updates, packed triangular solves): what replaces
+ * `schur_M.selfadjointView<Upper>().ldlt().solve()` (libvis lm_optimizer.h:1361) inside b200ba_optimize.
+ * A [n*n] symmetric, host; block_width a multiple of 128; the *_ms outputs (nullable) are device times.
+ * Returns 4 if A is not positive definite. Tests / profiling. */
+B200BA_API int b200ba_dense_cholesky_solve(int device, int32_t n, int32_t block_width, const double* A,
+                                           const double* b, double* x, double* factor_ms, double* solve_ms);
+
 /* CameraModel::ProjectWithInitialEstimate / Unproject for n points, on the device.
  * pixels is in/out (initial estimate / result); ok[i] = 1 on success. */
 B200BA_API int b200ba_project(int device, const b200ba_camera* cam, const double* intrinsics, int64_t n,

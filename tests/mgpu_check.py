@@ -20,10 +20,10 @@ def main():
     if os.environ.get("MGPU_FORCE_GROUPED"):
         os.environ["B200BA_GROUPED"] = "1"
         os.environ["B200BA_GROUP_BLOCKS"] = "7"
-    # third sweep: the column-block Cholesky over the ranks (panel broadcasts), tiny panels
-    if os.environ.get("MGPU_DIST_CHOL"):
-        os.environ["B200BA_DIST_CHOL"] = "1"
-        os.environ["B200BA_CHOL_NB"] = "64"
+    # third sweep: narrow column blocks, so that the block-cyclic Cholesky (panel broadcasts, look-ahead)
+    # spans many panels on the small problems
+    if os.environ.get("MGPU_SMALL_PANELS"):
+        os.environ["B200BA_DENSE_NB"] = "128"
     for cfg, kw in ((2, dict(n_imagesets=12, lattice=(12, 10), image_size=(410, 290))),
                     (4, dict(n_imagesets=10, lattice=(10, 8), image_size=(410, 290))),
                     (1, dict(n_imagesets=8, lattice=(10, 10)))):

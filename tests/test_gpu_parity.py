@@ -314,21 +314,66 @@ def test_multi_gpu_matches_single_gpu():
     cmd[cmd.index("29533")] = "29534"
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, env=env)
     assert r.returncode == 0 and "MGPU_OK" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
-    env = dict(os.environ, MGPU_DIST_CHOL="1")
+    env = dict(os.environ, MGPU_SMALL_PANELS="1")
     cmd[cmd.index("29534")] = "29535"
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, env=env)
     assert r.returncode == 0 and "MGPU_OK" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
 
 
-def test_column_block_cholesky_matches_potrf(monkeypatch):
-    """B200BA_DIST_CHOL=1 runs the multi-rank factorisation (column blocks, here all owned by the
-    one rank) instead of cusolver's potrf: same LM trajectory and state."""
+@pytest.mark.parametrize("n,nb", [(100, 128), (128, 128), (333, 128), (700, 256), (1031, 256), (1500, 384)])
+def test_dense_cholesky_solve_matches_numpy(n, nb):
+    """Blocked Cholesky (potrf tile + explicit tile inverse + DMMA panel solve / trailing update, with
+    look-ahead) and the packed triangular solves against numpy on random SPD systems whose sizes
+    exercise partial tiles, partial panels and odd leading dimensions."""
+    rng = np.random.default_rng(n)
+    M = rng.standard_normal((n, n + 20))
+    A = M @ M.T + 0.5 * np.eye(n)
+    b = rng.standard_normal(n)
+    x, fm, sm = api.dense_cholesky_solve(A, b, nb)
+    xr = np.linalg.solve(A, b)
+    assert np.abs(x - xr).max() <= 1e-9 * max(1.0, np.abs(xr).max()), np.abs(x - xr).max()
+
+
+def test_dense_cholesky_solve_reports_indefinite():
+    A = np.eye(200)
+    A[150, 150] = -1.0
+    with pytest.raises(api.B200BAError):
+        api.dense_cholesky_solve(A, np.ones(200), 128)
+
+
+def test_own_dense_kernels_match_library_path(monkeypatch):
+    """The in-tree dense phase (DMMA contraction with scatter epilogue, blocked Cholesky on packed
+    panels with explicit tile inverses, packed triangular solves; ba_dense.cu) against the cuBLAS /
+    cuSOLVER path (B200BA_DENSE=lib): same LM trajectory and state. Small block width so that the
+    problem spans several panels, for both the structured and the dense contraction."""
     sp = synthetic.make_problem(2, n_imagesets=12, lattice=(12, 10), image_size=(410, 290))
-    opt = cabi.default_options(max_iteration_count=5)
+    for grouped in ("1", "0"):
+        opt = cabi.default_options(max_iteration_count=5)
+        out = []
+        for mode, nb in (("lib", "256"), ("own", "128"), ("own", "256")):
+            monkeypatch.setenv("B200BA_DENSE", mode)
+            monkeypatch.setenv("B200BA_DENSE_NB", nb)
+            monkeypatch.setenv("B200BA_GROUPED", grouped)
+            monkeypatch.setenv("B200BA_GROUP_BLOCKS", "7")
+            with api.BundleAdjuster(sp.problem) as adj:
+                st = sp.init_state.copy()
+                rep = adj.optimize_host(st, opt)
+                out.append((rep.trace(), st))
+        (c0, l0, a0), s0 = out[0]
+        for (c1, l1, a1), s1 in out[1:]:
+            assert a0 == a1 and np.allclose(c0, c1, rtol=1e-10)
+            assert np.abs(s0.points - s1.points).max() < 1e-9
+            assert max(np.abs(x - y).max() for x, y in zip(s0.intrinsics, s1.intrinsics)) < 1e-9
+
+
+def test_own_dense_kernels_pose_elimination(monkeypatch):
+    """6x6 pose blocks eliminated (the product's default order): dense part = [rig | points | intrinsics]."""
+    sp = synthetic.make_problem(4, n_imagesets=10, lattice=(10, 8), image_size=(410, 290))
+    opt = cabi.default_options(max_iteration_count=4, eliminate_points=0)
     out = []
-    for mode in ("0", "1"):
-        monkeypatch.setenv("B200BA_DIST_CHOL", mode)
-        monkeypatch.setenv("B200BA_CHOL_NB", "96")
+    for mode in ("lib", "own"):
+        monkeypatch.setenv("B200BA_DENSE", mode)
+        monkeypatch.setenv("B200BA_DENSE_NB", "128")
         with api.BundleAdjuster(sp.problem) as adj:
             st = sp.init_state.copy()
             rep = adj.optimize_host(st, opt)
@@ -337,7 +382,6 @@ def test_column_block_cholesky_matches_potrf(monkeypatch):
     (c1, l1, a1), s1 = out[1]
     assert a0 == a1 and np.allclose(c0, c1, rtol=1e-10)
     assert np.abs(s0.points - s1.points).max() < 1e-9
-    assert max(np.abs(x - y).max() for x, y in zip(s0.intrinsics, s1.intrinsics)) < 1e-9
 
 
 def test_straggler_pass_equals_main_pass(oracle_lib):
