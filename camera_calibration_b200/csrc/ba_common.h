@@ -81,6 +81,14 @@ struct ObsOut {
   double* residual;    // [2 * n_obs] SoA: rx[n_obs], ry[n_obs]
   double* cost;        // [n_obs], -1 = invalid residual
   double* jac;         // [2 * n_jcols][n_obs] SoA: row-x of column c at (2c) * n_obs, row-y at (2c+1) * n_obs
+                       //   (NULL in compact mode, except while b200ba_get_jacobians expands it)
+  // Compact mode (all cameras central-generic): instead of the 2 x (9 + 6 + 32) Jacobian entries the
+  // kernel stores the 14 numbers they are all built from -- P = d pixel / d local_point (2x3), the two
+  // rows of Mn = -(A^T A)^-1 A^T / |sum w G| (2x3) and the fractions (fu, fv) of the B-spline support;
+  // consumers rebuild a column as  point / pose / rig: chain rule of P with the (L2-resident) poses,
+  // intrinsics: w_k(fu, fv) * Mn [t1 t2]_k with the tangent frames. 116 B instead of 656 B per observation.
+  double* cjac;        // [14][n_obs] SoA: P00 P01 P02 P10 P11 P12 | Mn00 Mn01 Mn02 Mn10 Mn11 Mn12 | fu fv
+  int compact;
   int32_t* cell;       // [n_obs] top-left control point x0 + y0 * gw of the 4x4 support (generic models)
   uint8_t* has_jac;    // [n_obs]
   uint16_t* evals;     // [n_obs] spline evaluations spent by the projection LM (diagnostics; may be NULL)

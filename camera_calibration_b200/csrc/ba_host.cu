@@ -163,6 +163,7 @@ struct b200ba_handle {
   bool use_grouped = false;
   std::vector<double> grp_sums;           // [sx | sy | count] per Schur block (see build_groups)
   int force_grouped = -1;                 // B200BA_GROUPED=0|1 overrides the cost model
+  bool compact_j = true;                  // B200BA_COMPACT_J=0: expanded Jacobian buffer also for central-generic cameras
 
   // multi-GPU
   void* comm = nullptr;
@@ -513,7 +514,15 @@ int make_layout(b200ba_handle* h, const b200ba_options* opt) {
   const int64_t n = h->n_obs;
   if (dev_alloc(h, &h->out.residual, 2 * n)) return 1;
   if (dev_alloc(h, &h->out.cost, n)) return 1;
-  if (dev_alloc(h, &h->out.jac, 2 * static_cast<size_t>(L.n_jcols) * n)) return 1;
+  // compact Jacobian records when every camera is central-generic (B200BA_COMPACT_J=0 keeps the expanded buffer)
+  h->out.compact = (h->uniform_model == B200BA_MODEL_CENTRAL_GENERIC && h->compact_j) ? 1 : 0;
+  if (h->out.compact) {
+    if (h->out.jac) cudaFree(h->out.jac);
+    h->out.jac = nullptr;
+    if (dev_alloc(h, &h->out.cjac, 14 * static_cast<size_t>(n))) return 1;
+  } else {
+    if (dev_alloc(h, &h->out.jac, 2 * static_cast<size_t>(L.n_jcols) * n)) return 1;
+  }
   if (dev_alloc(h, &h->out.cell, n)) return 1;
   if (dev_alloc(h, &h->out.has_jac, n)) return 1;
   if (dev_alloc(h, &h->out.evals, n)) return 1;
@@ -521,6 +530,8 @@ int make_layout(b200ba_handle* h, const b200ba_options* opt) {
   if (dev_alloc(h, &h->out_trial.residual, 2 * n)) return 1;
   if (dev_alloc(h, &h->out_trial.cost, n)) return 1;
   h->out_trial.jac = nullptr;
+  h->out_trial.cjac = nullptr;
+  h->out_trial.compact = 0;
   h->out_trial.cell = nullptr;
   h->out_trial.has_jac = nullptr;
 
@@ -640,14 +651,14 @@ int build_system(b200ba_handle* h, double huber, double* cost, double* n_valid) 
   {
     ScopedPhase ph(h, PH_ACC);
     CUDA_TRY(h, cudaMemsetAsync(h->sys.base, 0, h->sys.total * sizeof(double), h->stream));
-    launch_accumulate_scatter(h->pb, h->L, h->out, h->sys, huber, h->stream);
+    launch_accumulate_scatter(h->pb, h->L, h->st[h->cur], h->out, h->sys, huber, h->stream);
     if (!h->L.localize_only || h->L.rig_in_state) {
-      launch_accumulate_cells(h->pb, h->L, h->out, h->sys, huber, h->stream);
+      launch_accumulate_cells(h->pb, h->L, h->st[h->cur], h->out, h->sys, huber, h->stream);
       h->timings.kernel_launches += 1;
     }
     // join, then fold in the stragglers that succeeded after all
     CUDA_TRY(h, cudaStreamWaitEvent(h->stream, h->straggler_done, 0));
-    launch_accumulate_list(h->pb, h->L, h->out, h->sys, huber, h->d_straggler_list, h->d_straggler_count, h->stream);
+    launch_accumulate_list(h->pb, h->L, h->st[h->cur], h->out, h->sys, huber, h->d_straggler_list, h->d_straggler_count, h->stream);
     h->timings.kernel_launches += 2;
     launch_cost_reduce(h->n_obs, h->out.cost, nullptr, h->out.residual, h->d_partial, h->sys.scalars, h->stream);
     // trace(H) of this rank's partial system, for the lambda initialisation (lm_optimizer.h:766-781)
@@ -1095,7 +1106,7 @@ void free_handle_buffers(b200ba_handle* h) {
   F(h->d_last_projection);
   F(h->snap.points); F(h->snap.rig_tr_global); F(h->snap.camera_tr_rig); F(h->snap.intrinsics); F(h->d_snap_lp);
   h->have_snapshot = false;
-  F(h->out.residual); F(h->out.cost); F(h->out.jac); F(h->out.cell); F(h->out.has_jac); F(h->out.evals);
+  F(h->out.residual); F(h->out.cost); F(h->out.jac); F(h->out.cjac); F(h->out.cell); F(h->out.has_jac); F(h->out.evals);
   F(h->out_trial.residual); F(h->out_trial.cost);
   F(h->sys.base); F(h->d_W); F(h->d_S); F(h->d_Linv); F(h->d_v); F(h->d_y); F(h->d_x); F(h->d_potrf_work);
   F(h->d_info); F(h->d_fail); F(h->d_straggler_list); F(h->d_straggler_count); F(h->d_perm); F(h->d_lp_stage);
@@ -1297,6 +1308,7 @@ int b200ba_create(const b200ba_problem* p, int device, b200ba_handle** out) {
     TRYC(cuda_ok(cudaStreamCreateWithPriority(&h->panel_stream, cudaStreamNonBlocking, hi), "cudaStreamCreate"));
   }
   if (const char* e = getenv("B200BA_GROUPED")) h->force_grouped = atoi(e);
+  if (const char* e = getenv("B200BA_COMPACT_J")) h->compact_j = atoi(e) != 0;
   if (const char* e = getenv("B200BA_DIST_CHOL")) h->chol_mode = atoi(e);
   if (const char* e = getenv("B200BA_CHOL_NB")) h->chol_nb = std::max(32, atoi(e));
   h->pb.n_obs = n;
@@ -1625,7 +1637,17 @@ int b200ba_get_jacobians(b200ba_handle* h, double* j_point, double* j_pose, doub
   std::vector<double> jac(2 * static_cast<size_t>(L.n_jcols) * n);
   std::vector<int32_t> cell(n);
   std::vector<uint8_t> has(n);
-  CUDA_TRY(h, cudaMemcpy(jac.data(), h->out.jac, jac.size() * sizeof(double), cudaMemcpyDeviceToHost));
+  if (h->out.compact) {
+    // rebuild the expanded buffer from the compact records (state of the evaluation = current state)
+    double* tmp = nullptr;
+    CUDA_TRY(h, cudaMalloc(reinterpret_cast<void**>(&tmp), std::max<size_t>(1, jac.size()) * sizeof(double)));
+    launch_expand_jacobian(h->pb, L, h->st[h->cur], h->out, tmp, h->stream);
+    cudaError_t e = cudaStreamSynchronize(h->stream);
+    if (e == cudaSuccess) e = cudaMemcpy(jac.data(), tmp, jac.size() * sizeof(double), cudaMemcpyDeviceToHost);
+    cudaFree(tmp);
+    CUDA_TRY(h, e);
+  } else
+    CUDA_TRY(h, cudaMemcpy(jac.data(), h->out.jac, jac.size() * sizeof(double), cudaMemcpyDeviceToHost));
   CUDA_TRY(h, cudaMemcpy(cell.data(), h->out.cell, n * sizeof(int32_t), cudaMemcpyDeviceToHost));
   CUDA_TRY(h, cudaMemcpy(has.data(), h->out.has_jac, n, cudaMemcpyDeviceToHost));
   std::vector<uint32_t> cams(n);

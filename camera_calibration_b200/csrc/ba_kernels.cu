@@ -150,7 +150,136 @@ constexpr uint8_t kJacNone = 0, kJacValid = 1, kJacPending = 2, kJacLate = 3;
 static int g_main_eval_budget = 16;
 void set_main_eval_budget(int b) { g_main_eval_budget = b < 1 ? 1 : b; }
 
-template <int MODEL, bool JAC, bool STRAGGLER>
+// ---- chain rule to pose / rig / point (joint_optimization.cc:378-438) --------------------------
+// For the left update q <- (1, delta) q: d(R(q) v)/d delta = -2 [R v]_x. R is the COMPOSED rotation
+// image_tr_global; with a single camera the reference differentiates with it and an identity
+// translation block (joint_optimization.cc:392-397), reproduced as is.
+__device__ __forceinline__ void chain_rule(const Layout& L, const StateDev& st, int iset, int cam, const d3& point,
+                                           const double* R, const d3& rp, const double P[2][3], double jp[2][3],
+                                           double jo[2][6], double jr[2][6]) {
+  if (L.rig_in_state) {
+    const double* ca = st.camera_tr_rig + 7 * cam;
+    const double* rb = st.rig_tr_global + 7 * static_cast<int64_t>(iset);
+    double Rc[9], Rr[9];
+    qrot(q4{ca[0], ca[1], ca[2], ca[3]}, Rc);
+    qrot(q4{rb[0], rb[1], rb[2], rb[3]}, Rr);
+    const d3 rrp = rot_apply(Rr, point);
+    const d3 crp = rot_apply(Rc, rrp + mk3(rb[4], rb[5], rb[6]));
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      // PRc = P Rc
+      const double a0 = P[r][0] * Rc[0] + P[r][1] * Rc[3] + P[r][2] * Rc[6];
+      const double a1 = P[r][0] * Rc[1] + P[r][1] * Rc[4] + P[r][2] * Rc[7];
+      const double a2 = P[r][0] * Rc[2] + P[r][1] * Rc[5] + P[r][2] * Rc[8];
+      jo[r][0] = -2 * (a1 * rrp.z - a2 * rrp.y);
+      jo[r][1] = -2 * (-a0 * rrp.z + a2 * rrp.x);
+      jo[r][2] = -2 * (a0 * rrp.y - a1 * rrp.x);
+      jo[r][3] = a0;
+      jo[r][4] = a1;
+      jo[r][5] = a2;
+      jr[r][0] = -2 * (P[r][1] * crp.z - P[r][2] * crp.y);
+      jr[r][1] = -2 * (-P[r][0] * crp.z + P[r][2] * crp.x);
+      jr[r][2] = -2 * (P[r][0] * crp.y - P[r][1] * crp.x);
+      jr[r][3] = P[r][0];
+      jr[r][4] = P[r][1];
+      jr[r][5] = P[r][2];
+      jp[r][0] = a0 * Rr[0] + a1 * Rr[3] + a2 * Rr[6];
+      jp[r][1] = a0 * Rr[1] + a1 * Rr[4] + a2 * Rr[7];
+      jp[r][2] = a0 * Rr[2] + a1 * Rr[5] + a2 * Rr[8];
+    }
+  } else {
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      jo[r][0] = -2 * (P[r][1] * rp.z - P[r][2] * rp.y);
+      jo[r][1] = -2 * (-P[r][0] * rp.z + P[r][2] * rp.x);
+      jo[r][2] = -2 * (P[r][0] * rp.y - P[r][1] * rp.x);
+      jo[r][3] = P[r][0];
+      jo[r][4] = P[r][1];
+      jo[r][5] = P[r][2];
+      jp[r][0] = P[r][0] * R[0] + P[r][1] * R[3] + P[r][2] * R[6];
+      jp[r][1] = P[r][0] * R[1] + P[r][1] * R[4] + P[r][2] * R[7];
+      jp[r][2] = P[r][0] * R[2] + P[r][1] * R[5] + P[r][2] * R[8];
+#pragma unroll
+      for (int j = 0; j < 6; ++j) jr[r][j] = 0.0;
+    }
+  }
+}
+
+// Compact mode: P of observation o and the [point | pose | rig] Jacobian blocks rebuilt from it.
+__device__ __forceinline__ void compact_small_blocks(const ProblemDev& pb, const Layout& L, const StateDev& st,
+                                                     const ObsOut& out, int64_t o, double jp[2][3], double jo[2][6],
+                                                     double jr[2][6]) {
+  const int64_t n = pb.n_obs;
+  const int iset = static_cast<int>(pb.obs_imageset[o]);
+  const int cam = static_cast<int>(pb.obs_camera[o]);
+  const int pidx = static_cast<int>(pb.obs_point[o]);
+  double P[2][3];
+#pragma unroll
+  for (int q = 0; q < 6; ++q) P[q / 3][q % 3] = out.cjac[static_cast<int64_t>(q) * n + o];
+  const double* T = st.image_tr_global + 12 * (static_cast<int64_t>(iset) * L.n_cameras + cam);
+  double R[9];
+#pragma unroll
+  for (int i = 0; i < 9; ++i) R[i] = __ldg(T + i);
+  const d3 point = ld3(st.points + 3 * static_cast<int64_t>(pidx));
+  const d3 rp = rot_apply(R, point);
+  chain_rule(L, st, iset, cam, point, R, rp, P, jp, jo, jr);
+}
+
+// one cubic B-spline basis weight (bspline_basis() for a single index)
+__device__ __forceinline__ double bspline_w1(double u, int idx) {
+  constexpr double k6 = 1.0 / 6.0;
+  const double u2 = u * u, u3 = u2 * u, omu = 1.0 - u;
+  return idx == 0 ? omu * omu * omu * k6
+                  : (idx == 1 ? (3.0 * u3 - 6.0 * u2 + 4.0) * k6 : (idx == 2 ? (-3.0 * u3 + 3.0 * u2 + 3.0 * u + 1.0) * k6 : u3 * k6));
+}
+
+// Entry (rows x, y) of STORAGE column `col` of observation o: read from the expanded buffer, or rebuilt
+// from the compact record (central-generic cameras only).
+__device__ __forceinline__ void load_jcol(const ProblemDev& pb, const Layout& L, const StateDev& st, const ObsOut& out,
+                                          int64_t o, int col, double& jx, double& jy) {
+  const int64_t n = pb.n_obs;
+  if (!out.compact) {
+    jx = out.jac[(2 * static_cast<int64_t>(col)) * n + o];
+    jy = out.jac[(2 * static_cast<int64_t>(col) + 1) * n + o];
+    return;
+  }
+  if (col >= L.jc_intr) {
+    const int k = col - L.jc_intr, cp = k >> 1, dsel = k & 1, xx = cp & 3, yy = cp >> 2;
+    const CamDev& c = pb.cams[pb.obs_camera[o]];
+    const double fu = out.cjac[12 * n + o], fv = out.cjac[13 * n + o];
+    const double wk = bspline_w1(fu, xx) * bspline_w1(fv, yy);
+    const double* tan = st.tangents + c.tan_off + 6 * (static_cast<int64_t>(out.cell[o]) + xx + static_cast<int64_t>(yy) * c.gw) + 3 * dsel;
+    const d3 t = ld3(tan);
+    const d3 m0 = mk3(out.cjac[6 * n + o], out.cjac[7 * n + o], out.cjac[8 * n + o]);
+    const d3 m1 = mk3(out.cjac[9 * n + o], out.cjac[10 * n + o], out.cjac[11 * n + o]);
+    jx = wk * dot3(m0, t);
+    jy = wk * dot3(m1, t);
+    return;
+  }
+  double jp[2][3], jo[2][6], jr[2][6];
+  compact_small_blocks(pb, L, st, out, o, jp, jo, jr);
+  // register arrays are indexed with compile-time constants only
+  jx = jy = 0.0;
+#pragma unroll
+  for (int j = 0; j < 3; ++j)
+    if (col == L.jc_point + j) {
+      jx = jp[0][j];
+      jy = jp[1][j];
+    }
+#pragma unroll
+  for (int j = 0; j < 6; ++j) {
+    if (col == L.jc_pose + j) {
+      jx = jo[0][j];
+      jy = jo[1][j];
+    }
+    if (L.rig_in_state && col == L.jc_rig + j) {
+      jx = jr[0][j];
+      jy = jr[1][j];
+    }
+  }
+}
+
+template <int MODEL, bool JAC, bool STRAGGLER, bool COMPACT>
 __device__ __forceinline__ void process_observation(const ProblemDev& pb, const Layout& L, const StateDev& st,
                                                     double2* __restrict__ last_projection, const ObsOut& out,
                                                     double huber, uint32_t* __restrict__ straggler_list,
@@ -278,6 +407,29 @@ __device__ __forceinline__ void process_observation(const ProblemDev& pb, const 
     double fu, fv;
     locate(c, px, py, x0, y0, fu, fv);
     cell = x0 + y0 * c.gw;
+    if (COMPACT) {
+      // d unproj / d G_k = w_k / |s| (I - u u^T) and M u = 0 (the columns of A are orthogonal to u), so
+      // d pixel / d theta_k = w_k * Mn [t1 t2]_k with Mn = -M / |s|: the consumers rebuild the 32 columns
+      const int64_t n = pb.n_obs;
+      const double s = -ce.inv_n;
+      out.cjac[0 * n + o] = P[0][0];
+      out.cjac[1 * n + o] = P[0][1];
+      out.cjac[2 * n + o] = P[0][2];
+      out.cjac[3 * n + o] = P[1][0];
+      out.cjac[4 * n + o] = P[1][1];
+      out.cjac[5 * n + o] = P[1][2];
+      out.cjac[6 * n + o] = s * M0.x;
+      out.cjac[7 * n + o] = s * M0.y;
+      out.cjac[8 * n + o] = s * M0.z;
+      out.cjac[9 * n + o] = s * M1.x;
+      out.cjac[10 * n + o] = s * M1.y;
+      out.cjac[11 * n + o] = s * M1.z;
+      out.cjac[12 * n + o] = fu;
+      out.cjac[13 * n + o] = fv;
+      out.cell[o] = cell;
+      out.has_jac[o] = STRAGGLER ? kJacLate : kJacValid;
+      return;
+    }
     if (!L.localize_only) {
       double wx[4], dwx[4], wy[4], dwy[4];
       bspline_basis(fu, wx, dwx);
@@ -367,62 +519,26 @@ __device__ __forceinline__ void process_observation(const ProblemDev& pb, const 
   out.has_jac[o] = STRAGGLER ? kJacLate : kJacValid;
 
   // ---- chain rule to pose / rig / point (joint_optimization.cc:378-438) ----------------------
-  // For the left update q <- (1, delta) q: d(R(q) v)/d delta = -2 [R v]_x.
-  if (L.rig_in_state) {
-    const double* ca = st.camera_tr_rig + 7 * cam;
-    const double* rb = st.rig_tr_global + 7 * static_cast<int64_t>(iset);
-    double Rc[9], Rr[9];
-    qrot(q4{ca[0], ca[1], ca[2], ca[3]}, Rc);
-    qrot(q4{rb[0], rb[1], rb[2], rb[3]}, Rr);
-    const d3 rrp = rot_apply(Rr, point);
-    const d3 crp = rot_apply(Rc, rrp + mk3(rb[4], rb[5], rb[6]));
+  double jp[2][3], jo[2][6], jr[2][6];
+  chain_rule(L, st, iset, cam, point, R, rp, P, jp, jo, jr);
+  const int64_t stride = 2 * pb.n_obs;
 #pragma unroll
-    for (int r = 0; r < 2; ++r) {
-      // PRc = P Rc
-      const double a0 = P[r][0] * Rc[0] + P[r][1] * Rc[3] + P[r][2] * Rc[6];
-      const double a1 = P[r][0] * Rc[1] + P[r][1] * Rc[4] + P[r][2] * Rc[7];
-      const double a2 = P[r][0] * Rc[2] + P[r][1] * Rc[5] + P[r][2] * Rc[8];
-      double* dst = out.jac + (2 * static_cast<int64_t>(L.jc_pose) + r) * pb.n_obs + o;
-      const int64_t stride = 2 * pb.n_obs;
-      dst[0 * stride] = -2 * (a1 * rrp.z - a2 * rrp.y);
-      dst[1 * stride] = -2 * (-a0 * rrp.z + a2 * rrp.x);
-      dst[2 * stride] = -2 * (a0 * rrp.y - a1 * rrp.x);
-      dst[3 * stride] = a0;
-      dst[4 * stride] = a1;
-      dst[5 * stride] = a2;
+  for (int r = 0; r < 2; ++r) {
+    double* dst = out.jac + (2 * static_cast<int64_t>(L.jc_pose) + r) * pb.n_obs + o;
+#pragma unroll
+    for (int j = 0; j < 6; ++j) dst[j * stride] = jo[r][j];
+    double* dp = out.jac + (2 * static_cast<int64_t>(L.jc_point) + r) * pb.n_obs + o;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) dp[j * stride] = jp[r][j];
+    if (L.rig_in_state) {
       double* dr = out.jac + (2 * static_cast<int64_t>(L.jc_rig) + r) * pb.n_obs + o;
-      dr[0 * stride] = -2 * (P[r][1] * crp.z - P[r][2] * crp.y);
-      dr[1 * stride] = -2 * (-P[r][0] * crp.z + P[r][2] * crp.x);
-      dr[2 * stride] = -2 * (P[r][0] * crp.y - P[r][1] * crp.x);
-      dr[3 * stride] = P[r][0];
-      dr[4 * stride] = P[r][1];
-      dr[5 * stride] = P[r][2];
-      double* dp = out.jac + (2 * static_cast<int64_t>(L.jc_point) + r) * pb.n_obs + o;
-      dp[0 * stride] = a0 * Rr[0] + a1 * Rr[3] + a2 * Rr[6];
-      dp[1 * stride] = a0 * Rr[1] + a1 * Rr[4] + a2 * Rr[7];
-      dp[2 * stride] = a0 * Rr[2] + a1 * Rr[5] + a2 * Rr[8];
-    }
-  } else {
-    // single camera: composed rotation, identity translation block (joint_optimization.cc:392-397)
 #pragma unroll
-    for (int r = 0; r < 2; ++r) {
-      const int64_t stride = 2 * pb.n_obs;
-      double* dst = out.jac + (2 * static_cast<int64_t>(L.jc_pose) + r) * pb.n_obs + o;
-      dst[0 * stride] = -2 * (P[r][1] * rp.z - P[r][2] * rp.y);
-      dst[1 * stride] = -2 * (-P[r][0] * rp.z + P[r][2] * rp.x);
-      dst[2 * stride] = -2 * (P[r][0] * rp.y - P[r][1] * rp.x);
-      dst[3 * stride] = P[r][0];
-      dst[4 * stride] = P[r][1];
-      dst[5 * stride] = P[r][2];
-      double* dp = out.jac + (2 * static_cast<int64_t>(L.jc_point) + r) * pb.n_obs + o;
-      dp[0 * stride] = P[r][0] * R[0] + P[r][1] * R[3] + P[r][2] * R[6];
-      dp[1 * stride] = P[r][0] * R[1] + P[r][1] * R[4] + P[r][2] * R[7];
-      dp[2 * stride] = P[r][0] * R[2] + P[r][1] * R[5] + P[r][2] * R[8];
+      for (int j = 0; j < 6; ++j) dr[j * stride] = jr[r][j];
     }
   }
 }
 
-template <int MODEL, bool JAC, int MINB, bool STRAGGLER>
+template <int MODEL, bool JAC, int MINB, bool STRAGGLER, bool COMPACT>
 __global__ void __launch_bounds__(128, MINB)
     residual_jacobian_kernel(ProblemDev pb, Layout L, StateDev st, double2* __restrict__ last_projection,
                              ObsOut out, double huber, uint32_t* __restrict__ straggler_list,
@@ -430,7 +546,7 @@ __global__ void __launch_bounds__(128, MINB)
   if (!STRAGGLER) {
     const int64_t o = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
     if (o >= pb.n_obs) return;
-    process_observation<MODEL, JAC, false>(pb, L, st, last_projection, out, huber, straggler_list, straggler_count, o, 0,
+    process_observation<MODEL, JAC, false, COMPACT>(pb, L, st, last_projection, out, huber, straggler_list, straggler_count, o, 0,
                                            main_budget);
   } else {
     // two lanes per listed observation; the loop bound is warp-uniform so that the pair shuffle
@@ -446,7 +562,7 @@ __global__ void __launch_bounds__(128, MINB)
         pair = count - 1;
         role = 2;  // muted lane: computes, never writes
       }
-      process_observation<MODEL, JAC, true>(pb, L, st, last_projection, out, huber, straggler_list, straggler_count,
+      process_observation<MODEL, JAC, true, COMPACT>(pb, L, st, last_projection, out, huber, straggler_list, straggler_count,
                                             straggler_list[pair], role, main_budget);
     }
   }
@@ -496,8 +612,12 @@ static void launch_rj_model(const ProblemDev& pb, const Layout& L, const StateDe
                             cudaEvent_t main_done) {
   const int threads = jac_threads();
   const unsigned blocks = static_cast<unsigned>((pb.n_obs + threads - 1) / threads);
-  residual_jacobian_kernel<MODEL, JAC, MINB, false><<<blocks, threads, 0, s>>>(pb, L, st, lp, out, huber, list, count,
-                                                                               main_eval_budget());
+  if (MODEL == B200BA_MODEL_CENTRAL_GENERIC && JAC && out.compact)
+    residual_jacobian_kernel<MODEL, JAC, MINB, false, (MODEL == B200BA_MODEL_CENTRAL_GENERIC && JAC)>
+        <<<blocks, threads, 0, s>>>(pb, L, st, lp, out, huber, list, count, main_eval_budget());
+  else
+    residual_jacobian_kernel<MODEL, JAC, MINB, false, false><<<blocks, threads, 0, s>>>(pb, L, st, lp, out, huber, list, count,
+                                                                                        main_eval_budget());
   if (main_done) cudaEventRecord(main_done, s);  // between the main and the straggler pass
 }
 
@@ -534,18 +654,22 @@ static void launch_stragglers(int model, const ProblemDev& pb, const Layout& L, 
   if (pb.n_obs == 0) return;
   switch (model) {
     case B200BA_MODEL_CENTRAL_GENERIC:
-      residual_jacobian_kernel<B200BA_MODEL_CENTRAL_GENERIC, JAC, 2, true>
-          <<<kStragglerBlocks, kStragglerThreads, 0, s>>>(pb, L, st, lp, out, huber, list, count, 0);
+      if (JAC && out.compact)
+        residual_jacobian_kernel<B200BA_MODEL_CENTRAL_GENERIC, JAC, 2, true, JAC>
+            <<<kStragglerBlocks, kStragglerThreads, 0, s>>>(pb, L, st, lp, out, huber, list, count, 0);
+      else
+        residual_jacobian_kernel<B200BA_MODEL_CENTRAL_GENERIC, JAC, 2, true, false>
+            <<<kStragglerBlocks, kStragglerThreads, 0, s>>>(pb, L, st, lp, out, huber, list, count, 0);
       break;
     case B200BA_MODEL_NONCENTRAL_GENERIC:
-      residual_jacobian_kernel<B200BA_MODEL_NONCENTRAL_GENERIC, JAC, 2, true>
+      residual_jacobian_kernel<B200BA_MODEL_NONCENTRAL_GENERIC, JAC, 2, true, false>
           <<<kStragglerBlocks, kStragglerThreads, 0, s>>>(pb, L, st, lp, out, huber, list, count, 0);
       break;
     case B200BA_MODEL_CENTRAL_OPENCV:
       break;  // closed-form projection: the main pass never defers
     default:
-      residual_jacobian_kernel<-1, JAC, 2, true><<<kStragglerBlocks, kStragglerThreads, 0, s>>>(pb, L, st, lp, out, huber,
-                                                                                             list, count, 0);
+      residual_jacobian_kernel<-1, JAC, 2, true, false><<<kStragglerBlocks, kStragglerThreads, 0, s>>>(pb, L, st, lp, out, huber,
+                                                                                                    list, count, 0);
   }
 }
 
@@ -568,11 +692,28 @@ void launch_straggler_pass(int uniform_model, bool jac, const ProblemDev& pb, co
     launch_stragglers<false>(uniform_model, pb, L, st, last_projection, out, huber, straggler_list, straggler_count, s);
 }
 
+// b200ba_get_jacobians in compact mode: materialise the expanded SoA buffer from the compact records.
+__global__ void expand_jacobian_kernel(ProblemDev pb, Layout L, StateDev st, ObsOut out, double* __restrict__ jac) {
+  const int64_t o = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  const int col = blockIdx.y;
+  if (o >= pb.n_obs) return;
+  double jx = 0.0, jy = 0.0;
+  if (out.has_jac[o] == kJacValid || out.has_jac[o] == kJacLate) load_jcol(pb, L, st, out, o, col, jx, jy);
+  jac[(2 * static_cast<int64_t>(col)) * pb.n_obs + o] = jx;
+  jac[(2 * static_cast<int64_t>(col) + 1) * pb.n_obs + o] = jy;
+}
+void launch_expand_jacobian(const ProblemDev& pb, const Layout& L, const StateDev& st, const ObsOut& out, double* jac,
+                            cudaStream_t s) {
+  if (pb.n_obs == 0 || L.n_jcols == 0) return;
+  dim3 grid(static_cast<unsigned>((pb.n_obs + 127) / 128), L.n_jcols);
+  expand_jacobian_kernel<<<grid, 128, 0, s>>>(pb, L, st, out, jac);
+}
+
 // Folds the late successes of the straggler pass into the normal equations: one warp per listed
 // observation walks the upper triangle of its column set [point 3 | pose 6 | rig 6 | intrinsics K]
 // with FP64 atomics (LV/lm_optimizer_jtj_accumulator_base.h:287-412). The list is short in the
 // steady state; generality over speed.
-__global__ void accumulate_list_kernel(ProblemDev pb, Layout L, ObsOut out, SystemDev sys, double huber,
+__global__ void accumulate_list_kernel(ProblemDev pb, Layout L, StateDev st, ObsOut out, SystemDev sys, double huber,
                                        const uint32_t* __restrict__ list, const int* __restrict__ count) {
   const int lane = threadIdx.x & 31;
   const int64_t warp = (blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x) >> 5;
@@ -606,23 +747,27 @@ __global__ void accumulate_list_kernel(ProblemDev pb, Layout L, ObsOut out, Syst
       const int i = p / nc, j = p - i * nc;
       if (j < i) continue;
       const int ci = jcol(i), cj = jcol(j);
-      const double v = w * (out.jac[(2 * static_cast<int64_t>(ci)) * n + o] * out.jac[(2 * static_cast<int64_t>(cj)) * n + o] +
-                            out.jac[(2 * static_cast<int64_t>(ci) + 1) * n + o] * out.jac[(2 * static_cast<int64_t>(cj) + 1) * n + o]);
+      double ax, ay, bx, by;
+      load_jcol(pb, L, st, out, o, ci, ax, ay);
+      load_jcol(pb, L, st, out, o, cj, bx, by);
+      const double v = w * (ax * bx + ay * by);
       add_H(L, sys, gidx(i), gidx(j), v);
     }
     for (int i = lane; i < nc; i += 32) {
       const int ci = jcol(i);
-      const double v = w * (out.jac[(2 * static_cast<int64_t>(ci)) * n + o] * rx + out.jac[(2 * static_cast<int64_t>(ci) + 1) * n + o] * ry);
+      double ax, ay;
+      load_jcol(pb, L, st, out, o, ci, ax, ay);
+      const double v = w * (ax * rx + ay * ry);
       add_b(L, sys, gidx(i), v);
     }
     __syncwarp();
     if (lane == 0) out.has_jac[o] = kJacValid;
   }
 }
-void launch_accumulate_list(const ProblemDev& pb, const Layout& L, const ObsOut& out, const SystemDev& sys,
-                            double huber, const uint32_t* list, const int* count, cudaStream_t s) {
+void launch_accumulate_list(const ProblemDev& pb, const Layout& L, const StateDev& st, const ObsOut& out,
+                            const SystemDev& sys, double huber, const uint32_t* list, const int* count, cudaStream_t s) {
   if (pb.n_obs == 0) return;
-  accumulate_list_kernel<<<296, 128, 0, s>>>(pb, L, out, sys, huber, list, count);
+  accumulate_list_kernel<<<296, 128, 0, s>>>(pb, L, st, out, sys, huber, list, count);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -655,7 +800,7 @@ __device__ __forceinline__ double warp_sum(double v) {
 // elimination order and is decided by add_H(). Everything involving intrinsics columns, and
 // rig x rig, is left to accumulate_cells_kernel.
 __global__ void __launch_bounds__(128)
-    accumulate_scatter_kernel(ProblemDev pb, Layout L, ObsOut out, SystemDev sys, double huber) {
+    accumulate_scatter_kernel(ProblemDev pb, Layout L, StateDev st, ObsOut out, SystemDev sys, double huber) {
   const int64_t o = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
   const int64_t n = pb.n_obs;
   if (o >= n || out.has_jac[o] != kJacValid) return;
@@ -664,16 +809,37 @@ __global__ void __launch_bounds__(128)
   const int pidx = static_cast<int>(pb.obs_point[o]);
   const double rx = out.residual[o], ry = out.residual[n + o];
   const double w = huber_weight_sq(huber, rx * rx + ry * ry);
-  double jpx[3], jpy[3], jox[6], joy[6];
+  double jpx[3], jpy[3], jox[6], joy[6], jrx6[6], jry6[6];
+  if (out.compact) {
+    double jp[2][3], jo[2][6], jr[2][6];
+    compact_small_blocks(pb, L, st, out, o, jp, jo, jr);
 #pragma unroll
-  for (int a = 0; a < 3; ++a) {
-    jpx[a] = out.jac[(2 * static_cast<int64_t>(L.jc_point + a)) * n + o];
-    jpy[a] = out.jac[(2 * static_cast<int64_t>(L.jc_point + a) + 1) * n + o];
-  }
+    for (int a = 0; a < 3; ++a) {
+      jpx[a] = jp[0][a];
+      jpy[a] = jp[1][a];
+    }
 #pragma unroll
-  for (int a = 0; a < 6; ++a) {
-    jox[a] = out.jac[(2 * static_cast<int64_t>(L.jc_pose + a)) * n + o];
-    joy[a] = out.jac[(2 * static_cast<int64_t>(L.jc_pose + a) + 1) * n + o];
+    for (int a = 0; a < 6; ++a) {
+      jox[a] = jo[0][a];
+      joy[a] = jo[1][a];
+      jrx6[a] = jr[0][a];
+      jry6[a] = jr[1][a];
+    }
+  } else {
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      jpx[a] = out.jac[(2 * static_cast<int64_t>(L.jc_point + a)) * n + o];
+      jpy[a] = out.jac[(2 * static_cast<int64_t>(L.jc_point + a) + 1) * n + o];
+    }
+#pragma unroll
+    for (int a = 0; a < 6; ++a) {
+      jox[a] = out.jac[(2 * static_cast<int64_t>(L.jc_pose + a)) * n + o];
+      joy[a] = out.jac[(2 * static_cast<int64_t>(L.jc_pose + a) + 1) * n + o];
+      if (L.rig_in_state) {
+        jrx6[a] = out.jac[(2 * static_cast<int64_t>(L.jc_rig + a)) * n + o];
+        jry6[a] = out.jac[(2 * static_cast<int64_t>(L.jc_rig + a) + 1) * n + o];
+      }
+    }
   }
   const int gp = L.g_point + 3 * pidx, go = L.g_pose + 6 * iset;
 #pragma unroll
@@ -694,11 +860,9 @@ __global__ void __launch_bounds__(128)
   }
   if (L.rig_in_state) {
     const int gr = L.g_rig + 6 * cam;
-#pragma unroll 1
+#pragma unroll
     for (int b = 0; b < 6; ++b) {
-      const double jrx = out.jac[(2 * static_cast<int64_t>(L.jc_rig + b)) * n + o];
-      const double jry = out.jac[(2 * static_cast<int64_t>(L.jc_rig + b) + 1) * n + o];
-      const double wx_ = w * jrx, wy_ = w * jry;
+      const double wx_ = w * jrx6[b], wy_ = w * jry6[b];
 #pragma unroll
       for (int a = 0; a < 3; ++a) add_H(L, sys, gp + a, gr + b, wx_ * jpx[a] + wy_ * jpy[a]);
 #pragma unroll
@@ -707,12 +871,12 @@ __global__ void __launch_bounds__(128)
   }
 }
 
-void launch_accumulate_scatter(const ProblemDev& pb, const Layout& L, const ObsOut& out, const SystemDev& sys,
-                               double huber, cudaStream_t s) {
+void launch_accumulate_scatter(const ProblemDev& pb, const Layout& L, const StateDev& st, const ObsOut& out,
+                               const SystemDev& sys, double huber, cudaStream_t s) {
   const int threads = 128;
   const unsigned blocks = static_cast<unsigned>((pb.n_obs + threads - 1) / threads);
   if (blocks == 0) return;
-  accumulate_scatter_kernel<<<blocks, threads, 0, s>>>(pb, L, out, sys, huber);
+  accumulate_scatter_kernel<<<blocks, threads, 0, s>>>(pb, L, st, out, sys, huber);
 }
 
 // (rig U intrinsics) x (rig U intrinsics) and the matching b entries, grouped by (camera,
@@ -735,7 +899,7 @@ __device__ __forceinline__ uint32_t cell_key(const ProblemDev& pb, const ObsOut&
 
 template <int MAXPAIRS>
 __global__ void __launch_bounds__(kCellThreads)
-    accumulate_cells_kernel(ProblemDev pb, Layout L, ObsOut out, SystemDev sys, double huber) {
+    accumulate_cells_kernel(ProblemDev pb, Layout L, StateDev st, ObsOut out, SystemDev sys, double huber) {
   extern __shared__ double smem[];
   static_assert(kCellTile == 32, "one lane per observation of a tile");
   const int64_t n = pb.n_obs;
@@ -816,13 +980,17 @@ __global__ void __launch_bounds__(kCellThreads)
         const double sw = sqrt(huber_weight_sq(huber, rx * rx + ry * ry));
         for (int e = warp; e < E; e += kWarps) {
           const int col = (e < rigE) ? (L.jc_rig + e) : (L.jc_intr + (e - rigE));
-          sJx[lane * S + e] = sw * out.jac[(2 * static_cast<int64_t>(col)) * n + o];
-          sJy[lane * S + e] = sw * out.jac[(2 * static_cast<int64_t>(col) + 1) * n + o];
+          double jx, jy;
+          load_jcol(pb, L, st, out, o, col, jx, jy);
+          sJx[lane * S + e] = sw * jx;
+          sJy[lane * S + e] = sw * jy;
         }
         for (int r9 = warp; r9 < 9; r9 += kWarps) {
           const int col = (r9 < 3) ? (L.jc_point + r9) : (L.jc_pose + (r9 - 3));
-          sPx[lane * 9 + r9] = sw * out.jac[(2 * static_cast<int64_t>(col)) * n + o];
-          sPy[lane * 9 + r9] = sw * out.jac[(2 * static_cast<int64_t>(col) + 1) * n + o];
+          double jx, jy;
+          load_jcol(pb, L, st, out, o, col, jx, jy);
+          sPx[lane * 9 + r9] = sw * jx;
+          sPy[lane * 9 + r9] = sw * jy;
         }
         if (warp == 0) {
           sR[2 * lane] = sw * rx;
@@ -888,8 +1056,8 @@ __global__ void __launch_bounds__(kCellThreads)
   }
 }
 
-void launch_accumulate_cells(const ProblemDev& pb, const Layout& L, const ObsOut& out, const SystemDev& sys,
-                             double huber, cudaStream_t s) {
+void launch_accumulate_cells(const ProblemDev& pb, const Layout& L, const StateDev& st, const ObsOut& out,
+                             const SystemDev& sys, double huber, cudaStream_t s) {
   if (pb.n_obs == 0) return;
   const int rigE = L.rig_in_state ? 6 : 0;
   const int Emax = rigE + L.Kmax;
@@ -902,7 +1070,7 @@ void launch_accumulate_cells(const ProblemDev& pb, const Layout& L, const ObsOut
   do {                                                                                                       \
     cudaFuncSetAttribute(accumulate_cells_kernel<MP>, cudaFuncAttributeMaxDynamicSharedMemorySize,           \
                          static_cast<int>(smem));                                                            \
-    accumulate_cells_kernel<MP><<<blocks, kCellThreads, smem, s>>>(pb, L, out, sys, huber);                  \
+    accumulate_cells_kernel<MP><<<blocks, kCellThreads, smem, s>>>(pb, L, st, out, sys, huber);              \
   } while (0)
   if (per_thread <= 1)
     B200BA_LAUNCH_CELLS(1);

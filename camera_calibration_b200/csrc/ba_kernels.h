@@ -16,14 +16,16 @@ void launch_residual_jacobian(int uniform_model, bool jac, const ProblemDev& pb,
 void launch_straggler_pass(int uniform_model, bool jac, const ProblemDev& pb, const Layout& L, const StateDev& st,
                            double2* last_projection, const ObsOut& out, double huber, uint32_t* straggler_list,
                            int* straggler_count, cudaStream_t s);
-void launch_accumulate_list(const ProblemDev& pb, const Layout& L, const ObsOut& out, const SystemDev& sys,
-                            double huber, const uint32_t* list, const int* count, cudaStream_t s);
+void launch_accumulate_list(const ProblemDev& pb, const Layout& L, const StateDev& st, const ObsOut& out,
+                            const SystemDev& sys, double huber, const uint32_t* list, const int* count, cudaStream_t s);
+void launch_expand_jacobian(const ProblemDev& pb, const Layout& L, const StateDev& st, const ObsOut& out, double* jac,
+                            cudaStream_t s);
 // evaluation budget of the main pass before an observation is deferred to the straggler pass
 void set_main_eval_budget(int budget);
-void launch_accumulate_scatter(const ProblemDev& pb, const Layout& L, const ObsOut& out, const SystemDev& sys,
-                               double huber, cudaStream_t s);
-void launch_accumulate_cells(const ProblemDev& pb, const Layout& L, const ObsOut& out, const SystemDev& sys,
-                             double huber, cudaStream_t s);
+void launch_accumulate_scatter(const ProblemDev& pb, const Layout& L, const StateDev& st, const ObsOut& out,
+                               const SystemDev& sys, double huber, cudaStream_t s);
+void launch_accumulate_cells(const ProblemDev& pb, const Layout& L, const StateDev& st, const ObsOut& out,
+                             const SystemDev& sys, double huber, cudaStream_t s);
 void launch_schur_blocks(int bs, int n_blocks, const double* Dblk, const double* bp, double lambda, double* Linv,
                          double* v, int* fail, cudaStream_t s);
 void launch_schur_scale_rows(int bs, int n_blocks, int nd, const double* B, const double* Linv, double* W,
