@@ -98,6 +98,20 @@ class BundleAdjuster:
         _check(self.lib.b200ba_optimize(self._h, C.byref(opt), C.byref(rep)), self._h)
         return rep
 
+    def run_bundle_adjustment(self, opt: Options, max_iteration_count: int, cost_reduction_threshold: float,
+                              on_iteration=None) -> "cabi.BAReport":
+        """RunBundleAdjustment (calibration.cc:187-304) on the device-resident state: single LM
+        iterations + ChooseNiceCameraOrientation + the stop rule, without host round trips.
+        ``on_iteration(iteration, cost)`` may return True to stop (the reference's 'q' key)."""
+        rep = cabi.BAReport()
+        if on_iteration is None:
+            cb = C.cast(None, cabi.ON_ITERATION)
+        else:
+            cb = cabi.ON_ITERATION(lambda user, it, cost: 1 if on_iteration(int(it), float(cost)) else 0)
+        _check(self.lib.b200ba_run_bundle_adjustment(self._h, C.byref(opt), int(max_iteration_count),
+                                                     float(cost_reduction_threshold), C.byref(rep), cb, None), self._h)
+        return rep
+
     def optimize_host(self, state: FlatState, opt: Options) -> Report:
         """set_state + optimize + get_state with host buffers (one OptimizeJointly call)."""
         state.check(self.problem)
@@ -736,7 +750,8 @@ class _Context:
                 and np.array_equal(oxy.reshape(-1), np.asarray(p.obs_xy).reshape(-1)))
 
 
-def _run(dataset: Dataset, state: BAState, opt: Options) -> Report:
+def _prepare(dataset: Dataset, state: BAState):
+    """Cached device context for (dataset, state) + the state flattened into host buffers."""
     if len(state.image_used) != len(state.rig_tr_global):
         raise B200BAError("image_used and rig_tr_global differ in size")  # CHECK_EQ, joint_optimization.cc:72
     ctx = getattr(dataset, "_b200_context", None)
@@ -753,8 +768,12 @@ def _run(dataset: Dataset, state: BAState, opt: Options) -> Report:
     fs = FlatState(np.array(state.points, dtype=np.float64), np.array(state.rig_tr_global, dtype=np.float64)[used],
                    np.array(state.camera_tr_rig, dtype=np.float64), [m.flat_intrinsics().copy() for m in state.intrinsics],
                    lastp)
-    rep = ctx.adjuster.optimize_host(fs, opt)
-    # read back exactly what the reference writes (joint_optimization.cc:942-950) + last_projection
+    return ctx, fs
+
+
+def _write_back(ctx, dataset: Dataset, state: BAState, fs: FlatState):
+    """Read back exactly what the reference writes (joint_optimization.cc:942-950) + last_projection."""
+    used = ctx.used
     state.camera_tr_rig = fs.camera_tr_rig.copy()
     rtg = np.array(state.rig_tr_global, dtype=np.float64)
     rtg[used] = fs.rig_tr_global
@@ -768,6 +787,39 @@ def _run(dataset: Dataset, state: BAState, opt: Options) -> Report:
     state.intrinsics = new_models
     for (i, c, a, b) in ctx.slices:
         dataset.GetImageset(i).FeaturesOfCamera(c)["last_projection"] = fs.last_projection[a:b].copy()
+
+
+def _run(dataset: Dataset, state: BAState, opt: Options) -> Report:
+    ctx, fs = _prepare(dataset, state)
+    rep = ctx.adjuster.optimize_host(fs, opt)
+    _write_back(ctx, dataset, state, fs)
+    return rep
+
+
+def RunBundleAdjustmentOnDevice(dataset: Dataset, state: BAState, max_iteration_count: int, cost_reduction_threshold: float,
+                                regularization_weight: float = 0.0, localize_only: bool = False,
+                                eliminate_points: bool = False, schur_mode: SchurMode = SchurMode.Dense,
+                                on_iteration=None) -> "cabi.BAReport":
+    """The loop of RunBundleAdjustment (calibration.cc:187-304) with the state resident on the device
+    (``b200ba_run_bundle_adjustment``): one upload, single LM iterations + camera re-orientation + stop
+    rule on the device, one download. ``on_iteration(iteration, cost, sync)`` is called after every
+    iteration; ``sync()`` brings the current device state into ``state`` (for the reference's
+    per-iteration checkpoint)."""
+    ctx, fs = _prepare(dataset, state)
+    adj = ctx.adjuster
+    adj.set_state(fs)
+    opt = cabi.default_options(max_iteration_count=1, init_lambda=-1.0, numerical_diff_delta=1e-4,
+                               regularization_weight=float(regularization_weight), localize_only=int(localize_only),
+                               eliminate_points=int(eliminate_points), schur_mode=int(schur_mode), print_progress=0)
+
+    def sync():
+        _write_back(ctx, dataset, state, adj.get_state())
+
+    cb = None
+    if on_iteration is not None:
+        cb = lambda it, cost: on_iteration(it, cost, sync)  # noqa: E731
+    rep = adj.run_bundle_adjustment(opt, max_iteration_count, cost_reduction_threshold, cb)
+    sync()
     return rep
 
 

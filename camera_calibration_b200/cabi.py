@@ -153,6 +153,25 @@ class Report(C.Structure):
         return (list(self.trace_cost[:n]), list(self.trace_lambda[:n]), list(self.trace_attempts[:n]))
 
 
+class BAReport(C.Structure):
+    """b200ba_ba_report."""
+    _fields_ = [
+        ("initial_cost", C.c_double),
+        ("final_cost", C.c_double),
+        ("final_lambda", C.c_double),
+        ("rmse", C.c_double),
+        ("n_valid", C.c_int64),
+        ("n_invalid", C.c_int64),
+        ("iterations", C.c_int32),
+        ("lm_attempts", C.c_int32),
+        ("device_ms", C.c_double),
+        ("costs", C.c_double * MAX_TRACE),
+    ]
+
+
+ON_ITERATION = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int32, C.c_double)
+
+
 class Timings(C.Structure):
     _fields_ = [
         ("jacobian_kernel_ms", C.c_double),
@@ -344,6 +363,8 @@ SYMBOLS = {
     "b200ba_get_timings": (C.c_int, [C.c_void_p, C.POINTER(Timings)]),
     "b200ba_dense_cholesky_solve": (C.c_int, [C.c_int, C.c_int32, C.c_int32, C.POINTER(C.c_double), C.POINTER(C.c_double),
                                              C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+    "b200ba_run_bundle_adjustment": (C.c_int, [C.c_void_p, C.POINTER(Options), C.c_int32, C.c_double, C.POINTER(BAReport),
+                                              ON_ITERATION, C.c_void_p]),
     "b200ba_snapshot_state": (C.c_int, [C.c_void_p]),
     "b200ba_restore_state": (C.c_int, [C.c_void_p]),
     "b200ba_version": (C.c_char_p, []),

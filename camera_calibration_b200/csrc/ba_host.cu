@@ -138,6 +138,7 @@ struct b200ba_handle {
   uint32_t* d_straggler_list = nullptr;  // observations deferred by the main pass of the Jacobian kernel
   int* d_straggler_count = nullptr;
   double *d_partial = nullptr, *d_scal = nullptr;
+  double* d_rot = nullptr;  // [9 * n_cameras] rotations of ChooseNiceCameraOrientation
   double* h_scal = nullptr;  // pinned [16]
   int* h_flags = nullptr;    // pinned [2]
 
@@ -1113,7 +1114,7 @@ void free_handle_buffers(b200ba_handle* h) {
   F(h->d_group_of_block); F(h->d_group_blocks); F(h->d_flags); F(h->d_cols); F(h->d_count); F(h->d_Wc); F(h->d_P); F(h->d_u);
   if (h->h_count) cudaFreeHost(h->h_count);
   h->h_count = nullptr;
-  F(h->d_partial); F(h->d_scal);
+  F(h->d_partial); F(h->d_scal); F(h->d_rot);
   F(h->dn.Lpack); F(h->dn.Linv); F(h->dn.tmp); F(h->dn.d_panel_off); F(h->dn.d_panel_h); F(h->d_ident_cols);
   h->dn.S = nullptr;
   h->dense_planned_n = -1;
@@ -1594,6 +1595,59 @@ int b200ba_optimize(b200ba_handle* h, const b200ba_options* opt, b200ba_report* 
   report->rmse = report->n_valid > 0 ? std::sqrt(stat_sumsq / stat_valid) : 0.0;
   report->cost_and_jacobian_evaluation_time = 1e-3 * (h->timings.jacobian_kernel_ms + h->timings.accumulate_ms + h->timings.trial_cost_ms);
   report->solve_time = 1e-3 * (h->timings.schur_ms + h->timings.factor_ms);
+  return 0;
+}
+
+// RunBundleAdjustment (APP/calibration.cc:187-304) with the state resident on the device: single LM
+// iterations with the lambda carried over, the re-orientation of every camera after each iteration
+// (ChooseNiceCameraOrientation + camera_tr_rig update, calibration.cc:245-252) and the stopping
+// criterion `cost >= last_cost - cost_reduction_threshold` (:298-300). Nothing but the scalars the
+// stop rule needs crosses the PCIe bus between iterations.
+int b200ba_run_bundle_adjustment(b200ba_handle* h, const b200ba_options* opt_in, int32_t max_iteration_count,
+                                 double cost_reduction_threshold, b200ba_ba_report* out,
+                                 int (*on_iteration)(void* user, int32_t iteration, double cost), void* user) {
+  if (!h) return 1;
+  if (!opt_in || !out) {
+    h->error = "NULL argument";
+    return 2;
+  }
+  memset(out, 0, sizeof(*out));
+  b200ba_options opt = *opt_in;
+  opt.max_iteration_count = 1;
+  double lambda = opt_in->init_lambda;  // the reference starts from -1 (calibration.cc:203)
+  double last_cost = INFINITY;
+  b200ba_timings acc{};
+  for (int iteration = 0; iteration < max_iteration_count; ++iteration) {
+    opt.init_lambda = lambda;
+    b200ba_report rep;
+    if (int rc = b200ba_optimize(h, &opt, &rep)) return rc;
+    lambda = rep.final_lambda;
+    const double cost = rep.final_cost;
+    if (iteration == 0) out->initial_cost = rep.initial_cost;
+    out->final_cost = cost;
+    out->final_lambda = lambda;
+    out->rmse = rep.rmse;
+    out->n_valid = rep.n_valid;
+    out->n_invalid = rep.n_invalid;
+    out->lm_attempts += rep.trace_len ? rep.trace_attempts[0] : 0;
+    if (out->iterations < B200BA_MAX_TRACE) out->costs[out->iterations] = cost;
+    out->iterations += 1;
+    acc.total_ms += h->timings.total_ms;
+    if (!opt.localize_only) {
+      // beautify all camera orientations (calibration.cc:245-252)
+      if (!h->d_rot && dev_alloc(h, &h->d_rot, 9 * static_cast<size_t>(h->n_cameras))) return 1;
+      launch_nice_orientation(h->pb, h->st[h->cur], h->n_cameras, h->d_rot, h->stream);
+      CUDA_TRY(h, cudaGetLastError());
+    }
+    if (on_iteration) {
+      CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+      if (on_iteration(user, iteration, cost) != 0) break;  // the 'q' key of the reference (calibration.cc:293-295)
+    }
+    if (cost >= last_cost - cost_reduction_threshold) break;  // stopping criterion
+    last_cost = cost;
+  }
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  out->device_ms = acc.total_ms;
   return 0;
 }
 

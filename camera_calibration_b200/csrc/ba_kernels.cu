@@ -1938,4 +1938,156 @@ void launch_dirfit_update(int G, const double* grid, const double* x, double* ou
   if (G > 0) dirfit_update_kernel<<<(G + 127) / 128, 128, 0, s>>>(G, grid, x, out);
 }
 
+
+// ------------------------------------------------------------------------------------------
+// ChooseNiceCameraOrientation on the device (APP/models/central_generic.cc:570-621)
+// ------------------------------------------------------------------------------------------
+// One block per camera: forward = Unproject(image centre), right = mean Unproject over the 21-row strip to
+// the right of the centre; rotation = Rz(angle) * FromTwoVectors(forward, e_z). The rotation is written
+// to rot[9 * cam] (row-major); cameras that are not central-generic get the identity (the base class
+// and the non-central model return it: camera_model.h:120-122, noncentral_generic.h:128-132).
+__global__ void nice_orientation_kernel(ProblemDev pb, StateDev st, double* __restrict__ rot) {
+  const int cam = blockIdx.x;
+  const CamDev& c = pb.cams[cam];
+  double* Rout = rot + 9 * cam;
+  if (c.model_type != B200BA_MODEL_CENTRAL_GENERIC) {
+    if (threadIdx.x < 9) Rout[threadIdx.x] = (threadIdx.x % 4 == 0) ? 1.0 : 0.0;
+    return;
+  }
+  const double* grid = st.intrinsics + c.intr_off;
+  __shared__ double sh[4][256];
+  const int w = c.width, h = c.height;
+  const int x0 = min(w - 1, w / 2 + 11), x1 = w - 1;
+  const int y0 = max(0, h / 2 - 10), y1 = min(h - 1, h / 2 + 10);
+  const int nx = x1 - x0 + 1, ny = y1 - y0 + 1;
+  double sx = 0, sy = 0, sz = 0, cnt = 0;
+  for (int i = threadIdx.x; i < nx * ny; i += blockDim.x) {
+    const double px = static_cast<double>(x0 + i % nx) + 0.5, py = static_cast<double>(y0 + i / nx) + 0.5;
+    if (!in_area(c, px, py)) continue;
+    CentralEval e;
+    central_eval(c, grid, px, py, e);
+    sx += e.u.x;
+    sy += e.u.y;
+    sz += e.u.z;
+    cnt += 1.0;
+  }
+  sh[0][threadIdx.x] = sx;
+  sh[1][threadIdx.x] = sy;
+  sh[2][threadIdx.x] = sz;
+  sh[3][threadIdx.x] = cnt;
+  __syncthreads();
+  for (int o = blockDim.x / 2; o > 0; o >>= 1) {  // fixed-order tree: deterministic
+    if (threadIdx.x < o)
+      for (int q = 0; q < 4; ++q) sh[q][threadIdx.x] += sh[q][threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x != 0) return;
+  // the reference passes float pixel coordinates (0.5f * width())
+  const double cx = static_cast<double>(0.5f * static_cast<float>(w)), cy = static_cast<double>(0.5f * static_cast<float>(h));
+  d3 fwd = mk3(0, 0, 1);
+  if (in_area(c, cx, cy)) {
+    CentralEval e;
+    central_eval(c, grid, cx, cy, e);
+    fwd = e.u;
+  }
+  // Quaterniond::FromTwoVectors(forward, e_z)
+  const d3 v0 = rsqrt(dot3(fwd, fwd)) * fwd;
+  const double cc = v0.z;
+  q4 q;
+  if (cc < -1.0 + 1e-12) {
+    d3 axis = cross3(v0, mk3(1, 0, 0));
+    if (dot3(axis, axis) < 1e-12) axis = cross3(v0, mk3(0, 1, 0));
+    axis = rsqrt(dot3(axis, axis)) * axis;
+    q = q4{0.0, axis.x, axis.y, axis.z};
+  } else {
+    const d3 axis = cross3(v0, mk3(0, 0, 1));
+    const double s2 = sqrt((1.0 + cc) * 2.0);
+    q = q4{0.5 * s2, axis.x / s2, axis.y / s2, axis.z / s2};
+  }
+  double F[9];
+  qrot(q, F);
+  double Rz[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+  if (sh[3][0] > 0) {
+    const d3 mean = (1.0 / sh[3][0]) * mk3(sh[0][0], sh[1][0], sh[2][0]);
+    const d3 frr = rot_apply(F, mean);
+    const double angle = atan2(-frr.y, frr.x);
+    const double ca = cos(angle), sa = sin(angle);
+    Rz[0] = ca;
+    Rz[1] = -sa;
+    Rz[3] = sa;
+    Rz[4] = ca;
+  }
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) Rout[3 * i + j] = Rz[3 * i] * F[j] + Rz[3 * i + 1] * F[3 + j] + Rz[3 * i + 2] * F[6 + j];
+}
+
+// Rotate(): every grid direction d <- rotation d; camera_tr_rig <- SE3(rotation, 0) * camera_tr_rig
+// (APP/calibration.cc:246-252).
+__global__ void apply_orientation_kernel(ProblemDev pb, StateDev st, const double* __restrict__ rot, int n_cameras) {
+  const int cam = blockIdx.y;
+  const CamDev& c = pb.cams[cam];
+  if (c.model_type != B200BA_MODEL_CENTRAL_GENERIC) return;
+  double R[9];
+#pragma unroll
+  for (int i = 0; i < 9; ++i) R[i] = rot[9 * cam + i];
+  const int64_t G = static_cast<int64_t>(c.gw) * c.gh;
+  const int64_t k = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (k < G) {
+    double* g = st.intrinsics + c.intr_off + 3 * k;
+    const d3 r = rot_apply(R, mk3(g[0], g[1], g[2]));
+    g[0] = r.x;
+    g[1] = r.y;
+    g[2] = r.z;
+  }
+  if (k == 0) {
+    // rotation matrix -> unit quaternion (Eigen's QuaternionBase::operator=(MatrixBase))
+    q4 q;
+    const double t = R[0] + R[4] + R[8];
+    if (t > 0) {
+      const double s = sqrt(t + 1.0) * 2;
+      q = q4{0.25 * s, (R[7] - R[5]) / s, (R[2] - R[6]) / s, (R[3] - R[1]) / s};
+    } else {
+      int i = 0;
+      if (R[4] > R[0]) i = 1;
+      if (R[8] > R[4 * i]) i = 2;
+      const int j = (i + 1) % 3, kk = (i + 2) % 3;
+      const double s = sqrt(R[4 * i] - R[4 * j] - R[4 * kk] + 1.0) * 2;
+      double v[3];
+      v[i] = 0.25 * s;
+      v[j] = (R[3 * j + i] + R[3 * i + j]) / s;
+      v[kk] = (R[3 * kk + i] + R[3 * i + kk]) / s;
+      q = q4{(R[3 * kk + j] - R[3 * j + kk]) / s, v[0], v[1], v[2]};
+    }
+    const double qn = rsqrt(q.w * q.w + q.x * q.x + q.y * q.y + q.z * q.z);
+    q = q4{q.w * qn, q.x * qn, q.y * qn, q.z * qn};
+    double* p = st.camera_tr_rig + 7 * cam;
+    q4 r = qmul(q, q4{p[0], p[1], p[2], p[3]});
+    // Sophus' product renormalises to first order when the squared norm is not exactly 1
+    const double sn = r.w * r.w + r.x * r.x + r.y * r.y + r.z * r.z;
+    if (sn != 1.0) {
+      const double sc = 2.0 / (1.0 + sn);
+      r = q4{r.w * sc, r.x * sc, r.y * sc, r.z * sc};
+    }
+    double Q[9];
+    qrot(q, Q);
+    const d3 tt = rot_apply(Q, mk3(p[4], p[5], p[6]));
+    p[0] = r.w;
+    p[1] = r.x;
+    p[2] = r.y;
+    p[3] = r.z;
+    p[4] = tt.x;
+    p[5] = tt.y;
+    p[6] = tt.z;
+  }
+}
+
+void launch_nice_orientation(const ProblemDev& pb, const StateDev& st, int n_cameras, double* rot, cudaStream_t s) {
+  if (n_cameras <= 0) return;
+  nice_orientation_kernel<<<n_cameras, 256, 0, s>>>(pb, st, rot);
+  int64_t gmax = 1;
+  for (int c = 0; c < n_cameras; ++c) gmax = std::max<int64_t>(gmax, static_cast<int64_t>(pb.cams[c].gw) * pb.cams[c].gh);
+  dim3 grid(static_cast<unsigned>((gmax + 127) / 128), n_cameras);
+  apply_orientation_kernel<<<grid, 128, 0, s>>>(pb, st, rot, n_cameras);
+}
+
 }  // namespace b200ba

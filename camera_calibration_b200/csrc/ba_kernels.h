@@ -63,6 +63,9 @@ void launch_permute_double2(int64_t n, const uint32_t* perm, const double2* src,
                             cudaStream_t s);
 
 
+// ChooseNiceCameraOrientation + Rotate + camera_tr_rig update for every camera (rot: [9 * n_cameras] scratch)
+void launch_nice_orientation(const ProblemDev& pb, const StateDev& st, int n_cameras, double* rot, cudaStream_t s);
+
 // ---- dense phase (ba_dense.cu) ----------------------------------------------------------------
 // Storage map of the reduced system S (n_d x n_d, column-major, lower triangle valid): columns are
 // grouped in blocks of `nb`; block j lives in slot (j % ranks) * blocks_per_rank + j / ranks, so that

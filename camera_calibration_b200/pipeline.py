@@ -86,11 +86,31 @@ def RunBundleAdjustment(use_cuda: bool, schur_mode: SchurMode, max_iteration_cou
                         cost_reduction_threshold: float, dataset: Dataset, state: BAState,
                         regularization_weight: float, localize_only: bool,
                         state_output_path: Optional[str] = None, eliminate_points: bool = False,
-                        on_iteration: Optional[Callable[[int, float], None]] = None) -> List[float]:
+                        on_iteration: Optional[Callable[[int, float], None]] = None,
+                        device_resident: bool = True) -> List[float]:
     """calibration.cc:187-304: single LM iterations until the cost stops falling by more than
     ``cost_reduction_threshold``; the state directory is rewritten after every iteration (the
     reference's checkpoint / resume mechanism) and the cameras are re-oriented. Returns the cost
-    after each iteration. ``eliminate_points`` defaults to the product's choice (False)."""
+    after each iteration. ``eliminate_points`` defaults to the product's choice (False).
+
+    ``device_resident`` (default): the whole loop -- LM iterations, ChooseNiceCameraOrientation, stop
+    rule -- runs inside the library on the state in HBM (``b200ba_run_bundle_adjustment``); the state
+    comes back to the host only for the per-iteration checkpoint (when ``state_output_path`` is given)
+    and at the end. ``device_resident=False`` is the same loop driven from Python with one host round
+    trip per iteration (kept for the equivalence test)."""
+    if device_resident:
+        def cb(it, cost, sync):
+            if state_output_path:
+                from . import io
+                sync()
+                io.SaveBAState(state_output_path, state)
+            if on_iteration:
+                on_iteration(it, cost)
+            return False
+        rep = api.RunBundleAdjustmentOnDevice(dataset, state, max_iteration_count, cost_reduction_threshold,
+                                              regularization_weight, localize_only, eliminate_points, schur_mode,
+                                              cb if (state_output_path or on_iteration) else None)
+        return [float(rep.costs[i]) for i in range(rep.iterations)]
     numerical_diff_delta = 1e-4  # calibration.cc:201
     lam = -1.0
     last_cost = math.inf

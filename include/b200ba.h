@@ -183,6 +183,27 @@ B200BA_API int b200ba_optimize(b200ba_handle* h, const b200ba_options* opt, b200
 B200BA_API int b200ba_optimize_host(b200ba_handle* h, b200ba_state* state, const b200ba_options* opt,
                          b200ba_report* report);
 
+/* RunBundleAdjustment (calibration.cc:187-304) on the state held by the handle: up to
+ * max_iteration_count single LM iterations (lambda carried over, starting from opt->init_lambda, the
+ * reference passes -1), after each one ChooseNiceCameraOrientation + Rotate + the camera_tr_rig update
+ * for every camera (calibration.cc:245-252, models/central_generic.cc:570-621; skipped when
+ * localize_only), stop as soon as cost >= last_cost - cost_reduction_threshold (:298-300). The state
+ * never leaves the device; on_iteration (nullable) is called after every iteration -- the place for
+ * the reference's per-iteration SaveBAState checkpoint via b200ba_get_state (:240-243) -- and stops
+ * the loop by returning non-zero (the reference's 'q' key). With several ranks the call is collective. */
+typedef struct b200ba_ba_report {
+  double initial_cost, final_cost, final_lambda, rmse;
+  int64_t n_valid, n_invalid;
+  int32_t iterations;    /* LM iterations run (OptimizeJointly calls) */
+  int32_t lm_attempts;   /* linear solves over all of them */
+  double device_ms;      /* sum of the iterations' device times */
+  double costs[B200BA_MAX_TRACE]; /* cost after each iteration */
+} b200ba_ba_report;
+B200BA_API int b200ba_run_bundle_adjustment(b200ba_handle* h, const b200ba_options* opt, int32_t max_iteration_count,
+                                            double cost_reduction_threshold, b200ba_ba_report* report,
+                                            int (*on_iteration)(void* user, int32_t iteration, double cost),
+                                            void* user);
+
 /* ---- building blocks, exposed for parity tests and profiling -------------- */
 /* One pass of JointOptimizationCostFunction::Compute<compute_jacobians>
  * (joint_optimization.cc:240-306) at the current state.

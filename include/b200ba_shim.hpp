@@ -243,7 +243,9 @@ inline SE3d pose_at(const std::vector<double>& v, size_t i) {
   T.tx = v[7 * i + 4]; T.ty = v[7 * i + 5]; T.tz = v[7 * i + 6];
   return T;
 }
-inline void run(Dataset& dataset, BAState* state, const b200ba_options& opt, b200ba_report* rep) {
+// Flattens (dataset, state), creates a handle, runs `body(handle, &flat_state)` and reads the result back.
+template <class Body>
+inline void run_with_handle(Dataset& dataset, BAState* state, const char* what, Body body) {
   Flat f;
   flatten(dataset, state, &f);
   b200ba_problem pb{};
@@ -259,10 +261,10 @@ inline void run(Dataset& dataset, BAState* state, const b200ba_options& opt, b20
   b200ba_handle* h = nullptr;
   if (b200ba_create(&pb, -1, &h) != 0) throw std::runtime_error(std::string("b200ba_create: ") + b200ba_last_error(nullptr));
   b200ba_state st{f.points.data(), f.rtg.data(), f.ctr.data(), f.intr.data(), f.lastp.data()};
-  const int rc = b200ba_optimize_host(h, &st, &opt, rep);
+  const int rc = body(h, &st);
   const std::string err = rc ? b200ba_last_error(h) : "";
   b200ba_destroy(h);
-  if (rc) throw std::runtime_error("b200ba_optimize_host: " + err);
+  if (rc) throw std::runtime_error(std::string(what) + ": " + err);
   // read back what the reference writes (joint_optimization.cc:942-950) + last_projection;
   // the intrinsics were updated in place through flat_intrinsics()
   for (size_t c = 0; c < state->camera_tr_rig.size(); ++c) state->camera_tr_rig[c] = pose_at(f.ctr, c);
@@ -275,6 +277,10 @@ inline void run(Dataset& dataset, BAState* state, const b200ba_options& opt, b20
         ft.last_projection = Vec2d{f.lastp[2 * o], f.lastp[2 * o + 1]};
         ++o;
       }
+}
+inline void run(Dataset& dataset, BAState* state, const b200ba_options& opt, b200ba_report* rep) {
+  run_with_handle(dataset, state, "b200ba_optimize_host",
+                  [&](b200ba_handle* h, b200ba_state* st) { return b200ba_optimize_host(h, st, &opt, rep); });
 }
 }  // namespace detail
 
@@ -332,6 +338,45 @@ inline OptimizationReport CudaOptimizeJointly(Dataset& dataset, BAState* state, 
   r.cost_and_jacobian_evaluation_time = rep.cost_and_jacobian_evaluation_time;
   r.solve_time = rep.solve_time;
   return r;
+}
+
+
+// RunBundleAdjustment (calibration.cc:187-304) for the CPU branch of the reference (`use_cuda == false`;
+// the float32 PCG branch has no counterpart here): one upload, the whole loop -- single LM iterations,
+// ChooseNiceCameraOrientation + camera_tr_rig update, stopping criterion -- device-resident inside
+// b200ba_run_bundle_adjustment, one download. `on_iteration(iteration, cost)` (optional) returning true
+// stops the loop like the reference's 'q' key; the calibration window / state_output_path hooks of the
+// reference belong into it. Returns the cost after the last iteration.
+inline double RunBundleAdjustment(SchurMode schur_mode, int max_iteration_count, double cost_reduction_threshold,
+                                  Dataset* dataset, BAState* state, double regularization_weight, bool localize_only,
+                                  bool eliminate_points = false, bool (*on_iteration)(int, double) = nullptr,
+                                  b200ba_ba_report* report_out = nullptr) {
+  b200ba_options opt;
+  b200ba_default_options(&opt);
+  opt.init_lambda = -1;             // calibration.cc:203
+  opt.numerical_diff_delta = 1e-4;  // calibration.cc:201
+  opt.regularization_weight = regularization_weight;
+  opt.localize_only = localize_only ? 1 : 0;
+  opt.eliminate_points = eliminate_points ? 1 : 0;  // the product passes false (calibration.cc:232)
+  opt.schur_mode = static_cast<int32_t>(schur_mode);
+  opt.print_progress = 0;
+  b200ba_ba_report rep;
+  struct Ctx {
+    bool (*fn)(int, double);
+  } ctx{on_iteration};
+  auto tramp = [](void* user, int32_t it, double cost) -> int {
+    Ctx* c = static_cast<Ctx*>(user);
+    return (c->fn && c->fn(it, cost)) ? 1 : 0;
+  };
+  detail::run_with_handle(*dataset, state, "b200ba_run_bundle_adjustment", [&](b200ba_handle* h, b200ba_state* st) {
+    if (int rc = b200ba_set_state(h, st)) return rc;
+    if (int rc = b200ba_run_bundle_adjustment(h, &opt, max_iteration_count, cost_reduction_threshold, &rep,
+                                              on_iteration ? static_cast<int (*)(void*, int32_t, double)>(tramp) : nullptr, &ctx))
+      return rc;
+    return b200ba_get_state(h, st);
+  });
+  if (report_out) *report_out = rep;
+  return rep.final_cost;
 }
 
 }  // namespace b200ba_shim

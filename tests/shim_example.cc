@@ -51,6 +51,12 @@ int main() {
     double c1 = OptimizeJointly(dataset, &state, 3, lambda, 1e-4, 0, false, true, SchurMode::Dense, &lambda, &performed,
                                 false, false, false, false, false, false);
     std::printf("shim: cost after 1 iteration %.6g, after 4 iterations %.6g\n", c0, c1);
+    // the product's outer loop (calibration.cc:187-304), device-resident
+    b200ba_ba_report ba;
+    const double c2 = RunBundleAdjustment(SchurMode::Dense, 5, 1e-12, &dataset, &state, 0, false, /*eliminate_points=*/true,
+                                          nullptr, &ba);
+    std::printf("shim: RunBundleAdjustment: %d iterations, cost %.6g\n", ba.iterations, c2);
+    if (!(c2 <= c1 * (1 + 1e-9) + 1e-12)) return 1;
     // model fitting (FitToPixelDirections): pull the grid towards a shifted pinhole camera
     std::vector<Vec2d> pixels;
     std::vector<Vec3d> directions;

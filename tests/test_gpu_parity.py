@@ -27,7 +27,19 @@ def _small(cfg):
         return synthetic.make_problem(3, n_imagesets=10, lattice=(10, 8), image_size=(300, 240))
     if cfg == 4:
         return synthetic.make_problem(4, n_imagesets=10, lattice=(10, 8), image_size=(410, 290))
+    if cfg == 5:
+        return synthetic.make_problem(5, n_imagesets=8, lattice=(10, 8), image_size=(410, 290))
     raise ValueError(cfg)
+
+
+_FULL = {}
+
+
+def _full(cfg):
+    """Full-size BASELINE configuration, generated once per test session (read-only: tests copy states)."""
+    if cfg not in _FULL:
+        _FULL[cfg] = synthetic.make_problem(cfg)
+    return _FULL[cfg]
 
 
 def test_schur_known_answer_gpu():
@@ -108,7 +120,7 @@ def test_models_match_oracle(oracle_lib):
         assert np.abs(pg[okg] - po[okg]).max() < 1e-8
 
 
-@pytest.mark.parametrize("cfg", [1, 2, 3, 4])
+@pytest.mark.parametrize("cfg", [1, 2, 3, 4, 5])
 def test_residuals_and_jacobians_match_oracle(oracle_lib, cfg):
     sp = _small(cfg)
     opt = cabi.default_options()
@@ -133,7 +145,8 @@ def test_residuals_and_jacobians_match_oracle(oracle_lib, cfg):
         assert np.abs(a - b).max() < 1e-8 * scale, (cfg, k, np.abs(a - b).max(), scale)
 
 
-@pytest.mark.parametrize("cfg,eliminate_points", [(1, 1), (2, 1), (3, 1), (4, 1), (2, 0), (3, 0), (4, 0), (1, 0)])
+@pytest.mark.parametrize("cfg,eliminate_points", [(1, 1), (2, 1), (3, 1), (4, 1), (5, 1), (2, 0), (3, 0), (4, 0), (1, 0),
+                                                  (5, 0)])
 def test_normal_equations_match_oracle(oracle_lib, cfg, eliminate_points):
     sp = _small(cfg)
     opt = cabi.default_options(eliminate_points=eliminate_points)
@@ -150,8 +163,8 @@ def test_normal_equations_match_oracle(oracle_lib, cfg, eliminate_points):
     assert np.array_equal(Hg != 0, Ho != 0) or np.abs(Hg[(Hg != 0) != (Ho != 0)]).max() < 1e-12 * np.abs(Ho).max()
 
 
-@pytest.mark.parametrize("cfg,iters,eliminate_points", [(1, 8, 1), (2, 8, 1), (3, 6, 1), (4, 6, 1), (2, 6, 0), (4, 5, 0),
-                                                         (3, 4, 0)])
+@pytest.mark.parametrize("cfg,iters,eliminate_points", [(1, 8, 1), (2, 8, 1), (3, 6, 1), (4, 6, 1), (5, 6, 1), (2, 6, 0),
+                                                         (4, 5, 0), (3, 4, 0), (5, 4, 0)])
 def test_lm_trajectory_matches_oracle(oracle_lib, cfg, iters, eliminate_points):
     """Same accept / reject sequence, same cost after every iteration, same final state -- for the
     point-elimination order (3x3 blocks, what north_star names) and the pose-elimination order
@@ -175,19 +188,125 @@ def test_lm_trajectory_matches_oracle(oracle_lib, cfg, iters, eliminate_points):
         assert np.abs(a - b).max() < 1e-6 * max(1.0, np.abs(b).max())
 
 
-def test_matches_reference_numeric_path_on_rmse(oracle_lib):
-    """The reference differentiates numerically (delta 1e-4); the analytic device path must land
-    on the same optimum: final RMSE within 1e-6 px... on a noisy, well-constrained problem after
-    the same number of iterations the difference is second order in the Jacobian error."""
-    sp = synthetic.make_problem(2, n_imagesets=30, lattice=(14, 12), image_size=(410, 290), cell=40)
-    opt = cabi.default_options(max_iteration_count=25)
+def _run_to_stop_rule(step, max_iterations=60, threshold=1e-9):
+    """RunBundleAdjustment's loop (APP/calibration.cc:205-302): single LM iterations, lambda carried
+    over, stop when cost >= last_cost - threshold."""
+    lam, last, rep = -1.0, np.inf, None
+    for it in range(max_iterations):
+        rep = step(lam)
+        lam = rep.final_lambda
+        if rep.final_cost >= last - threshold or not rep.performed_an_iteration:
+            break
+        last = rep.final_cost
+    return rep, it + 1
+
+
+def test_final_rmse_matches_reference_numeric_path(oracle_lib):
+    """north_star: "final RMSE within 1e-6 px of reference". The reference differentiates NUMERICALLY
+    (3 + 32 re-projections per observation, delta 1e-4); the device path analytically. Both are run
+    to the reference's stop rule on a noisy, well-constrained problem (27 k observations for 704
+    intrinsic + 360 pose + 1 440 point unknowns) and must land on the same optimum: RMSE gap <= 1e-6 px.
+    (On a poorly constrained problem the numeric path stalls earlier along the flat directions and the
+    gap is ~1e-4 px -- a property of the reference's finite differences, see DESIGN.md.)"""
+    sp = synthetic.make_problem(2, n_imagesets=60, lattice=(24, 20), image_size=(615, 435), cell=30)
     st = sp.init_state.copy()
     with api.BundleAdjuster(sp.problem) as adj:
+        def gstep(lam):
+            return adj.optimize_host(st, cabi.default_options(max_iteration_count=1, init_lambda=lam))
+        grep, gn = _run_to_stop_rule(gstep)
+    oracle_lib.set_threads(0)
+    try:
+        box = {"st": sp.init_state.copy()}
+
+        def ostep(lam):
+            box["st"], rep = oracle_lib.optimize(sp.problem, box["st"], cabi.default_options(
+                max_iteration_count=1, init_lambda=lam, jacobian_mode=cabi.JACOBIAN_NUMERIC))
+            return rep
+        orep, on = _run_to_stop_rule(ostep)
+    finally:
+        oracle_lib.set_threads(1)
+    print(f"device: {gn} iterations rmse {grep.rmse:.9f}; reference (numeric): {on} iterations rmse {orep.rmse:.9f}")
+    assert abs(grep.rmse - orep.rmse) <= 1e-6
+    assert abs(grep.final_cost - orep.final_cost) <= 2e-5 * orep.final_cost
+
+
+@pytest.mark.parametrize("cfg", [2, 3, 4])
+def test_full_size_matches_oracle(oracle_lib, cfg):
+    """The BENCHMARKED configurations against the oracle at full size (~1 M / ~1.9 M observations):
+    every residual, cost and Jacobian entry of every observation at the perturbed start state; for
+    config 2 also H / b rows of 60 points and 60 poses plus 200 intrinsics rows, and the first two LM
+    iterations (cost, accept sequence, state)."""
+    sp = _full(cfg)
+    opt = cabi.default_options()
+    oracle_lib.set_threads(0)
+    try:
+        with api.BundleAdjuster(sp.problem) as adj:
+            adj.set_state(sp.init_state)
+            g = adj.evaluate(opt, compute_jacobians=True)
+            o = oracle_lib.evaluate(sp.problem, sp.init_state, opt, True)
+            vg, vo = g["costs"] >= 0, o["costs"] >= 0
+            assert np.array_equal(vg, vo)
+            assert np.abs(g["residuals"][vg] - o["residuals"][vo]).max() < 1e-9
+            assert np.abs(g["costs"] - o["costs"]).max() < 1e-9
+            assert abs(g["total_cost"] - o["total_cost"]) < 1e-9 * o["total_cost"]
+            hj = o["has_jacobian"] == 1
+            assert np.array_equal(g["intr_index"][hj], o["intr_index"][hj])
+            for k in ("j_point", "j_pose", "j_rig", "j_intr"):
+                a, b = g[k][hj], o[k][hj]
+                assert np.abs(a - b).max() < 1e-8 * max(np.abs(b).max(), 1e-30), (cfg, k)
+            del g, o
+            if cfg != 2:
+                return
+            Hg, bg, cg = adj.build_system(opt)
+            Ho, bo, co = oracle_lib.build_system(sp.problem, sp.init_state, opt)
+            rng = np.random.default_rng(7)
+            P, N = sp.problem.n_points, sp.problem.n_imagesets
+            rows = np.concatenate([
+                (3 * rng.choice(P, 60, replace=False)[:, None] + np.arange(3)).ravel(),
+                (3 * P + 6 * rng.choice(N, 60, replace=False)[:, None] + np.arange(6)).ravel(),
+                3 * P + 6 * N + rng.choice(Hg.shape[0] - 3 * P - 6 * N, 200, replace=False)])
+            scale = np.abs(Ho[rows]).max()
+            assert np.abs(Hg[rows] - Ho[rows]).max() < 1e-8 * scale
+            assert np.abs(Hg[:, rows] - Ho[:, rows]).max() < 1e-8 * scale
+            assert np.abs(bg - bo).max() < 1e-8 * np.abs(bo).max()
+            assert abs(cg - co) < 1e-9 * co
+            del Hg, Ho
+            st = sp.init_state.copy()
+            o2 = cabi.default_options(max_iteration_count=2)
+            rep = adj.optimize_host(st, o2)
+            ost, orep = oracle_lib.optimize(sp.problem, sp.init_state, o2)
+            assert rep.trace()[2] == orep.trace()[2]
+            assert np.allclose(rep.trace()[0], orep.trace()[0], rtol=1e-7)
+            assert abs(rep.rmse - orep.rmse) < 1e-6
+            assert np.abs(st.points - ost.points).max() < 1e-6
+            assert np.abs(st.rig_tr_global - ost.rig_tr_global).max() < 1e-6
+            assert np.abs(st.intrinsics[0] - ost.intrinsics[0]).max() < 1e-6
+    finally:
+        oracle_lib.set_threads(1)
+
+
+def test_config5_full_size():
+    """BASELINE config 5 (4-camera central-generic rig, 1 000 imagesets = 4 000 images, ~4 M
+    observations, 46 344 dense unknowns) on ONE GPU: memory fits, ground-truth cost at the noise level,
+    LM iterations accepted with decreasing cost."""
+    sp = synthetic.make_problem(5)
+    assert sp.problem.n_cameras == 4 and sp.n_obs > 3_000_000
+    opt = cabi.default_options(max_iteration_count=2)
+    with api.BundleAdjuster(sp.problem) as adj:
+        adj.set_state(sp.gt_state)
+        e0 = adj.evaluate(opt)
+        valid = e0["costs"] >= 0
+        assert valid.mean() > 0.9999
+        rmse_gt = np.sqrt((e0["residuals"][valid] ** 2).sum() / valid.sum())
+        assert abs(rmse_gt - 0.05 * np.sqrt(2)) < 3e-3
+        st = sp.init_state.copy()
         rep = adj.optimize_host(st, opt)
-    opt_n = cabi.default_options(max_iteration_count=25, jacobian_mode=cabi.JACOBIAN_NUMERIC)
-    _, orep = oracle_lib.optimize(sp.problem, sp.init_state, opt_n)
-    assert abs(rep.rmse - orep.rmse) < 2e-5
-    assert abs(rep.final_cost - orep.final_cost) < 1e-3 * orep.final_cost
+        assert rep.num_iterations_performed == 2
+        c = rep.trace()[0]
+        assert c[0] < rep.initial_cost and c[1] < c[0]
+        t = adj.timings()
+        print(f"config 5: n_obs {sp.n_obs} total {t.total_ms:.1f} ms jac {t.jacobian_kernel_ms:.3f} acc {t.accumulate_ms:.2f} "
+              f"schur {t.schur_ms:.1f} factor {t.factor_ms:.1f} (solve {t.solve_ms:.1f}) trial {t.trial_cost_ms:.2f}")
 
 
 def test_reference_ba_test_threshold_gpu():
@@ -272,7 +391,7 @@ def test_full_size_properties():
     that do not need the oracle -- every observation is valid at the ground truth, the cost at
     the ground truth is the noise level, an LM iteration from the perturbed state is accepted and
     lowers the cost, evaluation is idempotent under the warm start."""
-    sp = synthetic.make_problem(2)
+    sp = _full(2)
     assert sp.n_obs > 900_000
     opt = cabi.default_options(max_iteration_count=2)
     with api.BundleAdjuster(sp.problem) as adj:
@@ -418,7 +537,7 @@ def test_full_size_other_configs(cfg):
     """BASELINE configs 3 (non-central, ~1 M observations, 10 000 intrinsics) and 4 (2-camera rig,
     ~1.9 M observations, 20 172 unknown intrinsics + rig) at full size: ground-truth cost at the
     noise level, LM iterations accepted with decreasing cost, valid counts consistent."""
-    sp = synthetic.make_problem(cfg)
+    sp = _full(cfg)
     opt = cabi.default_options(max_iteration_count=2)
     with api.BundleAdjuster(sp.problem) as adj:
         adj.set_state(sp.gt_state)
