@@ -832,15 +832,16 @@ def OptimizeJointly(dataset: Dataset, state: BAState, max_iteration_count: int, 
     performed_an_iteration) -- the reference's return value and its two out-parameters.
 
     ``numerical_diff_delta`` is accepted for signature parity; the device path differentiates
-    analytically. ``regularization_weight`` must be 0 (the reference logs an error and ignores
-    it). The debug_fix_* switches (a slow dense fallback in the reference) are not supported."""
-    if debug_fix_points or debug_fix_poses or debug_fix_rig_poses or debug_fix_intrinsics:
-        raise B200BAError("debug_fix_* is not supported on the device path")
+    analytically. A non-zero ``regularization_weight`` is ignored with a warning (the reference logs
+    an error and ignores it). ``debug_verify_cost`` / ``debug_fix_*`` behave like the reference's."""
     opt = cabi.default_options(max_iteration_count=int(max_iteration_count), init_lambda=float(init_lambda),
                                numerical_diff_delta=float(numerical_diff_delta),
                                regularization_weight=float(regularization_weight), localize_only=int(localize_only),
                                eliminate_points=int(eliminate_points), schur_mode=int(schur_mode),
-                               print_progress=int(print_progress))
+                               print_progress=int(print_progress), debug_verify_cost=int(debug_verify_cost),
+                               debug_fix_points=int(debug_fix_points), debug_fix_poses=int(debug_fix_poses),
+                               debug_fix_rig_poses=int(debug_fix_rig_poses),
+                               debug_fix_intrinsics=int(debug_fix_intrinsics))
     rep = _run(dataset, state, opt)
     return rep.final_cost, rep.final_lambda, bool(rep.performed_an_iteration)
 

@@ -105,6 +105,11 @@ class Options(C.Structure):
         ("huber_parameter", C.c_double),
         ("jacobian_mode", C.c_int32),
         ("print_progress", C.c_int32),
+        ("debug_verify_cost", C.c_int32),
+        ("debug_fix_points", C.c_int32),
+        ("debug_fix_poses", C.c_int32),
+        ("debug_fix_rig_poses", C.c_int32),
+        ("debug_fix_intrinsics", C.c_int32),
     ]
 
 

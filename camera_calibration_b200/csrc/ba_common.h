@@ -107,4 +107,15 @@ struct SystemDev {
   double* scalars;  // [8]: cost, n_valid, ...
 };
 
+// Up to four ranges [lo, hi) of global unknown indices held fixed (debug_fix_* of OptimizeJointly).
+struct FixedRanges {
+  int n;
+  int lo[4], hi[4];
+  __host__ __device__ bool has(int g) const {
+    for (int i = 0; i < n; ++i)
+      if (g >= lo[i] && g < hi[i]) return true;
+    return false;
+  }
+};
+
 }  // namespace b200ba

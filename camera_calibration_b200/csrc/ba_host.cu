@@ -645,7 +645,7 @@ int evaluate_state(b200ba_handle* h, int which, bool jac, const ObsOut& out, dou
 }
 
 // Hot loop 1: H, b at the current state (LV/lm_optimizer.h:706-716).
-int build_system(b200ba_handle* h, double huber, double* cost, double* n_valid) {
+int build_system(b200ba_handle* h, double huber, double* cost, double* n_valid, const b200ba_options* fix = nullptr) {
   // The straggler pass (a handful of observations burning the reference's full iteration
   // allowance) runs on the side stream underneath the accumulation of everything else.
   if (evaluate_state(h, h->cur, true, h->out, huber, PH_JAC, /*overlap_stragglers=*/true)) return 1;
@@ -669,6 +669,28 @@ int build_system(b200ba_handle* h, double huber, double* cost, double* n_valid) 
   CUDA_TRY(h, cudaGetLastError());
   // ONE all-reduce per build covers D, b_p, B, b_d, the cost scalars and the trace
   if (all_reduce(h, h->sys.base, static_cast<size_t>(h->reduce_count))) return 1;
+  if (fix) {
+    // FixVariable (joint_optimization.cc:878-903): mask the fixed unknowns out of H, b. The trace for the
+    // lambda initialisation was taken from the full H, like the reference does before it thins the system.
+    const Layout& L = h->L;
+    FixedRanges fr{};
+    auto add = [&](int g0, int count) {
+      if (count > 0 && fr.n < 4) {
+        fr.lo[fr.n] = g0;
+        fr.hi[fr.n] = g0 + count;
+        fr.n++;
+      }
+    };
+    int n_intr = 0;
+    for (int c = 0; c < h->n_cameras; ++c) n_intr += update_parameter_count(h->cams_host[c]);
+    if (fix->debug_fix_points) add(L.g_point, 3 * L.n_points);
+    if (fix->debug_fix_poses) add(L.g_pose, 6 * L.n_imagesets);
+    if (fix->debug_fix_rig_poses && L.rig_in_state) add(L.g_rig, 6 * L.n_cameras);
+    if (fix->debug_fix_intrinsics && !L.localize_only) add(L.g_intr, n_intr);
+    // with several ranks C is a partial sum: rank 0 alone carries the unit diagonal of the fixed dense unknowns
+    launch_mask_fixed(L, h->sys, fr, h->rank == 0 ? 1.0 : 0.0, h->stream);
+    h->timings.kernel_launches += 3;
+  }
   CUDA_TRY(h, cudaMemcpyAsync(h->h_scal, h->sys.scalars, 9 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
   if (h->n_groups > 0 && h->L.nd > 0 && h->force_grouped != 0) {
     // exact column support of every group of Schur blocks, from the (global) B itself
@@ -1150,6 +1172,8 @@ void b200ba_default_options(b200ba_options* o) {
   o->huber_parameter = 1.0;         // joint_optimization.cc:346
   o->jacobian_mode = B200BA_JACOBIAN_ANALYTIC;
   o->print_progress = 0;
+  o->debug_verify_cost = 0;
+  o->debug_fix_points = o->debug_fix_poses = o->debug_fix_rig_poses = o->debug_fix_intrinsics = 0;
 }
 
 const char* b200ba_last_error(const b200ba_handle* h) { return h ? h->error.c_str() : g_create_error.c_str(); }
@@ -1489,9 +1513,32 @@ int b200ba_optimize(b200ba_handle* h, const b200ba_options* opt, b200ba_report* 
   // base pass of a build, or the trial pass of an accepted step) -- no extra pass for statistics
   double stat_valid = 0, stat_sumsq = 0;
   bool have_stats = false;
+  if (opt->debug_verify_cost) {
+    // LMOptimizer::VerifyCost twice (joint_optimization.cc:866-876, lm_optimizer.h:474-490)
+    double c[2] = {0, 0};
+    for (int rep2 = 0; rep2 < 2; ++rep2) {
+      double with_jac = 0;
+      for (int jac = 0; jac < 2; ++jac) {
+        if (evaluate_state(h, h->cur, jac != 0, jac ? h->out : h->out_trial, huber, PH_TRIAL)) return 1;
+        const ObsOut& oo = jac ? h->out : h->out_trial;
+        launch_cost_reduce(h->n_obs, oo.cost, nullptr, oo.residual, h->d_partial, h->d_scal, h->stream);
+        if (all_reduce(h, h->d_scal, 6)) return 1;
+        CUDA_TRY(h, cudaMemcpyAsync(h->h_scal, h->d_scal, 6 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        if (sync_stream(h)) return 1;
+        (jac ? with_jac : c[rep2]) = h->h_scal[3];
+      }
+      if (std::fabs(c[rep2] - with_jac) > 1e-3f)
+        fprintf(stderr, "[b200ba] Cost differs when computed with or without Jacobians: %.12g vs %.12g\n", c[rep2], with_jac);
+    }
+    if (!(std::fabs(c[0] - c[1]) <= 1e-3f)) {
+      h->error = "debug_verify_cost: two cost evaluations of the same state differ by more than 1e-3";
+      return 5;
+    }
+  }
+  const bool any_fixed = opt->debug_fix_points || opt->debug_fix_poses || opt->debug_fix_rig_poses || opt->debug_fix_intrinsics;
   for (int iteration = 0; iteration < opt->max_iteration_count; ++iteration) {
     double cost = 0, n_valid = 0;
-    if (build_system(h, huber, &cost, &n_valid)) return 1;
+    if (build_system(h, huber, &cost, &n_valid, any_fixed ? opt : nullptr)) return 1;
     h->timings.build_count += 1;
     stat_valid = h->h_scal[4];
     stat_sumsq = h->h_scal[5];

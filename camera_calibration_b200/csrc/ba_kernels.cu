@@ -2090,4 +2090,49 @@ void launch_nice_orientation(const ProblemDev& pb, const StateDev& st, int n_cam
   apply_orientation_kernel<<<grid, 128, 0, s>>>(pb, st, rot, n_cameras);
 }
 
+
+// ------------------------------------------------------------------------------------------
+// FixVariable (LV/lm_optimizer.h:360-368, :1069-1121): the fixed unknowns are removed from the system.
+// Here: their rows / columns of H are zeroed, the diagonal set to 1 and b to 0, so the solve returns a
+// zero update for them and the remaining unknowns see exactly the thinned system.
+// ------------------------------------------------------------------------------------------
+__global__ void mask_fixed_blocks_kernel(Layout L, SystemDev sys, FixedRanges fr) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= L.nblocks) return;
+  double* D = sys.Dblk + static_cast<int64_t>(L.dsz) * p;
+  for (int a = 0; a < L.bs; ++a)
+    for (int b = a; b < L.bs; ++b) {
+      const bool fa = fr.has(L.bs * p + a), fb = fr.has(L.bs * p + b);
+      if (fa || fb) D[a * L.bs - (a * (a - 1)) / 2 + (b - a)] = (a == b) ? 1.0 : 0.0;
+    }
+  for (int a = 0; a < L.bs; ++a)
+    if (fr.has(L.bs * p + a)) sys.bp[L.bs * p + a] = 0.0;
+}
+__global__ void mask_fixed_B_kernel(Layout L, SystemDev sys, FixedRanges fr) {
+  const int col = blockIdx.x * blockDim.x + threadIdx.x;
+  const int row = blockIdx.y;
+  if (col >= L.nd || row >= L.nbd) return;
+  if (fr.has(row) || fr.has(L.nbd + col)) sys.B[static_cast<int64_t>(row) * L.nd + col] = 0.0;
+}
+__global__ void mask_fixed_C_kernel(Layout L, SystemDev sys, FixedRanges fr, double unit) {
+  const int col = blockIdx.x * blockDim.x + threadIdx.x;
+  const int row = blockIdx.y;
+  if (col >= L.nd || row >= L.nd || col < row) return;
+  const bool fr_ = fr.has(L.nbd + row), fc = fr.has(L.nbd + col);
+  if (fr_ || fc) sys.C[static_cast<int64_t>(row) * L.nd + col] = (row == col) ? unit : 0.0;
+  if (row == col && fr_) sys.bd[row] = 0.0;
+}
+void launch_mask_fixed(const Layout& L, const SystemDev& sys, const FixedRanges& fr, double unit, cudaStream_t s) {
+  if (fr.n == 0) return;
+  if (L.nblocks > 0) mask_fixed_blocks_kernel<<<(L.nblocks + 127) / 128, 128, 0, s>>>(L, sys, fr);
+  if (L.nbd > 0 && L.nd > 0) {
+    dim3 g((L.nd + 255) / 256, L.nbd);
+    mask_fixed_B_kernel<<<g, 256, 0, s>>>(L, sys, fr);
+  }
+  if (L.nd > 0) {
+    dim3 g((L.nd + 255) / 256, L.nd);
+    mask_fixed_C_kernel<<<g, 256, 0, s>>>(L, sys, fr, unit);
+  }
+}
+
 }  // namespace b200ba

@@ -63,6 +63,7 @@ void launch_permute_double2(int64_t n, const uint32_t* perm, const double2* src,
                             cudaStream_t s);
 
 
+void launch_mask_fixed(const Layout& L, const SystemDev& sys, const FixedRanges& fr, double unit, cudaStream_t s);
 // ChooseNiceCameraOrientation + Rotate + camera_tr_rig update for every camera (rot: [9 * n_cameras] scratch)
 void launch_nice_orientation(const ProblemDev& pb, const StateDev& st, int n_cameras, double* rot, cudaStream_t s);
 

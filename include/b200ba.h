@@ -129,6 +129,19 @@ typedef struct b200ba_options {
   double huber_parameter;       /* reference: 1.0 */
   int32_t jacobian_mode;        /* B200BA_JACOBIAN_* */
   int32_t print_progress;
+  /* the debug_* switches of OptimizeJointly (joint_optimization.h:63-68):
+   *   debug_verify_cost: before optimising, the cost is evaluated without and with Jacobians, twice
+   *     (LMOptimizer::VerifyCost, lm_optimizer.h:474-490); the call fails with code 5 where the
+   *     reference CHECKs |cost1 - cost2| <= 1e-3 (joint_optimization.cc:866-876).
+   *   debug_fix_*: the variables of the group are held fixed (LMOptimizer::FixVariable,
+   *     joint_optimization.cc:878-903): their update is 0 and they are removed from the linear system
+   *     (lm_optimizer.h:1069-1121). The reference then solves the thinned system densely; here the rows /
+   *     columns are masked out of H, b and the Schur-complement path is kept (same solution). */
+  int32_t debug_verify_cost;
+  int32_t debug_fix_points;
+  int32_t debug_fix_poses;
+  int32_t debug_fix_rig_poses;
+  int32_t debug_fix_intrinsics;
 } b200ba_options;
 
 B200BA_API void b200ba_default_options(b200ba_options* opt);

@@ -285,7 +285,7 @@ inline void run(Dataset& dataset, BAState* state, const b200ba_options& opt, b20
 }  // namespace detail
 
 // joint_optimization.h:53-70 -- same parameters, same meaning. numerical_diff_delta is accepted
-// for signature parity (the device path differentiates analytically); debug_* are not supported.
+// for signature parity (the device path differentiates analytically); debug_* behave like the reference's.
 inline double OptimizeJointly(Dataset& dataset, BAState* state, int max_iteration_count, double init_lambda,
                               double numerical_diff_delta, double regularization_weight, bool localize_only,
                               bool eliminate_points, SchurMode schur_mode, double* final_lambda,
@@ -293,9 +293,6 @@ inline double OptimizeJointly(Dataset& dataset, BAState* state, int max_iteratio
                               bool debug_fix_points = false, bool debug_fix_poses = false,
                               bool debug_fix_rig_poses = false, bool debug_fix_intrinsics = false,
                               bool print_progress = true) {
-  (void)debug_verify_cost;
-  if (debug_fix_points || debug_fix_poses || debug_fix_rig_poses || debug_fix_intrinsics)
-    throw std::runtime_error("debug_fix_* is not supported on the device path");
   if (performed_an_iteration) *performed_an_iteration = false;
   b200ba_options opt;
   b200ba_default_options(&opt);
@@ -307,6 +304,11 @@ inline double OptimizeJointly(Dataset& dataset, BAState* state, int max_iteratio
   opt.eliminate_points = eliminate_points ? 1 : 0;
   opt.schur_mode = static_cast<int32_t>(schur_mode);
   opt.print_progress = print_progress ? 1 : 0;
+  opt.debug_verify_cost = debug_verify_cost ? 1 : 0;
+  opt.debug_fix_points = debug_fix_points ? 1 : 0;
+  opt.debug_fix_poses = debug_fix_poses ? 1 : 0;
+  opt.debug_fix_rig_poses = debug_fix_rig_poses ? 1 : 0;
+  opt.debug_fix_intrinsics = debug_fix_intrinsics ? 1 : 0;
   b200ba_report rep;
   detail::run(dataset, state, opt, &rep);
   if (final_lambda) *final_lambda = rep.final_lambda;

@@ -1795,6 +1795,36 @@ int oracle_optimize(const b200ba_problem* pb, b200ba_state* state, const b200ba_
   double final_cost = -1;
   std::vector<double> final_costs;
 
+  // debug switches of OptimizeJointly (joint_optimization.cc:866-903)
+  if (opt->debug_verify_cost) {
+    double c[2];
+    for (int r = 0; r < 2; ++r) {
+      Accumulator a1, a2;
+      a1.huber = a2.huber = opt->huber_parameter;
+      cf.compute(false, S, &a1);
+      Accumulator a2m;
+      a2m.huber = opt->huber_parameter;
+      a2m.allocate(L.block_size, L.num_blocks, nd);
+      cf.compute(true, S, &a2m);
+      if (std::fabs(a1.cost - a2m.cost) > 1e-3f)
+        fprintf(stderr, "[oracle] Cost differs when computed with or without Jacobians: %.12g vs %.12g\n", a1.cost, a2m.cost);
+      c[r] = a1.cost;
+    }
+    if (!(std::fabs(c[0] - c[1]) <= 1e-3f)) return 5;
+  }
+  std::vector<char> fixed;
+  if (opt->debug_fix_points || opt->debug_fix_poses || opt->debug_fix_rig_poses || opt->debug_fix_intrinsics) {
+    fixed.assign(dof, 0);
+    if (opt->debug_fix_points)
+      for (int i = 0; i < 3 * P.n_points; ++i) fixed[L.first_points + i] = 1;
+    if (opt->debug_fix_poses)
+      for (int i = 0; i < 6 * P.n_imagesets; ++i) fixed[L.first_rig_tr_global + i] = 1;
+    if (opt->debug_fix_rig_poses && L.rig_in_state)
+      for (int i = 0; i < 6 * P.n_cameras; ++i) fixed[L.first_camera_tr_rig + i] = 1;
+    if (opt->debug_fix_intrinsics && !L.localize_only)
+      for (int i = L.intrinsics_offset[0]; i < dof; ++i) fixed[i] = 1;
+  }
+
   // OptimizeJointly's loop of single LM iterations (joint_optimization.cc:905-940); each
   // pass is LMOptimizer::OptimizeImpl with max_iteration_count = 1 (LV/lm_optimizer.h:628-991).
   for (int iteration = 0; iteration < opt->max_iteration_count; ++iteration) {
@@ -1847,7 +1877,33 @@ int oracle_optimize(const b200ba_problem* pb, b200ba_state* state, const b200ba_
             acc.block_diag[(size_t(b) * L.block_size + k) * L.block_size + k] = orig_diag[di++] + lambda;
         for (int i = 0; i < nd; ++i) acc.dense[size_t(i) * nd + i] = orig_diag[di++] + lambda;
       }
-      if (nbd > 0 && (nd >= kFastDenseMinN || g_force_fast_dense)) {
+      if (!fixed.empty()) {
+        // SolveWithFixedVariables (LV/lm_optimizer.h:1069-1121): full H with the fixed rows / columns
+        // removed, lambda on the thinned diagonal, dense LDLT, zero update for the fixed unknowns.
+        // (the block / dense diagonals already carry + lambda from the loop above; the reference adds it
+        // to the thinned copy of the un-damped H -- same matrix)
+        std::vector<int> keep;
+        for (int i = 0; i < dof; ++i)
+          if (!fixed[i]) keep.push_back(i);
+        const int m = static_cast<int>(keep.size());
+        auto Hat = [&](int i, int k) -> double {  // i <= k, global indices
+          if (k < nbd) {
+            const int bi = i / L.block_size, bk = k / L.block_size;
+            if (bi != bk) return 0.0;
+            return acc.block_diag[(size_t(bi) * L.block_size + (i - bi * L.block_size)) * L.block_size + (k - bk * L.block_size)];
+          }
+          if (i < nbd) return acc.off_diag[size_t(i) * nd + (k - nbd)];
+          return acc.dense[size_t(i - nbd) * nd + (k - nbd)];
+        };
+        std::vector<double> Ht(size_t(m) * m, 0.0), bt(m), xt(m);
+        for (int a = 0; a < m; ++a) {
+          for (int c = a; c < m; ++c) Ht[size_t(a) * m + c] = Hat(keep[a], keep[c]);
+          bt[a] = keep[a] < nbd ? acc.b_block[keep[a]] : acc.b_dense[keep[a] - nbd];
+        }
+        ldlt_solve(m, Ht.data(), m, bt.data(), 1, 1, xt.data(), 1);
+        std::fill(x.begin(), x.end(), 0.0);
+        for (int a = 0; a < m; ++a) x[keep[a]] = xt[a];
+      } else if (nbd > 0 && (nd >= kFastDenseMinN || g_force_fast_dense)) {
         schur_solve_fast(L.block_size, L.num_blocks, nd, acc.block_diag, acc.off_diag, acc.dense,
                          acc.b_block.data(), acc.b_dense.data(), x.data());
       } else if (nbd > 0) {
