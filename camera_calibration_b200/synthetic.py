@@ -329,7 +329,7 @@ def _lattice(nx: int, ny: int, pitch: float) -> np.ndarray:
 def make_problem(config: int = 2, *, seed: Optional[int] = None, n_imagesets: Optional[int] = None,
                  lattice: Optional[Tuple[int, int]] = None, image_size: Optional[Tuple[int, int]] = None,
                  cell: int = 25, noise_px: float = 0.05, n_cameras: Optional[int] = None,
-                 perturb: bool = True, min_visible: float = 0.9) -> SyntheticProblem:
+                 perturb: bool = True, min_visible: float = 0.9, batched: Optional[bool] = None) -> SyntheticProblem:
     """Build BASELINE.json config 1..5; the keyword overrides shrink it for tests.
 
     config 1: CentralOpenCV 640x480, 20 imagesets, 20x20 lattice            (seed 1)
@@ -337,6 +337,11 @@ def make_problem(config: int = 2, *, seed: Optional[int] = None, n_imagesets: Op
     config 3: noncentral-generic 1200x950 (50x40 grid), 500 imagesets       (seed 3)
     config 4: 2x central-generic rig, 500 imagesets                         (seed 4)
     config 5: 4x central-generic rig, 1000 imagesets                        (seed 5)
+
+    ``batched`` (default: config 5 only): all poses are drawn first (cheap pinhole visibility test), the
+    ground-truth projections of every (imageset, camera) then run as ONE vectorised call per camera and the
+    pixel noise comes from a second stream (seed + 1000). Same distribution, 5x faster for the 4 000-image
+    problem; configs 1-4 keep the interleaved single-stream order their quoted observation counts come from.
     """
     defaults = {
         1: dict(model=cabi.MODEL_CENTRAL_OPENCV, size=(640, 480), f=480.0, n=20, lat=(20, 20), pitch=0.0119, z0=0.27, cams=1),
@@ -396,6 +401,10 @@ def make_problem(config: int = 2, *, seed: Optional[int] = None, n_imagesets: Op
     rtg = np.zeros((N, 7))
     obs_is, obs_cam, obs_pt, obs_xy = [], [], [], []
     n_redraw = 0
+    if batched is None:
+        batched = config == 5
+    rng_noise = np.random.Generator(np.random.PCG64(seed + 1000)) if batched else rng
+    all_lps = [[] for _ in range(C_)]
     for i in range(N):
         for attempt in range(200):
             rot = se3_exp(np.concatenate([np.zeros(3), 0.25 * _u(rng, 3)]))
@@ -420,11 +429,16 @@ def make_problem(config: int = 2, *, seed: Optional[int] = None, n_imagesets: Op
             if not vis_ok:
                 n_redraw += 1
                 continue
-            per_cam = [_project_gt(cams[c], gt_intr[c], cam_f[c], lps[c]) for c in range(C_)]
+            if not batched:
+                per_cam = [_project_gt(cams[c], gt_intr[c], cam_f[c], lps[c]) for c in range(C_)]
             break
         else:
             raise RuntimeError("could not draw a pose that sees the pattern")
         rtg[i] = pose
+        if batched:
+            for c in range(C_):
+                all_lps[c].append(lps[c])
+            continue
         for c in range(C_):
             xy, ok = per_cam[c]
             idx = np.nonzero(ok)[0]
@@ -437,6 +451,22 @@ def make_problem(config: int = 2, *, seed: Optional[int] = None, n_imagesets: Op
             obs_cam.append(np.full(len(idx), c, dtype=np.uint32))
             obs_pt.append(idx.astype(np.uint32))
             obs_xy.append(noisy.astype(np.float32))
+    if batched:
+        proj = []
+        for c in range(C_):
+            xy_all, ok_all = _project_gt(cams[c], gt_intr[c], cam_f[c], np.concatenate(all_lps[c]))
+            proj.append((xy_all.reshape(N, P, 2), ok_all.reshape(N, P)))
+        for i in range(N):
+            for c in range(C_):
+                xy, ok = proj[c][0][i], proj[c][1][i]
+                idx = np.nonzero(ok)[0]
+                noisy = xy[idx] + noise_px * rng_noise.standard_normal((len(idx), 2))
+                keep = in_area(cams[c], noisy[:, 0].astype(np.float32), noisy[:, 1].astype(np.float32))
+                idx, noisy = idx[keep], noisy[keep]
+                obs_is.append(np.full(len(idx), i, dtype=np.uint32))
+                obs_cam.append(np.full(len(idx), c, dtype=np.uint32))
+                obs_pt.append(idx.astype(np.uint32))
+                obs_xy.append(noisy.astype(np.float32))
 
     problem = FlatProblem(cams, N, P, np.concatenate(obs_is), np.concatenate(obs_cam), np.concatenate(obs_pt),
                           np.concatenate(obs_xy))
