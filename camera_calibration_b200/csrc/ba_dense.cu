@@ -32,7 +32,7 @@ namespace {
 
 constexpr int BM = 128, BN = 128, BK = 16, STAGES = 4;
 constexpr int LDT = BM + 4;  // shared-memory row pitch: (k * LDT + m) mod 16 is distinct for k, m in 0..3 -> no bank conflicts
-constexpr int GEMM_THREADS = 256;
+constexpr int GEMM_THREADS = 512;  // 16 warps, 4 (m) x 4 (n), warp tile 32 x 32: 4 warps per scheduler hide the DMMA latency
 constexpr size_t kGemmSmem = static_cast<size_t>(STAGES) * 2 * BK * LDT * sizeof(double);
 
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem, int src_bytes) {
@@ -49,7 +49,7 @@ __device__ __forceinline__ void cp_async_wait() {
   asm volatile("cp.async.wait_group %0;\n" ::"n"(N));
 }
 __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
-  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+  asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
                : "+d"(c0), "+d"(c1)
                : "d"(a), "d"(b));
 }
@@ -60,9 +60,9 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
 __device__ __forceinline__ void load_tile(double* dst, const double* __restrict__ X, int64_t ldx, int rows, int K, int i0,
                                           int k0, bool aligned) {
   if (aligned) {
-    // 16 rows x 64 chunks of 2 doubles = 1024 chunks, 4 per thread
+    // 16 rows x 64 chunks of 2 doubles = 1024 chunks, 2 per thread
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
+    for (int q = 0; q < 1024 / GEMM_THREADS; ++q) {
       const int c = threadIdx.x + q * GEMM_THREADS;
       const int kk = c >> 6, ch = c & 63;
       const int i = i0 + 2 * ch, k = k0 + kk;
@@ -72,7 +72,7 @@ __device__ __forceinline__ void load_tile(double* dst, const double* __restrict_
     }
   } else {
 #pragma unroll
-    for (int q = 0; q < 8; ++q) {
+    for (int q = 0; q < 2048 / GEMM_THREADS; ++q) {
       const int c = threadIdx.x + q * GEMM_THREADS;
       const int kk = c >> 7, ii = c & 127;
       const int i = i0 + ii, k = k0 + kk;
@@ -94,13 +94,13 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) dgemm_nt_kernel(GemmArgs g) {
   double* Bs = smem_d + static_cast<size_t>(STAGES) * BK * LDT;
   const int m0 = tm * BM, n0 = tn * BN;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int wm = (warp & 1) * 64, wn = (warp >> 1) * 32;  // warp tile 64 (m) x 32 (n)
+  const int wm = (warp & 3) * 32, wn = (warp >> 2) * 32;  // warp tile 32 (m) x 32 (n)
   const int lr = lane >> 2, lc = lane & 3;
   const bool same = LOWER && (tm == tn) && (g.A == g.B) && (g.lda == g.ldb);  // diagonal tile of a syrk: one operand
 
-  double acc[8][4][2];
+  double acc[4][4][2];
 #pragma unroll
-  for (int i = 0; i < 8; ++i)
+  for (int i = 0; i < 4; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
@@ -131,48 +131,49 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) dgemm_nt_kernel(GemmArgs g) {
     const double* b_s = same ? a_s : (Bs + (kt % STAGES) * BK * LDT);
 #pragma unroll
     for (int ks = 0; ks < BK / 4; ++ks) {
-      double af[8], bf[4];
+      double af[4], bf[4];
       const double* ap = a_s + (ks * 4 + lc) * LDT + wm + lr;
       const double* bp = b_s + (ks * 4 + lc) * LDT + wn + lr;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) af[i] = ap[8 * i];
+      for (int i = 0; i < 4; ++i) af[i] = ap[8 * i];
 #pragma unroll
       for (int j = 0; j < 4; ++j) bf[j] = bp[8 * j];
 #pragma unroll
-      for (int i = 0; i < 8; ++i)
+      for (int i = 0; i < 4; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
     }
   }
   cp_async_wait<0>();
 
-  // epilogue: accumulator (i, j) holds rows m0 + wm + 8 i + lr, columns n0 + wn + 8 j + 2 lc + {0, 1}
+  // epilogue: accumulator (i, j) holds rows m0 + wm + 8 i + lr, columns n0 + wn + 8 j + 2 lc + {0, 1}.
+  // Per output column the 4 read-modify-writes of a thread are issued as 4 loads, then 4 stores, so
+  // that they overlap instead of forming a load -> store chain.
+  int rowidx[4];
+  bool rowok[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int m = m0 + wm + 8 * i + lr;
+    rowok[i] = m < g.M;
+    rowidx[i] = (EPI == 1) ? (rowok[i] ? __ldg(g.cols + m) : 0) : m;
+  }
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
 #pragma unroll
     for (int e = 0; e < 2; ++e) {
       const int n = n0 + wn + 8 * j + 2 * lc + e;
       if (n >= g.N) continue;
-      if (EPI == 0) {
-        double* ccol = g.C + static_cast<int64_t>(n) * g.ldc;
+      double* ccol = (EPI == 0) ? (g.C + static_cast<int64_t>(n) * g.ldc) : (g.C + g.map.col_offset(__ldg(g.cols + n)));
+      double old[4];
+      bool ok[4];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int m = m0 + wm + 8 * i + lr;
-          if (m >= g.M || (LOWER && m < n)) continue;
-          const double v = g.alpha * acc[i][j][e];
-          ccol[m] = (g.beta == 0.0) ? v : fma(g.beta, ccol[m], v);
-        }
-      } else {
-        // scatter: compact column n is dense column cols[n] of S; rows likewise (cols ascending, m >= n)
-        const int cn = g.cols[n];
-        double* scol = g.C + g.map.col_offset(cn);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int m = m0 + wm + 8 * i + lr;
-          if (m >= g.M || m < n) continue;
-          scol[g.cols[m]] += g.alpha * acc[i][j][e];
-        }
+      for (int i = 0; i < 4; ++i) {
+        ok[i] = rowok[i] && !(LOWER && (m0 + wm + 8 * i + lr) < n);
+        old[i] = (ok[i] && g.beta != 0.0) ? ccol[rowidx[i]] : 0.0;
       }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        if (ok[i]) ccol[rowidx[i]] = fma(g.beta, old[i], g.alpha * acc[i][j][e]);
     }
   }
 }
@@ -225,78 +226,96 @@ __device__ __forceinline__ void load_lower_tile(double* L, const double* __restr
   }
 }
 
+// Register-resident right-looking Cholesky: thread t owns row r = t & 127 and the 32 columns c = (t >> 7) + 4 m of
+// the tile in registers. Step j (fully unrolled, so every register index is a compile-time constant): the
+// owners of column j publish it un-scaled through a double-buffered shared-memory column; everybody then
+// updates its own columns c > j with a(r, c) -= a(r, j) a(c, j) / a(j, j) -- one barrier, one reciprocal and
+// <= 32 broadcast-load + FMA pairs per step -- and the owners keep L(r, j) = a(r, j) / sqrt(a(j, j)).
 __global__ void __launch_bounds__(POTRF_THREADS, 1)
     potrf_tile_kernel(double* __restrict__ A, int64_t lda, int n, int* __restrict__ info) {
-  extern __shared__ __align__(16) double sm[];
-  double* L = sm;  // [PT][PLD] column-major: L(i, j) at L[j * PLD + i]
+  __shared__ double colbuf[2][PT];
   const int tid = threadIdx.x;
-  __shared__ int s_bad;
-  if (tid == 0) s_bad = 0;
-  load_lower_tile(L, A, lda, n);
-  // right-looking, one column at a time. Fixed ownership for the trailing update: thread t owns row
-  // (t & 127) and the columns c with c % 4 == t >> 7, so consecutive threads touch consecutive
-  // shared-memory words of one column and L(row, j) is read once per step.
-  const int prow = tid & 127, pgrp = tid >> 7;
-  for (int j = 0; j < PT; ++j) {
-    __syncthreads();
-    const double d = L[j * PLD + j];
-    if (tid == 0 && !(d > 0.0)) s_bad = 1;
-    const double sq = (d > 0.0) ? sqrt(d) : 1.0;
-    __syncthreads();
-    if (tid < PT - j) {
-      const int i = j + tid;
-      L[j * PLD + i] = (tid == 0) ? sq : L[j * PLD + i] / sq;
-    }
-    __syncthreads();
-    if (prow > j) {
-      const double lrj = L[j * PLD + prow];
-      int c = j + 1 + ((pgrp - (j + 1)) & 3);  // first column > j with c % 4 == pgrp
-      for (; c <= prow; c += 4) L[c * PLD + prow] -= lrj * L[j * PLD + c];
-    }
+  const int r = tid & 127, grp = tid >> 7;
+  double a[32];
+#pragma unroll
+  for (int m = 0; m < 32; ++m) {
+    const int c = grp + 4 * m;
+    double v = (r == c) ? 1.0 : 0.0;
+    if (r < n && c < n && r >= c) v = A[static_cast<int64_t>(c) * lda + r];
+    a[m] = v;
   }
-  __syncthreads();
-  if (tid == 0 && s_bad) info[0] = 1;
-  for (int e = tid; e < PT * PT; e += POTRF_THREADS) {
-    const int j = e >> 7, i = e & 127;
-    if (i < n && j < n && i >= j) A[static_cast<int64_t>(j) * lda + i] = L[j * PLD + i];
+  bool bad = false;
+#pragma unroll
+  for (int j = 0; j < PT; ++j) {
+    const int mj = j >> 2, gj = j & 3;
+    double* cb = colbuf[j & 1];
+    if (grp == gj) cb[r] = (r >= j) ? a[mj] : 0.0;
+    __syncthreads();
+    const double d = cb[j];
+    bad |= !(d > 0.0);
+    const double lrj = cb[r] * (1.0 / d);
+#pragma unroll
+    for (int m = mj; m < 32; ++m) {
+      const int c = grp + 4 * m;
+      if (m > mj || grp > gj) a[m] = fma(-lrj, cb[c], a[m]);
+    }
+    if (grp == gj) a[mj] = (r == j) ? sqrt(d) : cb[r] / sqrt(d);
+  }
+  if (tid == 0 && bad) info[0] = 1;
+#pragma unroll
+  for (int m = 0; m < 32; ++m) {
+    const int c = grp + 4 * m;
+    if (r < n && c < n && r >= c) A[static_cast<int64_t>(c) * lda + r] = a[m];
   }
 }
 
+// Inverse of the lower-triangular tile: one warp per column c solves L x = e_c by column-oriented forward
+// substitution with the residual spread over the lanes' registers (lane l: rows l, l + 32, l + 64, l + 96).
+// Per row only a multiply, one shuffle broadcast and the FMAs of the residual update are on the dependency
+// chain (the L entries are loaded ahead, the reciprocal diagonal is precomputed).
 constexpr int TRINV_CTAS = 8;
 __global__ void __launch_bounds__(POTRF_THREADS, 1)
     trinv_tile_kernel(const double* __restrict__ A, int64_t lda, int n, double* __restrict__ Linv) {
   extern __shared__ __align__(16) double sm[];
-  double* L = sm;
+  double* L = sm;  // [PT][PLD] column-major: L(i, j) at L[j * PLD + i]
+  __shared__ double invd[PT];
   load_lower_tile(L, A, lda, n);
+  __syncthreads();
+  if (threadIdx.x < PT) invd[threadIdx.x] = 1.0 / L[threadIdx.x * PLD + threadIdx.x];
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int c = blockIdx.x * (POTRF_THREADS / 32) + warp;  // 16 warps x 8 CTAs = 128 columns
-  // lane l keeps x_k for k = l, l + 32, l + 64, l + 96
-  double x0 = 0.0, x1 = 0.0, x2 = 0.0, x3 = 0.0;
-  for (int i = c; i < PT; ++i) {
-    // s = sum_{k = c}^{i - 1} L(i, k) x_k ; entries with k < c or k >= i are zero in x
-    double s = 0.0;
-    s = fma(L[(lane)*PLD + i], x0, s);
-    s = fma(L[(lane + 32) * PLD + i], x1, s);
-    s = fma(L[(lane + 64) * PLD + i], x2, s);
-    s = fma(L[(lane + 96) * PLD + i], x3, s);
+  double res[4], x[4];
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    const double xi = (((i == c) ? 1.0 : 0.0) - s) / L[i * PLD + i];
-    if ((i & 31) == lane) {
-      const int m = i >> 5;
-      if (m == 0) x0 = xi;
-      else if (m == 1) x1 = xi;
-      else if (m == 2) x2 = xi;
-      else x3 = xi;
+  for (int q = 0; q < 4; ++q) {
+    res[q] = (lane + 32 * q == c) ? 1.0 : 0.0;
+    x[q] = 0.0;
+  }
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    for (int ii = 0; ii < 32; ++ii) {
+      const int i = 32 * q + ii;
+      if (i < c) continue;  // warp-uniform
+      const double* col = L + i * PLD;
+      // entries of column i below the diagonal (independent of x_i: loaded before the broadcast completes)
+      double l0 = 0, l1 = 0, l2 = 0, l3 = 0;
+      if (q <= 0) l0 = col[lane];
+      if (q <= 1) l1 = col[lane + 32];
+      if (q <= 2) l2 = col[lane + 64];
+      l3 = col[lane + 96];
+      const double mine = res[q] * invd[i];
+      const double xi = __shfl_sync(0xffffffffu, mine, ii);
+      if (lane == ii) x[q] = xi;
+      // rows k > i (entries with k <= i of column i are zero or the diagonal: masked)
+      if (q <= 0) res[0] = (lane > i) ? fma(-l0, xi, res[0]) : res[0];
+      if (q <= 1) res[1] = (lane + 32 > i) ? fma(-l1, xi, res[1]) : res[1];
+      if (q <= 2) res[2] = (lane + 64 > i) ? fma(-l2, xi, res[2]) : res[2];
+      res[3] = (lane + 96 > i) ? fma(-l3, xi, res[3]) : res[3];
     }
   }
-  // L(i, k) for k > i is zero in shared memory, so the not-yet-computed x_k (still 0) never contribute
   double* out = Linv + c * PT;
-  out[lane] = x0;
-  out[lane + 32] = x1;
-  out[lane + 64] = x2;
-  out[lane + 96] = x3;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) out[lane + 32 * q] = x[q];
 }
 
 int launch_potrf_tile(double* A, int64_t lda, int n, double* Linv, int* info, cudaStream_t s) {
@@ -309,7 +328,7 @@ int launch_potrf_tile(double* A, int64_t lda, int n, double* Linv, int* info, cu
     cudaFuncSetAttribute(trinv_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kTileSmem));
     configured = true;
   }
-  potrf_tile_kernel<<<1, POTRF_THREADS, kTileSmem, s>>>(A, lda, n, info);
+  potrf_tile_kernel<<<1, POTRF_THREADS, 0, s>>>(A, lda, n, info);
   trinv_tile_kernel<<<TRINV_CTAS, POTRF_THREADS, kTileSmem, s>>>(A, lda, n, Linv);
   return cudaGetLastError() == cudaSuccess ? 0 : 1;
 }
@@ -334,30 +353,43 @@ void launch_add_diagonal_map(int n, double* S, const DenseMap& map, double lambd
 // (i - k0)]. Every 128 x 128 diagonal tile also has its explicit inverse (Linv tiles, from potrf_tile).
 //
 // forward step, tile t (columns c0 .. c0 + 128): y_t = Linv_t b_t ; b_i -= sum_c L(i, c) y_c for i below.
-// One launch per tile; every CTA recomputes y_t (128 x 128 product, L2 resident) and owns 256 rows below.
+// One launch per tile. Every CTA recomputes y_t (a 128 x 128 product out of L2) and owns 64 rows below,
+// each row's 128-term dot product split over 4 threads (32 independent loads in flight per thread
+// group instead of a 128-deep chain). CTA 0 also publishes y_t (into `yout`, a separate vector: the
+// other CTAs are still reading b_t).
 constexpr int TS_THREADS = 256;
+constexpr int TS_ROWS = 64;
 __global__ void __launch_bounds__(TS_THREADS)
-    trsv_forward_step_kernel(const double* __restrict__ P, int64_t hk, int row0_in_panel, int col_in_panel, int live,
-                             int rows_below, const double* __restrict__ Linv, double* __restrict__ b /* at row c0 */) {
+    trsv_forward_step_kernel(const double* __restrict__ P, int64_t hk, int off_in_panel, int live, int rows_below,
+                             const double* __restrict__ Linv, double* __restrict__ b /* at row c0 */,
+                             double* __restrict__ yout /* at row c0 */) {
   __shared__ double y[PT];
+  __shared__ double part[4][TS_ROWS];
   const int tid = threadIdx.x;
-  if (tid < PT) {
+  {
+    // y_i = sum_{c <= i} Linv(i, c) b_c : 2 threads per row (even / odd c), combined through shared memory
+    const int i = tid & 127, half = tid >> 7;
     double acc = 0.0;
-    if (tid < live)
-      for (int c = 0; c <= tid; ++c) acc = fma(Linv[c * PT + tid], b[c], acc);
-    y[tid] = acc;
+    if (i < live)
+      for (int c = half; c <= i; c += 2) acc = fma(Linv[c * PT + i], b[c], acc);
+    if (half == 1) y[i] = acc;
+    __syncthreads();
+    if (half == 0) y[i] += acc;
+    __syncthreads();
   }
-  __syncthreads();
-  const int r = blockIdx.x * TS_THREADS + tid;  // row below the tile
+  if (blockIdx.x == 0 && tid < live) yout[tid] = y[tid];
+  const int r = blockIdx.x * TS_ROWS + (tid & 63);  // row below the tile
+  const int cg = tid >> 6;                          // column group: columns cg * 32 .. cg * 32 + 31
+  double acc = 0.0;
   if (r < rows_below) {
-    const double* Lp = P + static_cast<int64_t>(col_in_panel) * hk + row0_in_panel + PT + r;
-    double acc = 0.0;
+    const double* Lp = P + static_cast<int64_t>(off_in_panel + cg * 32) * hk + off_in_panel + PT + r;
 #pragma unroll 8
-    for (int c = 0; c < live; ++c) acc = fma(Lp[static_cast<int64_t>(c) * hk], y[c], acc);
-    b[PT + r] -= acc;
+    for (int c = 0; c < 32; ++c)
+      if (cg * 32 + c < live) acc = fma(Lp[static_cast<int64_t>(c) * hk], y[cg * 32 + c], acc);
   }
-  // the tile's own solution is written last by block 0 (every CTA has read b_t by now? no: other CTAs may
-  // still be reading b_t) -> it goes to a separate output vector
+  part[cg][tid & 63] = acc;
+  __syncthreads();
+  if (cg == 0 && r < rows_below) b[PT + r] -= (part[0][tid] + part[1][tid]) + (part[2][tid] + part[3][tid]);
 }
 __global__ void trsv_store_tile_kernel(const double* __restrict__ Linv, const double* __restrict__ b, int live,
                                        double* __restrict__ out, bool transpose) {
@@ -378,16 +410,21 @@ __global__ void __launch_bounds__(TS_THREADS)
     trsv_backward_step_kernel(const double* __restrict__ Lpack, const int64_t* __restrict__ panel_off,
                               const int* __restrict__ panel_h, int NB, int r0, int live, int n_cols_left,
                               const double* __restrict__ Linv, const double* __restrict__ yt /* y at row r0 */,
-                              double* __restrict__ y /* full vector */) {
+                              double* __restrict__ y /* full vector */, double* __restrict__ xout /* at row r0 */) {
   __shared__ double x[PT];
   const int tid = threadIdx.x;
-  if (tid < PT) {
+  {
+    // x_j = sum_{i >= j} Linv(i, j) y_i : 2 threads per entry (even / odd i)
+    const int j = tid & 127, half = tid >> 7;
     double acc = 0.0;
-    if (tid < live)
-      for (int i = tid; i < live; ++i) acc = fma(Linv[tid * PT + i], yt[i], acc);
-    x[tid] = acc;
+    if (j < live)
+      for (int i = j + half; i < live; i += 2) acc = fma(Linv[j * PT + i], yt[i], acc);
+    if (half == 1) x[j] = acc;
+    __syncthreads();
+    if (half == 0) x[j] += acc;
+    __syncthreads();
   }
-  __syncthreads();
+  if (blockIdx.x == 0 && tid < live) xout[tid] = x[tid];
   const int warp = tid >> 5, lane = tid & 31;
   const int c = blockIdx.x * (TS_THREADS / 32) + warp;
   if (c >= n_cols_left) return;
@@ -552,28 +589,30 @@ int dense_solve(DenseCtx* d, double* b) {
     const int k = (t * PT) / NB, sub = (t * PT - k * NB) / PT;
     return d->Linv + static_cast<int64_t>(k * sub_n + sub) * PT * PT;
   };
-  // forward: L y = b
+  // forward: L y = b  (y is collected in d->tmp)
   for (int t = 0; t < d->ntiles; ++t) {
     const int c0 = t * PT, live = std::min(PT, n - c0), k = c0 / NB;
     const int rows_below = n - c0 - PT;
     const double* Li = linv_of(t);
     if (rows_below > 0) {
-      const int grid = (rows_below + TS_THREADS - 1) / TS_THREADS;
-      trsv_forward_step_kernel<<<grid, TS_THREADS, 0, sm>>>(d->Lpack + d->panel_off[k], d->panel_h[k], c0 - k * NB,
-                                                              c0 - k * NB, live, rows_below, Li, b + c0);
+      const int grid = (rows_below + TS_ROWS - 1) / TS_ROWS;
+      trsv_forward_step_kernel<<<grid, TS_THREADS, 0, sm>>>(d->Lpack + d->panel_off[k], d->panel_h[k], c0 - k * NB, live,
+                                                              rows_below, Li, b + c0, d->tmp + c0);
+    } else {
+      trsv_store_tile_kernel<<<1, PT, 0, sm>>>(Li, b + c0, live, d->tmp + c0, false);
     }
-    trsv_store_tile_kernel<<<1, PT, 0, sm>>>(Li, b + c0, live, d->tmp + c0, false);
   }
-  // backward: L^T x = y  (y = d->tmp)
+  // backward: L^T x = y  (x lands in b)
   for (int t = d->ntiles - 1; t >= 0; --t) {
     const int r0 = t * PT, live = std::min(PT, n - r0);
     const double* Li = linv_of(t);
     if (r0 > 0) {
       const int grid = (r0 + TS_THREADS / 32 - 1) / (TS_THREADS / 32);
       trsv_backward_step_kernel<<<grid, TS_THREADS, 0, sm>>>(d->Lpack, d->d_panel_off, d->d_panel_h, NB, r0, live, r0, Li,
-                                                               d->tmp + r0, d->tmp);
+                                                               d->tmp + r0, d->tmp, b + r0);
+    } else {
+      trsv_store_tile_kernel<<<1, PT, 0, sm>>>(Li, d->tmp + r0, live, b + r0, true);
     }
-    trsv_store_tile_kernel<<<1, PT, 0, sm>>>(Li, d->tmp + r0, live, b + r0, true);
   }
   return cudaGetLastError() == cudaSuccess ? 0 : 1;
 }

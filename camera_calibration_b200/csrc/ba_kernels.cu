@@ -913,6 +913,8 @@ __global__ void __launch_bounds__(kCellThreads)
   double* sR = sJy + kCellTile * S;        // [32][2]  sqrt(w) * r
   double* sPx = sR + 2 * kCellTile;        // [32][9]  sqrt(w) * J row x of [point 3 | pose 6]
   double* sPy = sPx + 9 * kCellTile;       // [32][9]
+  __shared__ double sObs[kCellTile * 16];  // compact mode: sw, wx[4], wy[4], Mn[6] per observation of the tile
+  __shared__ double sTan[96];              // compact mode: tangent frames of the run's 4x4 control points
   __shared__ uint32_t sKey[kCellTile];
   __shared__ int sPoint[kCellTile];
   __shared__ int sIset[kCellTile];
@@ -974,23 +976,79 @@ __global__ void __launch_bounds__(kCellThreads)
       while (run_n < tile_n && sKey[run_n] == key) ++run_n;
       if (run_n < tile_n) run_done = true;
       // stage sqrt(w) * J: warp <-> column, lane <-> observation (coalesced column reads)
-      if (lane < run_n) {
+      if (out.compact) {
+        // compact records: per-observation quantities first (one lane per observation), then the columns
+        // are rebuilt from shared memory: J(k) = sw * wx * wy * Mn [t1 t2]_k
+        if (warp == 0 && lane < run_n) {
+          const int64_t o = pos + lane;
+          const double rx = out.residual[o], ry = out.residual[n + o];
+          const double sw = sqrt(huber_weight_sq(huber, rx * rx + ry * ry));
+          double wx[4], dwx[4], wy[4], dwy[4];
+          bspline_basis(out.cjac[12 * n + o], wx, dwx);
+          bspline_basis(out.cjac[13 * n + o], wy, dwy);
+          double* so = sObs + lane * 16;
+          so[0] = sw;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            so[1 + q] = wx[q];
+            so[5 + q] = wy[q];
+          }
+#pragma unroll
+          for (int q = 0; q < 6; ++q) so[9 + q] = out.cjac[static_cast<int64_t>(6 + q) * n + o];
+          sR[2 * lane] = sw * rx;
+          sR[2 * lane + 1] = sw * ry;
+          sPoint[lane] = static_cast<int>(pb.obs_point[o]);
+          sIset[lane] = static_cast<int>(pb.obs_imageset[o]);
+        }
+        if (warp == 1 && lane < run_n) {
+          const int64_t o = pos + lane;
+          const double rx = out.residual[o], ry = out.residual[n + o];
+          const double sw = sqrt(huber_weight_sq(huber, rx * rx + ry * ry));
+          double jp[2][3], jo[2][6], jr[2][6];
+          compact_small_blocks(pb, L, st, out, o, jp, jo, jr);
+#pragma unroll
+          for (int q = 0; q < 3; ++q) {
+            sPx[lane * 9 + q] = sw * jp[0][q];
+            sPy[lane * 9 + q] = sw * jp[1][q];
+          }
+#pragma unroll
+          for (int q = 0; q < 6; ++q) {
+            sPx[lane * 9 + 3 + q] = sw * jo[0][q];
+            sPy[lane * 9 + 3 + q] = sw * jo[1][q];
+            if (rigE) {
+              sJx[lane * S + q] = sw * jr[0][q];
+              sJy[lane * S + q] = sw * jr[1][q];
+            }
+          }
+        }
+        if (threadIdx.x >= 64 && threadIdx.x < 64 + 96 && K > 0) {
+          const int q = threadIdx.x - 64, cp = q / 6;
+          sTan[q] = st.tangents[c.tan_off + 6 * (static_cast<int64_t>(cell) + (cp & 3) + static_cast<int64_t>(cp >> 2) * c.gw) + (q - 6 * cp)];
+        }
+        __syncthreads();
+        if (lane < run_n) {
+          const double* so = sObs + lane * 16;
+          for (int k = warp; k < K; k += kWarps) {
+            const int cp = k >> 1;
+            const double wk = so[0] * so[1 + (cp & 3)] * so[5 + (cp >> 2)];
+            const double* t = sTan + 6 * cp + 3 * (k & 1);
+            sJx[lane * S + rigE + k] = wk * (so[9] * t[0] + so[10] * t[1] + so[11] * t[2]);
+            sJy[lane * S + rigE + k] = wk * (so[12] * t[0] + so[13] * t[1] + so[14] * t[2]);
+          }
+        }
+      } else if (lane < run_n) {
         const int64_t o = pos + lane;
         const double rx = out.residual[o], ry = out.residual[n + o];
         const double sw = sqrt(huber_weight_sq(huber, rx * rx + ry * ry));
         for (int e = warp; e < E; e += kWarps) {
           const int col = (e < rigE) ? (L.jc_rig + e) : (L.jc_intr + (e - rigE));
-          double jx, jy;
-          load_jcol(pb, L, st, out, o, col, jx, jy);
-          sJx[lane * S + e] = sw * jx;
-          sJy[lane * S + e] = sw * jy;
+          sJx[lane * S + e] = sw * out.jac[(2 * static_cast<int64_t>(col)) * n + o];
+          sJy[lane * S + e] = sw * out.jac[(2 * static_cast<int64_t>(col) + 1) * n + o];
         }
         for (int r9 = warp; r9 < 9; r9 += kWarps) {
           const int col = (r9 < 3) ? (L.jc_point + r9) : (L.jc_pose + (r9 - 3));
-          double jx, jy;
-          load_jcol(pb, L, st, out, o, col, jx, jy);
-          sPx[lane * 9 + r9] = sw * jx;
-          sPy[lane * 9 + r9] = sw * jy;
+          sPx[lane * 9 + r9] = sw * out.jac[(2 * static_cast<int64_t>(col)) * n + o];
+          sPy[lane * 9 + r9] = sw * out.jac[(2 * static_cast<int64_t>(col) + 1) * n + o];
         }
         if (warp == 0) {
           sR[2 * lane] = sw * rx;
