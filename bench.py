@@ -159,6 +159,27 @@ def cpu_baseline_sampled(sp, opt_numeric, budget_s=20.0):
             "breakdown_s": {"jacobian": t_jac_full, "residual": t_res_full, "contraction": t_con_full, "ldlt": t_ldlt_full}}
 
 
+def physical_cores() -> int:
+    """Physical cores of the host (hyper-threads do not help the FMA-bound dense kernels)."""
+    try:
+        seen = set()
+        phys = core = None
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("physical id"):
+                phys = line.split(":")[1].strip()
+            elif line.startswith("core id"):
+                core = line.split(":")[1].strip()
+            elif not line.strip():
+                if phys is not None and core is not None:
+                    seen.add((phys, core))
+                phys = core = None
+        if seen:
+            return len(seen)
+    except OSError:
+        pass
+    return os.cpu_count() or 1
+
+
 class CpuTrajectory:
     """The reference's CPU algorithm (oracle port, NUMERIC Jacobians like the reference) driven exactly
     like the GPU arm: single LM iterations from the start state under the stop rule of
@@ -169,7 +190,10 @@ class CpuTrajectory:
         from camera_calibration_b200 import cabi
         from oracle import oracle
         self.oracle = oracle
-        self.threads = oracle.use_native(threads)  # -march=native build made on THIS box, all host cores
+        # one thread per physical core, pinned and spread over the sockets (must be set before libgomp starts)
+        os.environ.setdefault("OMP_PROC_BIND", "spread")
+        os.environ.setdefault("OMP_PLACES", "cores")
+        self.threads = oracle.use_native(threads if threads > 0 else physical_cores())  # -march=native build made on THIS box
         self.sp = sp
         self.opt = cabi.default_options(jacobian_mode=cabi.JACOBIAN_NUMERIC, max_iteration_count=1)
         # start state: the perturbed initial state with the projection cache warmed by one residual pass

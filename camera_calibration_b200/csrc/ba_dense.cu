@@ -87,16 +87,39 @@ __device__ __forceinline__ void load_tile(double* dst, const double* __restrict_
 // C(i, j) at Cbase + col_off(j) + i, where col_off maps a column to its storage offset (see DenseMap).
 template <bool LOWER, int EPI>
 __global__ void __launch_bounds__(GEMM_THREADS, 1) dgemm_nt_kernel(GemmArgs g) {
-  const int tm = blockIdx.x, tn = blockIdx.y;
-  if (LOWER && tn > tm) return;
   extern __shared__ __align__(16) double smem_d[];
   double* As = smem_d;
   double* Bs = smem_d + static_cast<size_t>(STAGES) * BK * LDT;
-  const int m0 = tm * BM, n0 = tn * BN;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int wm = (warp & 3) * 32, wn = (warp >> 2) * 32;  // warp tile 32 (m) x 32 (n)
   const int lr = lane >> 2, lc = lane & 3;
+  // Persistent CTAs: the grid is capped (launch_dgemm_nt leaves a few SMs to the panel stream of the
+  // factorisation, whose small kernels would otherwise queue behind whole tiles) and every CTA walks the
+  // tile list with stride gridDim.x. LOWER: only tiles tn <= tm, enumerated row by row.
+  const int tiles_m = (g.M + BM - 1) / BM, tiles_n = (g.N + BN - 1) / BN;
+  const int64_t n_tiles = LOWER ? g.n_tiles_lower : static_cast<int64_t>(tiles_m) * tiles_n;
+  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+  int tm, tn;
+  if (LOWER) {
+    // tile -> (tm, tn): rows tm < tiles_n hold tm + 1 tiles, later rows hold tiles_n
+    const int64_t tri = static_cast<int64_t>(tiles_n) * (tiles_n + 1) / 2;
+    if (tile < tri) {
+      tm = static_cast<int>((sqrt(8.0 * static_cast<double>(tile) + 1.0) - 1.0) * 0.5);
+      while (static_cast<int64_t>(tm) * (tm + 1) / 2 > tile) --tm;
+      while (static_cast<int64_t>(tm + 1) * (tm + 2) / 2 <= tile) ++tm;
+      tn = static_cast<int>(tile - static_cast<int64_t>(tm) * (tm + 1) / 2);
+    } else {
+      const int64_t rest = tile - tri;
+      tm = tiles_n + static_cast<int>(rest / tiles_n);
+      tn = static_cast<int>(rest - static_cast<int64_t>(tm - tiles_n) * tiles_n);
+    }
+  } else {
+    tm = static_cast<int>(tile / tiles_n);
+    tn = static_cast<int>(tile - static_cast<int64_t>(tm) * tiles_n);
+  }
+  const int m0 = tm * BM, n0 = tn * BN;
   const bool same = LOWER && (tm == tn) && (g.A == g.B) && (g.lda == g.ldb);  // diagonal tile of a syrk: one operand
+  __syncthreads();  // the previous tile's shared-memory stages are free
 
   double acc[4][4][2];
 #pragma unroll
@@ -176,11 +199,16 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) dgemm_nt_kernel(GemmArgs g) {
         if (ok[i]) ccol[rowidx[i]] = fma(g.beta, old[i], g.alpha * acc[i][j][e]);
     }
   }
+  }  // tile loop
 }
 
-int launch_dgemm_nt(const GemmArgs& g, bool lower, bool scatter, cudaStream_t s) {
-  if (g.M <= 0 || g.N <= 0) return 0;
+static int g_gemm_reserve_sms = 0;
+void set_gemm_sm_reserve(int n) { g_gemm_reserve_sms = n < 0 ? 0 : n; }
+
+int launch_dgemm_nt(const GemmArgs& g_in, bool lower, bool scatter, cudaStream_t s, bool leave_sms) {
+  if (g_in.M <= 0 || g_in.N <= 0) return 0;
   static bool configured_dev[64] = {};
+  static int sm_count[64] = {};
   int dev = 0;
   cudaGetDevice(&dev);
   bool& configured = configured_dev[dev & 63];  // function attributes are per device
@@ -188,9 +216,22 @@ int launch_dgemm_nt(const GemmArgs& g, bool lower, bool scatter, cudaStream_t s)
     cudaFuncSetAttribute(dgemm_nt_kernel<true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kGemmSmem));
     cudaFuncSetAttribute(dgemm_nt_kernel<false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kGemmSmem));
     cudaFuncSetAttribute(dgemm_nt_kernel<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kGemmSmem));
+    cudaDeviceGetAttribute(&sm_count[dev & 63], cudaDevAttrMultiProcessorCount, dev);
     configured = true;
   }
-  dim3 grid((g.M + BM - 1) / BM, (g.N + BN - 1) / BN);
+  GemmArgs g = g_in;
+  const int64_t tm = (g.M + BM - 1) / BM, tn = (g.N + BN - 1) / BN;
+  int64_t n_tiles;
+  if (lower || scatter) {
+    // rows tm' < tn hold tm' + 1 tiles, the remaining rows tn tiles each (tiles with tn' <= tm')
+    const int64_t tnn = std::min(tm, tn);
+    n_tiles = tnn * (tnn + 1) / 2 + (tm - tnn) * tn;
+    g.n_tiles_lower = n_tiles;
+  } else {
+    n_tiles = tm * tn;
+  }
+  int cap = std::max(1, sm_count[dev & 63] - (leave_sms ? g_gemm_reserve_sms : 0));
+  const unsigned grid = static_cast<unsigned>(std::min<int64_t>(n_tiles, cap));
   if (scatter)
     dgemm_nt_kernel<true, 1><<<grid, GEMM_THREADS, kGemmSmem, s>>>(g);
   else if (lower)
@@ -233,7 +274,7 @@ __device__ __forceinline__ void load_lower_tile(double* L, const double* __restr
 // <= 32 broadcast-load + FMA pairs per step -- and the owners keep L(r, j) = a(r, j) / sqrt(a(j, j)).
 __global__ void __launch_bounds__(POTRF_THREADS, 1)
     potrf_tile_kernel(double* __restrict__ A, int64_t lda, int n, int* __restrict__ info) {
-  __shared__ double colbuf[2][PT];
+  __shared__ double colbuf[2][PT + 1];  // column j un-scaled, + 1 / sqrt(a_jj) in the last slot
   const int tid = threadIdx.x;
   const int r = tid & 127, grp = tid >> 7;
   double a[32];
@@ -249,17 +290,22 @@ __global__ void __launch_bounds__(POTRF_THREADS, 1)
   for (int j = 0; j < PT; ++j) {
     const int mj = j >> 2, gj = j & 3;
     double* cb = colbuf[j & 1];
-    if (grp == gj) cb[r] = (r >= j) ? a[mj] : 0.0;
+    if (grp == gj) {
+      cb[r] = (r >= j) ? a[mj] : 0.0;
+      // the owner of the diagonal entry also publishes 1 / sqrt(a_jj): the only transcendental on the
+      // critical path of a step (rsqrt: <= 1 ulp; L(r, j) = a(r, j) * rs, the update uses rs^2 = 1 / a_jj)
+      if (r == j) cb[PT] = rsqrt(a[mj]);
+    }
     __syncthreads();
-    const double d = cb[j];
+    const double d = cb[j], rs = cb[PT];
     bad |= !(d > 0.0);
-    const double lrj = cb[r] * (1.0 / d);
+    const double lrj = cb[r] * (rs * rs);
 #pragma unroll
     for (int m = mj; m < 32; ++m) {
       const int c = grp + 4 * m;
       if (m > mj || grp > gj) a[m] = fma(-lrj, cb[c], a[m]);
     }
-    if (grp == gj) a[mj] = (r == j) ? sqrt(d) : cb[r] / sqrt(d);
+    if (grp == gj) a[mj] = cb[r] * rs;  // L(r, j); the diagonal becomes d * rs = sqrt(d)
   }
   if (tid == 0 && bad) info[0] = 1;
 #pragma unroll
@@ -475,7 +521,7 @@ int dense_factor(DenseCtx* d) {
   cudaStreamWaitEvent(sp, d->ev_misc, 0);
 
   // trailing update of the block columns [j_first, j_last] by panel k (single launch when they are contiguous in S)
-  auto update = [&](int k, int j_first, int j_last, cudaStream_t st) -> int {
+  auto update = [&](int k, int j_first, int j_last, cudaStream_t st, bool leave_sms) -> int {
     const int k0 = k * NB, kw = std::min(NB, n - k0);
     const int j0 = j_first * NB;
     const int jn = std::min(n, (j_last + 1) * NB) - j0;
@@ -493,7 +539,7 @@ int dense_factor(DenseCtx* d) {
     g.alpha = -1.0;
     g.beta = 1.0;
     g.a_aligned = g.b_aligned = gemm_operand_aligned(g.A, g.lda);
-    return launch_dgemm_nt(g, /*lower=*/true, /*scatter=*/false, st);
+    return launch_dgemm_nt(g, /*lower=*/true, /*scatter=*/false, st, leave_sms);
   };
 
   for (int k = 0; k < d->nblk; ++k) {
@@ -562,15 +608,15 @@ int dense_factor(DenseCtx* d) {
     int first_rest = k + 1;
     if (k + 1 < d->nblk && owner(k + 1) == me) {
       if (k > 0) cudaStreamWaitEvent(sp, d->ev_main[(k - 1) & 1], 0);
-      if (update(k, k + 1, k + 1, sp)) return 1;
+      if (update(k, k + 1, k + 1, sp, false)) return 1;
       first_rest = k + 2;
     }
     cudaStreamWaitEvent(sm, d->ev_ready[k & 1], 0);
     if (R == 1) {
-      if (first_rest < d->nblk && update(k, first_rest, d->nblk - 1, sm)) return 1;
+      if (first_rest < d->nblk && update(k, first_rest, d->nblk - 1, sm, true)) return 1;
     } else {
       for (int j = first_rest; j < d->nblk; ++j)
-        if (owner(j) == me && update(k, j, j, sm)) return 1;
+        if (owner(j) == me && update(k, j, j, sm, true)) return 1;
     }
     cudaEventRecord(d->ev_main[k & 1], sm);
   }

@@ -1327,6 +1327,7 @@ int b200ba_create(const b200ba_problem* p, int device, b200ba_handle** out) {
   }
   if (const char* e = getenv("B200BA_DENSE")) h->own_dense = !(strcmp(e, "lib") == 0 || strcmp(e, "0") == 0);
   if (const char* e = getenv("B200BA_DENSE_NB")) h->dense_nb = std::max(128, atoi(e) / 128 * 128);
+  set_gemm_sm_reserve(getenv("B200BA_PANEL_SMS") ? atoi(getenv("B200BA_PANEL_SMS")) : 8);
   {
     int lo = 0, hi = 0;
     cudaDeviceGetStreamPriorityRange(&lo, &hi);
@@ -1860,6 +1861,7 @@ int b200ba_dense_cholesky_solve(int device, int32_t n, int32_t nb, const double*
     return 3;
   }
   if (device >= 0) cudaSetDevice(device);
+  set_gemm_sm_reserve(getenv("B200BA_PANEL_SMS") ? atoi(getenv("B200BA_PANEL_SMS")) : 8);
   DenseCtx d;
   dense_plan(&d, n, nb, 0, 1);
   int rc = 0;

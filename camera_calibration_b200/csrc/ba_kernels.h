@@ -98,12 +98,16 @@ struct GemmArgs {
   // scatter epilogue: C is the base of S, compact row / column i is dense column cols[i] (ascending)
   const int* cols;
   DenseMap map;
+  int64_t n_tiles_lower;  // set by launch_dgemm_nt
 };
 inline bool gemm_operand_aligned(const double* p, int64_t ld) {
   return (reinterpret_cast<uintptr_t>(p) % 16 == 0) && (ld % 2 == 0);
 }
 // lower: only tiles / entries with i >= j (M == N); scatter: the scatter-subtract epilogue (implies lower).
-int launch_dgemm_nt(const GemmArgs& g, bool lower, bool scatter, cudaStream_t s);
+// leave_sms: cap the persistent grid at (SM count - reserve) so that concurrently running panel kernels find
+// a free SM at once (set_gemm_sm_reserve; used for the trailing updates of the factorisation).
+int launch_dgemm_nt(const GemmArgs& g, bool lower, bool scatter, cudaStream_t s, bool leave_sms = false);
+void set_gemm_sm_reserve(int n);
 // Cholesky of a 128 x 128 (live size n) column-major diagonal tile in place + Linv [128 x 128, ld 128].
 int launch_potrf_tile(double* A, int64_t lda, int n, double* Linv, int* info, cudaStream_t s);
 

@@ -292,7 +292,7 @@ def test_config5_dense_size():
     bench line, profiles/): memory fits, ground-truth cost at the noise level, LM iterations accepted
     with decreasing cost."""
     sp = synthetic.make_problem(5, n_imagesets=200)
-    assert sp.problem.n_cameras == 4 and sp.n_obs > 600_000
+    assert sp.problem.n_cameras == 4 and sp.n_obs > 500_000
     opt = cabi.default_options(max_iteration_count=2)
     with api.BundleAdjuster(sp.problem) as adj:
         adj.set_state(sp.gt_state)
