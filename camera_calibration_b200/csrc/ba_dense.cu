@@ -23,6 +23,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 
 #include "ba_kernels.h"
 
@@ -30,10 +31,10 @@ namespace b200ba {
 
 namespace {
 
-constexpr int BM = 128, BN = 128, BK = 16, STAGES = 4;
+constexpr int BM = 128, BN = 128;
 constexpr int LDT = BM + 4;  // shared-memory row pitch: (k * LDT + m) mod 16 is distinct for k, m in 0..3 -> no bank conflicts
 constexpr int GEMM_THREADS = 512;  // 16 warps, 4 (m) x 4 (n), warp tile 32 x 32: 4 warps per scheduler hide the DMMA latency
-constexpr size_t kGemmSmem = static_cast<size_t>(STAGES) * 2 * BK * LDT * sizeof(double);
+constexpr size_t gemm_smem(int bk, int stages) { return static_cast<size_t>(stages) * 2 * bk * LDT * sizeof(double); }
 
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem, int src_bytes) {
   const unsigned s = static_cast<unsigned>(__cvta_generic_to_shared(smem));
@@ -54,15 +55,16 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
                : "d"(a), "d"(b));
 }
 
-// One BK x 128 operand tile: rows k0 .. k0 + BK of the k-strided matrix X (leading dimension ldx), columns
+// One BK x 128 operand tile (BK = 16 or 32): rows k0 .. k0 + BK of the k-strided matrix X (leading dimension ldx), columns
 // i0 .. i0 + 128, zero-filled beyond (rows, K). `aligned` = every 16-byte chunk is 16-byte aligned in
 // global memory (even ldx, even i0, 16-byte aligned base); otherwise 8-byte copies.
+template <int BK>
 __device__ __forceinline__ void load_tile(double* dst, const double* __restrict__ X, int64_t ldx, int rows, int K, int i0,
                                           int k0, bool aligned) {
   if (aligned) {
-    // 16 rows x 64 chunks of 2 doubles = 1024 chunks, 2 per thread
+    // BK rows x 64 chunks of 2 doubles
 #pragma unroll
-    for (int q = 0; q < 1024 / GEMM_THREADS; ++q) {
+    for (int q = 0; q < BK * 64 / GEMM_THREADS; ++q) {
       const int c = threadIdx.x + q * GEMM_THREADS;
       const int kk = c >> 6, ch = c & 63;
       const int i = i0 + 2 * ch, k = k0 + kk;
@@ -72,7 +74,7 @@ __device__ __forceinline__ void load_tile(double* dst, const double* __restrict_
     }
   } else {
 #pragma unroll
-    for (int q = 0; q < 2048 / GEMM_THREADS; ++q) {
+    for (int q = 0; q < BK * 128 / GEMM_THREADS; ++q) {
       const int c = threadIdx.x + q * GEMM_THREADS;
       const int kk = c >> 7, ii = c & 127;
       const int i = i0 + ii, k = k0 + kk;
@@ -85,7 +87,7 @@ __device__ __forceinline__ void load_tile(double* dst, const double* __restrict_
 }  // namespace
 
 // C(i, j) at Cbase + col_off(j) + i, where col_off maps a column to its storage offset (see DenseMap).
-template <bool LOWER, int EPI>
+template <bool LOWER, int EPI, int BK, int STAGES>
 __global__ void __launch_bounds__(GEMM_THREADS, 1) dgemm_nt_kernel(GemmArgs g) {
   extern __shared__ __align__(16) double smem_d[];
   double* As = smem_d;
@@ -132,8 +134,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) dgemm_nt_kernel(GemmArgs g) {
 #pragma unroll
   for (int s = 0; s < STAGES - 1; ++s) {
     if (s < nk) {
-      load_tile(As + s * BK * LDT, g.A, g.lda, g.M, g.K, m0, s * BK, g.a_aligned);
-      if (!same) load_tile(Bs + s * BK * LDT, g.B, g.ldb, g.N, g.K, n0, s * BK, g.b_aligned);
+      load_tile<BK>(As + s * BK * LDT, g.A, g.lda, g.M, g.K, m0, s * BK, g.a_aligned);
+      if (!same) load_tile<BK>(Bs + s * BK * LDT, g.B, g.ldb, g.N, g.K, n0, s * BK, g.b_aligned);
     }
     cp_async_commit();
   }
@@ -145,8 +147,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) dgemm_nt_kernel(GemmArgs g) {
       const int nt = kt + STAGES - 1;
       if (nt < nk) {
         const int s = nt % STAGES;
-        load_tile(As + s * BK * LDT, g.A, g.lda, g.M, g.K, m0, nt * BK, g.a_aligned);
-        if (!same) load_tile(Bs + s * BK * LDT, g.B, g.ldb, g.N, g.K, n0, nt * BK, g.b_aligned);
+        load_tile<BK>(As + s * BK * LDT, g.A, g.lda, g.M, g.K, m0, nt * BK, g.a_aligned);
+        if (!same) load_tile<BK>(Bs + s * BK * LDT, g.B, g.ldb, g.N, g.K, n0, nt * BK, g.b_aligned);
       }
       cp_async_commit();
     }
@@ -212,10 +214,15 @@ int launch_dgemm_nt(const GemmArgs& g_in, bool lower, bool scatter, cudaStream_t
   int dev = 0;
   cudaGetDevice(&dev);
   bool& configured = configured_dev[dev & 63];  // function attributes are per device
+  static int variant = -1;  // B200BA_GEMM_BK=16 (4 stages) | 32 (3 stages)
+  if (variant < 0) variant = (getenv("B200BA_GEMM_BK") && atoi(getenv("B200BA_GEMM_BK")) == 16) ? 16 : 32;
   if (!configured) {
-    cudaFuncSetAttribute(dgemm_nt_kernel<true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kGemmSmem));
-    cudaFuncSetAttribute(dgemm_nt_kernel<false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kGemmSmem));
-    cudaFuncSetAttribute(dgemm_nt_kernel<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kGemmSmem));
+    cudaFuncSetAttribute(dgemm_nt_kernel<true, 0, 16, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(gemm_smem(16, 4)));
+    cudaFuncSetAttribute(dgemm_nt_kernel<false, 0, 16, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(gemm_smem(16, 4)));
+    cudaFuncSetAttribute(dgemm_nt_kernel<true, 1, 16, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(gemm_smem(16, 4)));
+    cudaFuncSetAttribute(dgemm_nt_kernel<true, 0, 32, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(gemm_smem(32, 3)));
+    cudaFuncSetAttribute(dgemm_nt_kernel<false, 0, 32, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(gemm_smem(32, 3)));
+    cudaFuncSetAttribute(dgemm_nt_kernel<true, 1, 32, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(gemm_smem(32, 3)));
     cudaDeviceGetAttribute(&sm_count[dev & 63], cudaDevAttrMultiProcessorCount, dev);
     configured = true;
   }
@@ -232,12 +239,21 @@ int launch_dgemm_nt(const GemmArgs& g_in, bool lower, bool scatter, cudaStream_t
   }
   int cap = std::max(1, sm_count[dev & 63] - (leave_sms ? g_gemm_reserve_sms : 0));
   const unsigned grid = static_cast<unsigned>(std::min<int64_t>(n_tiles, cap));
-  if (scatter)
-    dgemm_nt_kernel<true, 1><<<grid, GEMM_THREADS, kGemmSmem, s>>>(g);
-  else if (lower)
-    dgemm_nt_kernel<true, 0><<<grid, GEMM_THREADS, kGemmSmem, s>>>(g);
-  else
-    dgemm_nt_kernel<false, 0><<<grid, GEMM_THREADS, kGemmSmem, s>>>(g);
+  if (variant == 16) {
+    if (scatter)
+      dgemm_nt_kernel<true, 1, 16, 4><<<grid, GEMM_THREADS, gemm_smem(16, 4), s>>>(g);
+    else if (lower)
+      dgemm_nt_kernel<true, 0, 16, 4><<<grid, GEMM_THREADS, gemm_smem(16, 4), s>>>(g);
+    else
+      dgemm_nt_kernel<false, 0, 16, 4><<<grid, GEMM_THREADS, gemm_smem(16, 4), s>>>(g);
+  } else {
+    if (scatter)
+      dgemm_nt_kernel<true, 1, 32, 3><<<grid, GEMM_THREADS, gemm_smem(32, 3), s>>>(g);
+    else if (lower)
+      dgemm_nt_kernel<true, 0, 32, 3><<<grid, GEMM_THREADS, gemm_smem(32, 3), s>>>(g);
+    else
+      dgemm_nt_kernel<false, 0, 32, 3><<<grid, GEMM_THREADS, gemm_smem(32, 3), s>>>(g);
+  }
   return cudaGetLastError() == cudaSuccess ? 0 : 1;
 }
 

@@ -1907,6 +1907,7 @@ int b200ba_dense_cholesky_solve(int device, int32_t n, int32_t nb, const double*
     ok(cudaMemset(dinfo, 0, sizeof(int)));
     ok(cudaMemcpy2D(d.S, d.map.ld * sizeof(double), dA, static_cast<size_t>(n) * sizeof(double),
                     static_cast<size_t>(n) * sizeof(double), n, cudaMemcpyDeviceToDevice));
+    ok(cudaDeviceSynchronize());  // device-to-device copies are asynchronous; the work below runs on non-blocking streams
   }
   if (rc == 0) {
     cudaEventRecord(e0, d.s_main);
