@@ -521,6 +521,17 @@ def run_b200(args):
                     "host_memory": "pinned" if pinned else "pageable"},
             "gpu_launches": int(launches), "clocks": clocks,
         }
+        # parity across GPU counts: the first trajectory against the committed 1-GPU trajectory of this config
+        tp = os.path.join(ROOT, "profiles", f"r02_config{args.config}_trajectory.json")
+        if os.path.exists(tp) and not args.imagesets:
+            try:
+                ref = json.load(open(tp))["first_trajectory_costs"]
+                m = min(len(ref), len(first_traj_costs))
+                if m:
+                    line["parity_vs_1gpu"] = {"iterations_compared": m, "reference": os.path.relpath(tp, ROOT),
+                                              "max_rel_cost_diff": max(abs(a - b) / abs(b) for a, b in zip(first_traj_costs[:m], ref[:m]))}
+            except Exception:
+                pass
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(sp, budget_s=args.cpu_budget)
         _emit(line)

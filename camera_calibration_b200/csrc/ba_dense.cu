@@ -31,10 +31,12 @@ namespace b200ba {
 
 namespace {
 
-constexpr int BM = 128, BN = 128;
+constexpr int BM = 128;
 constexpr int LDT = BM + 4;  // shared-memory row pitch: (k * LDT + m) mod 16 is distinct for k, m in 0..3 -> no bank conflicts
-constexpr int GEMM_THREADS = 512;  // 16 warps, 4 (m) x 4 (n), warp tile 32 x 32: 4 warps per scheduler hide the DMMA latency
-constexpr size_t gemm_smem(int bk, int stages) { return static_cast<size_t>(stages) * 2 * bk * LDT * sizeof(double); }
+__host__ __device__ constexpr int gemm_threads(int bn) { return 4 * (bn / 32) * 32; }  // 4 x (bn / 32) warps, warp tile 32 x 32
+constexpr size_t gemm_smem(int bn, int bk, int stages) {
+  return static_cast<size_t>(stages) * bk * (LDT + bn + 4) * sizeof(double);
+}
 
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem, int src_bytes) {
   const unsigned s = static_cast<unsigned>(__cvta_generic_to_shared(smem));
@@ -51,35 +53,36 @@ __device__ __forceinline__ void cp_async_wait() {
 }
 __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
   asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
-               : "+d"(c0), "+d"(c1)
-               : "d"(a), "d"(b));
+      : "+d"(c0), "+d"(c1)
+      : "d"(a), "d"(b));
 }
 
-// One BK x 128 operand tile (BK = 16 or 32): rows k0 .. k0 + BK of the k-strided matrix X (leading dimension ldx), columns
-// i0 .. i0 + 128, zero-filled beyond (rows, K). `aligned` = every 16-byte chunk is 16-byte aligned in
-// global memory (even ldx, even i0, 16-byte aligned base); otherwise 8-byte copies.
-template <int BK>
+// One BK x W operand tile (pitch W + 4): rows k0 .. k0 + BK of the k-strided matrix X (leading dimension
+// ldx), columns i0 .. i0 + W, zero-filled beyond (rows, K). `aligned` = every 16-byte chunk is 16-byte
+// aligned in global memory (even ldx, even i0, 16-byte aligned base); otherwise 8-byte copies.
+template <int BK, int W, int THREADS>
 __device__ __forceinline__ void load_tile(double* dst, const double* __restrict__ X, int64_t ldx, int rows, int K, int i0,
                                           int k0, bool aligned) {
+  constexpr int LD = W + 4;
   if (aligned) {
-    // BK rows x 64 chunks of 2 doubles
+    constexpr int CH = W / 2;  // 16-byte chunks per row
 #pragma unroll
-    for (int q = 0; q < BK * 64 / GEMM_THREADS; ++q) {
-      const int c = threadIdx.x + q * GEMM_THREADS;
-      const int kk = c >> 6, ch = c & 63;
+    for (int q = 0; q < BK * CH / THREADS; ++q) {
+      const int c = threadIdx.x + q * THREADS;
+      const int kk = c / CH, ch = c % CH;
       const int i = i0 + 2 * ch, k = k0 + kk;
       int bytes = 0;
       if (k < K) bytes = (i + 1 < rows) ? 16 : ((i < rows) ? 8 : 0);
-      cp_async16(dst + kk * LDT + 2 * ch, bytes ? (X + static_cast<int64_t>(k) * ldx + i) : X, bytes);
+      cp_async16(dst + kk * LD + 2 * ch, bytes ? (X + static_cast<int64_t>(k) * ldx + i) : X, bytes);
     }
   } else {
 #pragma unroll
-    for (int q = 0; q < BK * 128 / GEMM_THREADS; ++q) {
-      const int c = threadIdx.x + q * GEMM_THREADS;
-      const int kk = c >> 7, ii = c & 127;
+    for (int q = 0; q < BK * W / THREADS; ++q) {
+      const int c = threadIdx.x + q * THREADS;
+      const int kk = c / W, ii = c % W;
       const int i = i0 + ii, k = k0 + kk;
       const bool ok = (k < K) && (i < rows);
-      cp_async8(dst + kk * LDT + ii, ok ? (X + static_cast<int64_t>(k) * ldx + i) : X, ok ? 8 : 0);
+      cp_async8(dst + kk * LD + ii, ok ? (X + static_cast<int64_t>(k) * ldx + i) : X, ok ? 8 : 0);
     }
   }
 }
@@ -87,8 +90,12 @@ __device__ __forceinline__ void load_tile(double* dst, const double* __restrict_
 }  // namespace
 
 // C(i, j) at Cbase + col_off(j) + i, where col_off maps a column to its storage offset (see DenseMap).
-template <bool LOWER, int EPI, int BK, int STAGES>
-__global__ void __launch_bounds__(GEMM_THREADS, 1) dgemm_nt_kernel(GemmArgs g) {
+// CTA tile 128 x BN_ (BN_ = 128: 16 warps, one CTA per SM; BN_ = 64: 8 warps, two CTAs per SM so that one
+// CTA's read-modify-write epilogue overlaps the other's tensor-core main loop).
+template <bool LOWER, int EPI, int BN_, int BK, int STAGES>
+__global__ void __launch_bounds__(gemm_threads(BN_), BN_ == 64 ? 2 : 1) dgemm_nt_kernel(GemmArgs g) {
+  constexpr int THREADS = gemm_threads(BN_);
+  constexpr int LDB = BN_ + 4;
   extern __shared__ __align__(16) double smem_d[];
   double* As = smem_d;
   double* Bs = smem_d + static_cast<size_t>(STAGES) * BK * LDT;
@@ -97,115 +104,149 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) dgemm_nt_kernel(GemmArgs g) {
   const int lr = lane >> 2, lc = lane & 3;
   // Persistent CTAs: the grid is capped (launch_dgemm_nt leaves a few SMs to the panel stream of the
   // factorisation, whose small kernels would otherwise queue behind whole tiles) and every CTA walks the
-  // tile list with stride gridDim.x. LOWER: only tiles tn <= tm, enumerated row by row.
-  const int tiles_m = (g.M + BM - 1) / BM, tiles_n = (g.N + BN - 1) / BN;
+  // tile list with stride gridDim.x. LOWER: only the tiles that intersect i >= j, enumerated row by row:
+  // row tm holds min(q (tm + 1), tiles_n) tiles with q = 128 / BN_.
+  constexpr int Q = BM / BN_;
+  const int tiles_m = (g.M + BM - 1) / BM, tiles_n = (g.N + BN_ - 1) / BN_;
   const int64_t n_tiles = LOWER ? g.n_tiles_lower : static_cast<int64_t>(tiles_m) * tiles_n;
+  const int t_full = min(tiles_m, tiles_n / Q);  // rows whose tile count is still growing
+  const int64_t tri = static_cast<int64_t>(Q) * t_full * (t_full + 1) / 2;
   for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-  int tm, tn;
-  if (LOWER) {
-    // tile -> (tm, tn): rows tm < tiles_n hold tm + 1 tiles, later rows hold tiles_n
-    const int64_t tri = static_cast<int64_t>(tiles_n) * (tiles_n + 1) / 2;
-    if (tile < tri) {
-      tm = static_cast<int>((sqrt(8.0 * static_cast<double>(tile) + 1.0) - 1.0) * 0.5);
-      while (static_cast<int64_t>(tm) * (tm + 1) / 2 > tile) --tm;
-      while (static_cast<int64_t>(tm + 1) * (tm + 2) / 2 <= tile) ++tm;
-      tn = static_cast<int>(tile - static_cast<int64_t>(tm) * (tm + 1) / 2);
+    int tm, tn;
+    if (LOWER) {
+      if (tile < tri) {
+        // largest tm with Q tm (tm + 1) / 2 <= tile
+        tm = static_cast<int>((sqrt(8.0 * static_cast<double>(tile) / Q + 1.0) - 1.0) * 0.5);
+        while (static_cast<int64_t>(Q) * tm * (tm + 1) / 2 > tile) --tm;
+        while (static_cast<int64_t>(Q) * (tm + 1) * (tm + 2) / 2 <= tile) ++tm;
+        tn = static_cast<int>(tile - static_cast<int64_t>(Q) * tm * (tm + 1) / 2);
+      } else {
+        const int64_t rest = tile - tri;
+        tm = t_full + static_cast<int>(rest / tiles_n);
+        tn = static_cast<int>(rest - static_cast<int64_t>(tm - t_full) * tiles_n);
+      }
     } else {
-      const int64_t rest = tile - tri;
-      tm = tiles_n + static_cast<int>(rest / tiles_n);
-      tn = static_cast<int>(rest - static_cast<int64_t>(tm - tiles_n) * tiles_n);
+      tm = static_cast<int>(tile / tiles_n);
+      tn = static_cast<int>(tile - static_cast<int64_t>(tm) * tiles_n);
     }
-  } else {
-    tm = static_cast<int>(tile / tiles_n);
-    tn = static_cast<int>(tile - static_cast<int64_t>(tm) * tiles_n);
-  }
-  const int m0 = tm * BM, n0 = tn * BN;
-  const bool same = LOWER && (tm == tn) && (g.A == g.B) && (g.lda == g.ldb);  // diagonal tile of a syrk: one operand
-  __syncthreads();  // the previous tile's shared-memory stages are free
-
-  double acc[4][4][2];
-#pragma unroll
-  for (int i = 0; i < 4; ++i)
-#pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
-
-  const int nk = (g.K + BK - 1) / BK;
-  // prologue
-#pragma unroll
-  for (int s = 0; s < STAGES - 1; ++s) {
-    if (s < nk) {
-      load_tile<BK>(As + s * BK * LDT, g.A, g.lda, g.M, g.K, m0, s * BK, g.a_aligned);
-      if (!same) load_tile<BK>(Bs + s * BK * LDT, g.B, g.ldb, g.N, g.K, n0, s * BK, g.b_aligned);
+    const int m0 = tm * BM, n0 = tn * BN_;
+    if (EPI == 2) {
+      // block-cyclic ownership of the column blocks: this rank updates only the tiles of its own blocks
+      const int blk = (g.col_base + n0) / g.map.nb;
+      if (blk % g.map.ranks != g.rank) continue;
     }
-    cp_async_commit();
-  }
-  for (int kt = 0; kt < nk; ++kt) {
-    cp_async_wait<STAGES - 2>();
-    __syncthreads();
-    // prefetch the tile STAGES - 1 ahead into the slot that was consumed in the previous iteration
-    {
-      const int nt = kt + STAGES - 1;
-      if (nt < nk) {
-        const int s = nt % STAGES;
-        load_tile<BK>(As + s * BK * LDT, g.A, g.lda, g.M, g.K, m0, nt * BK, g.a_aligned);
-        if (!same) load_tile<BK>(Bs + s * BK * LDT, g.B, g.ldb, g.N, g.K, n0, nt * BK, g.b_aligned);
+    const bool same = (BN_ == BM) && LOWER && (tm == tn) && (g.A == g.B) && (g.lda == g.ldb);  // diagonal syrk tile
+    __syncthreads();  // the previous tile's shared-memory stages are free
+
+    double acc[4][4][2];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+    const int nk = (g.K + BK - 1) / BK;
+#pragma unroll
+    for (int s = 0; s < STAGES - 1; ++s) {
+      if (s < nk) {
+        load_tile<BK, BM, THREADS>(As + s * BK * LDT, g.A, g.lda, g.M, g.K, m0, s * BK, g.a_aligned);
+        if (!same) load_tile<BK, BN_, THREADS>(Bs + s * BK * LDB, g.B, g.ldb, g.N, g.K, n0, s * BK, g.b_aligned);
       }
       cp_async_commit();
     }
-    const double* a_s = As + (kt % STAGES) * BK * LDT;
-    const double* b_s = same ? a_s : (Bs + (kt % STAGES) * BK * LDT);
-#pragma unroll
-    for (int ks = 0; ks < BK / 4; ++ks) {
-      double af[4], bf[4];
-      const double* ap = a_s + (ks * 4 + lc) * LDT + wm + lr;
-      const double* bp = b_s + (ks * 4 + lc) * LDT + wn + lr;
-#pragma unroll
-      for (int i = 0; i < 4; ++i) af[i] = ap[8 * i];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) bf[j] = bp[8 * j];
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
-    }
-  }
-  cp_async_wait<0>();
-
-  // epilogue: accumulator (i, j) holds rows m0 + wm + 8 i + lr, columns n0 + wn + 8 j + 2 lc + {0, 1}.
-  // Per output column the 4 read-modify-writes of a thread are issued as 4 loads, then 4 stores, so
-  // that they overlap instead of forming a load -> store chain.
-  int rowidx[4];
-  bool rowok[4];
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int m = m0 + wm + 8 * i + lr;
-    rowok[i] = m < g.M;
-    rowidx[i] = (EPI == 1) ? (rowok[i] ? __ldg(g.cols + m) : 0) : m;
-  }
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-#pragma unroll
-    for (int e = 0; e < 2; ++e) {
-      const int n = n0 + wn + 8 * j + 2 * lc + e;
-      if (n >= g.N) continue;
-      double* ccol = (EPI == 0) ? (g.C + static_cast<int64_t>(n) * g.ldc) : (g.C + g.map.col_offset(__ldg(g.cols + n)));
-      double old[4];
-      bool ok[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        ok[i] = rowok[i] && !(LOWER && (m0 + wm + 8 * i + lr) < n);
-        old[i] = (ok[i] && g.beta != 0.0) ? ccol[rowidx[i]] : 0.0;
+    for (int kt = 0; kt < nk; ++kt) {
+      cp_async_wait<STAGES - 2>();
+      __syncthreads();
+      {
+        // prefetch the tile STAGES - 1 ahead into the slot that was consumed in the previous iteration
+        const int nt = kt + STAGES - 1;
+        if (nt < nk) {
+          const int s = nt % STAGES;
+          load_tile<BK, BM, THREADS>(As + s * BK * LDT, g.A, g.lda, g.M, g.K, m0, nt * BK, g.a_aligned);
+          if (!same) load_tile<BK, BN_, THREADS>(Bs + s * BK * LDB, g.B, g.ldb, g.N, g.K, n0, nt * BK, g.b_aligned);
+        }
+        cp_async_commit();
       }
+      const double* a_s = As + (kt % STAGES) * BK * LDT;
+      const double* b_s = same ? a_s : (Bs + (kt % STAGES) * BK * LDB);
+      const int ldb_s = same ? LDT : LDB;
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
-        if (ok[i]) ccol[rowidx[i]] = fma(g.beta, old[i], g.alpha * acc[i][j][e]);
+      for (int ks = 0; ks < BK / 4; ++ks) {
+        double af[4], bf[4];
+        const double* ap = a_s + (ks * 4 + lc) * LDT + wm + lr;
+        const double* bp = b_s + (ks * 4 + lc) * ldb_s + wn + lr;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) af[i] = ap[8 * i];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) bf[j] = bp[8 * j];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+      }
     }
-  }
+    cp_async_wait<0>();
+
+    // epilogue: accumulator (i, j) holds rows m0 + wm + 8 i + lr, columns n0 + wn + 8 j + 2 lc + {0, 1}.
+    // Per output column the 4 read-modify-writes of a thread are issued as 4 loads, then 4 stores, so
+    // that they overlap instead of forming a load -> store chain.
+    int rowidx[4];
+    bool rowok[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int m = m0 + wm + 8 * i + lr;
+      rowok[i] = m < g.M;
+      rowidx[i] = (EPI == 1) ? (rowok[i] ? __ldg(g.cols + m) : 0) : m;
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int n = n0 + wn + 8 * j + 2 * lc + e;
+        if (n >= g.N) continue;
+        double* ccol = (EPI == 0) ? (g.C + static_cast<int64_t>(n) * g.ldc)
+                                  : (EPI == 1 ? (g.C + g.map.col_offset(__ldg(g.cols + n)))
+                                              : (g.C + g.map.col_offset(g.col_base + n) + g.col_base));
+        double old[4];
+        bool ok[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          ok[i] = rowok[i] && !(LOWER && (m0 + wm + 8 * i + lr) < n);
+          old[i] = (ok[i] && g.beta != 0.0) ? ccol[rowidx[i]] : 0.0;
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          if (ok[i]) ccol[rowidx[i]] = fma(g.beta, old[i], g.alpha * acc[i][j][e]);
+      }
+    }
   }  // tile loop
 }
 
 static int g_gemm_reserve_sms = 0;
 void set_gemm_sm_reserve(int n) { g_gemm_reserve_sms = n < 0 ? 0 : n; }
+
+namespace {
+template <int BN_, int BK, int STAGES>
+void configure_gemm_variant() {
+  const int smem = static_cast<int>(gemm_smem(BN_, BK, STAGES));
+  cudaFuncSetAttribute(dgemm_nt_kernel<true, 0, BN_, BK, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  cudaFuncSetAttribute(dgemm_nt_kernel<false, 0, BN_, BK, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  cudaFuncSetAttribute(dgemm_nt_kernel<true, 1, BN_, BK, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  cudaFuncSetAttribute(dgemm_nt_kernel<true, 2, BN_, BK, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+}
+template <int BN_, int BK, int STAGES>
+void launch_gemm_variant(const GemmArgs& g, bool lower, bool scatter, unsigned grid, cudaStream_t s) {
+  const size_t smem = gemm_smem(BN_, BK, STAGES);
+  constexpr int T = gemm_threads(BN_);
+  if (g.owned_only)
+    dgemm_nt_kernel<true, 2, BN_, BK, STAGES><<<grid, T, smem, s>>>(g);
+  else if (scatter)
+    dgemm_nt_kernel<true, 1, BN_, BK, STAGES><<<grid, T, smem, s>>>(g);
+  else if (lower)
+    dgemm_nt_kernel<true, 0, BN_, BK, STAGES><<<grid, T, smem, s>>>(g);
+  else
+    dgemm_nt_kernel<false, 0, BN_, BK, STAGES><<<grid, T, smem, s>>>(g);
+}
+}  // namespace
 
 int launch_dgemm_nt(const GemmArgs& g_in, bool lower, bool scatter, cudaStream_t s, bool leave_sms) {
   if (g_in.M <= 0 || g_in.N <= 0) return 0;
@@ -214,46 +255,39 @@ int launch_dgemm_nt(const GemmArgs& g_in, bool lower, bool scatter, cudaStream_t
   int dev = 0;
   cudaGetDevice(&dev);
   bool& configured = configured_dev[dev & 63];  // function attributes are per device
-  static int variant = -1;  // B200BA_GEMM_BK=16 (4 stages) | 32 (3 stages)
-  if (variant < 0) variant = (getenv("B200BA_GEMM_BK") && atoi(getenv("B200BA_GEMM_BK")) == 16) ? 16 : 32;
+  // B200BA_GEMM=64 (default: 128 x 64 tiles, BK 16 x 4 stages, 2 CTAs / SM) | 128 (128 x 128 tiles, BK 32 x 3
+  // stages, 1 CTA / SM) | 12816 (128 x 128, BK 16 x 4 stages)
+  static int variant = -1;
+  if (variant < 0) variant = getenv("B200BA_GEMM") ? atoi(getenv("B200BA_GEMM")) : 64;
   if (!configured) {
-    cudaFuncSetAttribute(dgemm_nt_kernel<true, 0, 16, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(gemm_smem(16, 4)));
-    cudaFuncSetAttribute(dgemm_nt_kernel<false, 0, 16, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(gemm_smem(16, 4)));
-    cudaFuncSetAttribute(dgemm_nt_kernel<true, 1, 16, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(gemm_smem(16, 4)));
-    cudaFuncSetAttribute(dgemm_nt_kernel<true, 0, 32, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(gemm_smem(32, 3)));
-    cudaFuncSetAttribute(dgemm_nt_kernel<false, 0, 32, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(gemm_smem(32, 3)));
-    cudaFuncSetAttribute(dgemm_nt_kernel<true, 1, 32, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(gemm_smem(32, 3)));
+    configure_gemm_variant<64, 16, 4>();
+    configure_gemm_variant<128, 32, 3>();
+    configure_gemm_variant<128, 16, 4>();
     cudaDeviceGetAttribute(&sm_count[dev & 63], cudaDevAttrMultiProcessorCount, dev);
     configured = true;
   }
   GemmArgs g = g_in;
-  const int64_t tm = (g.M + BM - 1) / BM, tn = (g.N + BN - 1) / BN;
+  const int bn = (variant == 64) ? 64 : 128;
+  const int q = BM / bn;
+  const int64_t tm = (g.M + BM - 1) / BM, tn = (g.N + bn - 1) / bn;
+  const bool tri_enum = lower || scatter || g.owned_only;
   int64_t n_tiles;
-  if (lower || scatter) {
-    // rows tm' < tn hold tm' + 1 tiles, the remaining rows tn tiles each (tiles with tn' <= tm')
-    const int64_t tnn = std::min(tm, tn);
-    n_tiles = tnn * (tnn + 1) / 2 + (tm - tnn) * tn;
+  if (tri_enum) {
+    const int64_t t_full = std::min<int64_t>(tm, tn / q);
+    n_tiles = q * t_full * (t_full + 1) / 2 + (tm - t_full) * tn;
     g.n_tiles_lower = n_tiles;
   } else {
     n_tiles = tm * tn;
   }
-  int cap = std::max(1, sm_count[dev & 63] - (leave_sms ? g_gemm_reserve_sms : 0));
+  const int per_sm = (bn == 64) ? 2 : 1;
+  const int cap = std::max(1, (sm_count[dev & 63] - (leave_sms ? g_gemm_reserve_sms : 0)) * per_sm);
   const unsigned grid = static_cast<unsigned>(std::min<int64_t>(n_tiles, cap));
-  if (variant == 16) {
-    if (scatter)
-      dgemm_nt_kernel<true, 1, 16, 4><<<grid, GEMM_THREADS, gemm_smem(16, 4), s>>>(g);
-    else if (lower)
-      dgemm_nt_kernel<true, 0, 16, 4><<<grid, GEMM_THREADS, gemm_smem(16, 4), s>>>(g);
-    else
-      dgemm_nt_kernel<false, 0, 16, 4><<<grid, GEMM_THREADS, gemm_smem(16, 4), s>>>(g);
-  } else {
-    if (scatter)
-      dgemm_nt_kernel<true, 1, 32, 3><<<grid, GEMM_THREADS, gemm_smem(32, 3), s>>>(g);
-    else if (lower)
-      dgemm_nt_kernel<true, 0, 32, 3><<<grid, GEMM_THREADS, gemm_smem(32, 3), s>>>(g);
-    else
-      dgemm_nt_kernel<false, 0, 32, 3><<<grid, GEMM_THREADS, gemm_smem(32, 3), s>>>(g);
-  }
+  if (variant == 64)
+    launch_gemm_variant<64, 16, 4>(g, tri_enum, scatter, grid, s);
+  else if (variant == 12816)
+    launch_gemm_variant<128, 16, 4>(g, tri_enum, scatter, grid, s);
+  else
+    launch_gemm_variant<128, 32, 3>(g, tri_enum, scatter, grid, s);
   return cudaGetLastError() == cudaSuccess ? 0 : 1;
 }
 
@@ -432,8 +466,10 @@ __global__ void __launch_bounds__(TS_THREADS)
     // y_i = sum_{c <= i} Linv(i, c) b_c : 2 threads per row (even / odd c), combined through shared memory
     const int i = tid & 127, half = tid >> 7;
     double acc = 0.0;
-    if (i < live)
-      for (int c = half; c <= i; c += 2) acc = fma(Linv[c * PT + i], b[c], acc);
+    if (i < live) {
+#pragma unroll 8
+      for (int c = half; c <= i; c += 2) acc = fma(__ldg(Linv + c * PT + i), b[c], acc);
+    }
     if (half == 1) y[i] = acc;
     __syncthreads();
     if (half == 0) y[i] += acc;
@@ -479,8 +515,10 @@ __global__ void __launch_bounds__(TS_THREADS)
     // x_j = sum_{i >= j} Linv(i, j) y_i : 2 threads per entry (even / odd i)
     const int j = tid & 127, half = tid >> 7;
     double acc = 0.0;
-    if (j < live)
-      for (int i = j + half; i < live; i += 2) acc = fma(Linv[j * PT + i], yt[i], acc);
+    if (j < live) {
+#pragma unroll 8
+      for (int i = j + half; i < live; i += 2) acc = fma(__ldg(Linv + j * PT + i), yt[i], acc);
+    }
     if (half == 1) x[j] = acc;
     __syncthreads();
     if (half == 0) x[j] += acc;
@@ -620,22 +658,39 @@ int dense_factor(DenseCtx* d) {
         return 1;
     }
     cudaEventRecord(d->ev_ready[k & 1], sp);
-    // look-ahead: the owner of the next block column updates it first, on the panel stream
+    // look-ahead: the owner of the next block column updates it FIRST (on the main stream, with the whole
+    // GPU), hands it to the panel stream, and only then applies panel k to the rest of its columns. The
+    // panel stream factors block k + 1 on the SMs the persistent rest-update leaves free.
+    cudaStreamWaitEvent(sm, d->ev_ready[k & 1], 0);
     int first_rest = k + 1;
     if (k + 1 < d->nblk && owner(k + 1) == me) {
-      if (k > 0) cudaStreamWaitEvent(sp, d->ev_main[(k - 1) & 1], 0);
-      if (update(k, k + 1, k + 1, sp, false)) return 1;
+      if (update(k, k + 1, k + 1, sm, false)) return 1;
+      cudaEventRecord(d->ev_main[k & 1], sm);
+      cudaStreamWaitEvent(sp, d->ev_main[k & 1], 0);
       first_rest = k + 2;
     }
-    cudaStreamWaitEvent(sm, d->ev_ready[k & 1], 0);
     if (R == 1) {
       if (first_rest < d->nblk && update(k, first_rest, d->nblk - 1, sm, true)) return 1;
-    } else {
-      for (int j = first_rest; j < d->nblk; ++j)
-        if (owner(j) == me && update(k, j, j, sm, true)) return 1;
+    } else if (first_rest < d->nblk) {
+      // one launch over the whole trailing matrix; the kernel skips the tiles of column blocks other ranks own
+      const int k0u = k * NB, kwu = std::min(NB, n - k0u), j0 = first_rest * NB;
+      GemmArgs g{};
+      g.M = g.N = n - j0;
+      g.K = kwu;
+      g.A = g.B = d->Lpack + d->panel_off[k] + (j0 - k0u);
+      g.lda = g.ldb = d->panel_h[k];
+      g.C = d->S;
+      g.alpha = -1.0;
+      g.beta = 1.0;
+      g.a_aligned = g.b_aligned = gemm_operand_aligned(g.A, g.lda);
+      g.map = d->map;
+      g.owned_only = true;
+      g.rank = me;
+      g.col_base = j0;
+      if (launch_dgemm_nt(g, true, false, sm, true)) return 1;
     }
-    cudaEventRecord(d->ev_main[k & 1], sm);
   }
+  // the last panel was factored on the panel stream: join
   cudaEventRecord(d->ev_misc, sp);
   cudaStreamWaitEvent(sm, d->ev_misc, 0);
   return cudaGetLastError() == cudaSuccess ? 0 : 1;

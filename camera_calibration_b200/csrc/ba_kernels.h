@@ -99,6 +99,10 @@ struct GemmArgs {
   const int* cols;
   DenseMap map;
   int64_t n_tiles_lower;  // set by launch_dgemm_nt
+  // owned-only trailing update of the block-cyclic factorisation: C = base of S, column n of the product is
+  // global column col_base + n (rows likewise); tiles of column blocks owned by other ranks are skipped
+  bool owned_only;
+  int rank, col_base;
 };
 inline bool gemm_operand_aligned(const double* p, int64_t ld) {
   return (reinterpret_cast<uintptr_t>(p) % 16 == 0) && (ld % 2 == 0);

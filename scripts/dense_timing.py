@@ -7,7 +7,7 @@ rng = np.random.default_rng(0)
 R = rng.uniform(-1, 1, (n, n))
 A = R + R.T + 2.5 * n * np.eye(n)   # diagonally dominant: SPD
 b = rng.standard_normal(n)
-for nb in (256, 128, 384):
+for nb in (256, 512):
     for rep in range(2):
         x, fm, sm = api.dense_cholesky_solve(A, b, nb)
     r = np.abs(A @ x - b).max()
