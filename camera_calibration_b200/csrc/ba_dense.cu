@@ -317,16 +317,52 @@ __device__ __forceinline__ void load_lower_tile(double* L, const double* __restr
   }
 }
 
-// Register-resident right-looking Cholesky: thread t owns row r = t & 127 and the 32 columns c = (t >> 7) + 4 m of
-// the tile in registers. Step j (fully unrolled, so every register index is a compile-time constant): the
-// owners of column j publish it un-scaled through a double-buffered shared-memory column; everybody then
-// updates its own columns c > j with a(r, c) -= a(r, j) a(c, j) / a(j, j) -- one barrier, one reciprocal and
-// <= 32 broadcast-load + FMA pairs per step -- and the owners keep L(r, j) = a(r, j) / sqrt(a(j, j)).
+// Register-resident right-looking Cholesky: thread t owns row r = t & 127 and the columns c = (t >> 7) + 4 m of
+// the tile in registers, as a window that slides with the factorisation: a[i] is column grp + 4 (jo + i) while
+// the outer iteration jo handles the four columns 4 jo .. 4 jo + 3 (one per thread group), after which the
+// window shifts by one register. All register indices are compile-time constants with a loop body of a few
+// hundred instructions (a fully unrolled 128-step version is 180 KB of code and streams through the
+// instruction cache on every launch). Step j: the owners of column j publish it un-scaled through a
+// double-buffered shared-memory column, the owner of the diagonal adds 1 / sqrt(a_jj) (the only
+// transcendental on the critical path); after ONE barrier everybody updates its own columns c > j with
+// a(r, c) -= a(r, j) a(c, j) / a_jj, and the owners store L(r, j) = a(r, j) / sqrt(a_jj) straight to memory.
+// The window length W shrinks in four segments (32, 24, 16, 8 live columns).
+template <int W>
+__device__ __forceinline__ void potrf_segment(double (&a)[32], double (*colbuf)[2 * PT + 1], int jo_begin, int jo_end, int r,
+                                              int grp, double* __restrict__ A, int64_t lda, int n, bool& bad) {
+#pragma unroll 1
+  for (int jo = jo_begin; jo < jo_end; ++jo) {
+#pragma unroll
+    for (int g4 = 0; g4 < 4; ++g4) {
+      const int j = 4 * jo + g4;
+      double* cb = colbuf[g4 & 1];
+      if (grp == g4) {
+        cb[r] = (r >= j) ? a[0] : 0.0;
+        if (r == j) cb[2 * PT] = rsqrt(a[0]);
+      }
+      __syncthreads();
+      const double d = cb[j], rs = cb[2 * PT];
+      bad |= !(d > 0.0);
+      const double lrj = cb[r] * (rs * rs);
+      const double* cc = cb + grp + 4 * jo;  // cc[4 i] = a(c_i, j) for this thread's window columns
+#pragma unroll
+      for (int i = 0; i < W; ++i)
+        if (i > 0 || grp > g4) a[i] = fma(-lrj, cc[4 * i], a[i]);
+      if (grp == g4 && r >= j && r < n && j < n) A[static_cast<int64_t>(j) * lda + r] = cb[r] * rs;  // L(r, j)
+    }
+#pragma unroll
+    for (int i = 0; i + 1 < W; ++i) a[i] = a[i + 1];
+    a[W - 1] = 0.0;
+  }
+}
+
 __global__ void __launch_bounds__(POTRF_THREADS, 1)
     potrf_tile_kernel(double* __restrict__ A, int64_t lda, int n, int* __restrict__ info) {
-  __shared__ double colbuf[2][PT + 1];  // column j un-scaled, + 1 / sqrt(a_jj) in the last slot
+  // column j un-scaled in [0, 128); zeros in [128, 256) (window columns beyond the tile); 1 / sqrt(a_jj) last
+  __shared__ double colbuf[2][2 * PT + 1];
   const int tid = threadIdx.x;
   const int r = tid & 127, grp = tid >> 7;
+  for (int e = tid; e < 2 * (2 * PT + 1); e += POTRF_THREADS) (&colbuf[0][0])[e] = 0.0;
   double a[32];
 #pragma unroll
   for (int m = 0; m < 32; ++m) {
@@ -335,34 +371,13 @@ __global__ void __launch_bounds__(POTRF_THREADS, 1)
     if (r < n && c < n && r >= c) v = A[static_cast<int64_t>(c) * lda + r];
     a[m] = v;
   }
+  __syncthreads();
   bool bad = false;
-#pragma unroll
-  for (int j = 0; j < PT; ++j) {
-    const int mj = j >> 2, gj = j & 3;
-    double* cb = colbuf[j & 1];
-    if (grp == gj) {
-      cb[r] = (r >= j) ? a[mj] : 0.0;
-      // the owner of the diagonal entry also publishes 1 / sqrt(a_jj): the only transcendental on the
-      // critical path of a step (rsqrt: <= 1 ulp; L(r, j) = a(r, j) * rs, the update uses rs^2 = 1 / a_jj)
-      if (r == j) cb[PT] = rsqrt(a[mj]);
-    }
-    __syncthreads();
-    const double d = cb[j], rs = cb[PT];
-    bad |= !(d > 0.0);
-    const double lrj = cb[r] * (rs * rs);
-#pragma unroll
-    for (int m = mj; m < 32; ++m) {
-      const int c = grp + 4 * m;
-      if (m > mj || grp > gj) a[m] = fma(-lrj, cb[c], a[m]);
-    }
-    if (grp == gj) a[mj] = cb[r] * rs;  // L(r, j); the diagonal becomes d * rs = sqrt(d)
-  }
+  potrf_segment<32>(a, colbuf, 0, 8, r, grp, A, lda, n, bad);
+  potrf_segment<24>(a, colbuf, 8, 16, r, grp, A, lda, n, bad);
+  potrf_segment<16>(a, colbuf, 16, 24, r, grp, A, lda, n, bad);
+  potrf_segment<8>(a, colbuf, 24, 32, r, grp, A, lda, n, bad);
   if (tid == 0 && bad) info[0] = 1;
-#pragma unroll
-  for (int m = 0; m < 32; ++m) {
-    const int c = grp + 4 * m;
-    if (r < n && c < n && r >= c) A[static_cast<int64_t>(c) * lda + r] = a[m];
-  }
 }
 
 // Inverse of the lower-triangular tile: one warp per column c solves L x = e_c by column-oriented forward
