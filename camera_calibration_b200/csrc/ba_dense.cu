@@ -468,6 +468,43 @@ void launch_add_diagonal_map(int n, double* S, const DenseMap& map, double lambd
 // each row's 128-term dot product split over 4 threads (32 independent loads in flight per thread
 // group instead of a 128-deep chain). CTA 0 also publishes y_t (into `yout`, a separate vector: the
 // other CTAs are still reading b_t).
+// y_i = sum_{c = c_lo, c_lo + 2, ... <= c_hi} M[c * PT + i] * v[c] for this thread's (row i, parity) with the loads of
+// eight terms issued together (a plain loop left them in a load -> FMA chain: one L2 round trip per term).
+__device__ __forceinline__ double tile_dot_strided(const double* __restrict__ M, const double* v, int i, int c_lo, int c_hi) {
+  double acc0 = 0.0, acc1 = 0.0;
+  int c = c_lo;
+  for (; c + 14 <= c_hi; c += 16) {
+    double l[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) l[q] = __ldg(M + (c + 2 * q) * PT + i);
+#pragma unroll
+    for (int q = 0; q < 8; q += 2) {
+      acc0 = fma(l[q], v[c + 2 * q], acc0);
+      acc1 = fma(l[q + 1], v[c + 2 * q + 2], acc1);
+    }
+  }
+  for (; c <= c_hi; c += 2) acc0 = fma(__ldg(M + c * PT + i), v[c], acc0);
+  return acc0 + acc1;
+}
+// same for the transposed product: x_j = sum_{i = i_lo, i_lo + 2, ... <= i_hi} M[j * PT + i] * v[i]
+__device__ __forceinline__ double tile_dot_contig(const double* __restrict__ M, const double* v, int j, int i_lo, int i_hi) {
+  double acc0 = 0.0, acc1 = 0.0;
+  int i = i_lo;
+  const double* col = M + j * PT;
+  for (; i + 14 <= i_hi; i += 16) {
+    double l[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) l[q] = __ldg(col + i + 2 * q);
+#pragma unroll
+    for (int q = 0; q < 8; q += 2) {
+      acc0 = fma(l[q], v[i + 2 * q], acc0);
+      acc1 = fma(l[q + 1], v[i + 2 * q + 2], acc1);
+    }
+  }
+  for (; i <= i_hi; i += 2) acc0 = fma(__ldg(col + i), v[i], acc0);
+  return acc0 + acc1;
+}
+
 constexpr int TS_THREADS = 256;
 constexpr int TS_ROWS = 64;
 __global__ void __launch_bounds__(TS_THREADS)
@@ -475,16 +512,15 @@ __global__ void __launch_bounds__(TS_THREADS)
                              const double* __restrict__ Linv, double* __restrict__ b /* at row c0 */,
                              double* __restrict__ yout /* at row c0 */) {
   __shared__ double y[PT];
+  __shared__ double bs[PT];
   __shared__ double part[4][TS_ROWS];
   const int tid = threadIdx.x;
+  if (tid < PT) bs[tid] = (tid < live) ? b[tid] : 0.0;
+  __syncthreads();
   {
     // y_i = sum_{c <= i} Linv(i, c) b_c : 2 threads per row (even / odd c), combined through shared memory
     const int i = tid & 127, half = tid >> 7;
-    double acc = 0.0;
-    if (i < live) {
-#pragma unroll 8
-      for (int c = half; c <= i; c += 2) acc = fma(__ldg(Linv + c * PT + i), b[c], acc);
-    }
+    const double acc = (i < live) ? tile_dot_strided(Linv, bs, i, half, i) : 0.0;
     if (half == 1) y[i] = acc;
     __syncthreads();
     if (half == 0) y[i] += acc;
@@ -496,9 +532,22 @@ __global__ void __launch_bounds__(TS_THREADS)
   double acc = 0.0;
   if (r < rows_below) {
     const double* Lp = P + static_cast<int64_t>(off_in_panel + cg * 32) * hk + off_in_panel + PT + r;
-#pragma unroll 8
-    for (int c = 0; c < 32; ++c)
-      if (cg * 32 + c < live) acc = fma(Lp[static_cast<int64_t>(c) * hk], y[cg * 32 + c], acc);
+    const double* yc = y + cg * 32;
+    const int cmax = min(32, live - cg * 32);
+    double acc1 = 0.0;
+    int c = 0;
+    for (; c + 8 <= cmax; c += 8) {
+      double l[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) l[q] = Lp[static_cast<int64_t>(c + q) * hk];
+#pragma unroll
+      for (int q = 0; q < 8; q += 2) {
+        acc = fma(l[q], yc[c + q], acc);
+        acc1 = fma(l[q + 1], yc[c + q + 1], acc1);
+      }
+    }
+    for (; c < cmax; ++c) acc = fma(Lp[static_cast<int64_t>(c) * hk], yc[c], acc);
+    acc += acc1;
   }
   part[cg][tid & 63] = acc;
   __syncthreads();
@@ -525,15 +574,14 @@ __global__ void __launch_bounds__(TS_THREADS)
                               const double* __restrict__ Linv, const double* __restrict__ yt /* y at row r0 */,
                               double* __restrict__ y /* full vector */, double* __restrict__ xout /* at row r0 */) {
   __shared__ double x[PT];
+  __shared__ double ys[PT];
   const int tid = threadIdx.x;
+  if (tid < PT) ys[tid] = (tid < live) ? yt[tid] : 0.0;
+  __syncthreads();
   {
     // x_j = sum_{i >= j} Linv(i, j) y_i : 2 threads per entry (even / odd i)
     const int j = tid & 127, half = tid >> 7;
-    double acc = 0.0;
-    if (j < live) {
-#pragma unroll 8
-      for (int i = j + half; i < live; i += 2) acc = fma(__ldg(Linv + j * PT + i), yt[i], acc);
-    }
+    const double acc = (j < live) ? tile_dot_contig(Linv, ys, j, j + half, live - 1) : 0.0;
     if (half == 1) x[j] = acc;
     __syncthreads();
     if (half == 0) x[j] += acc;
