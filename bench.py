@@ -532,10 +532,41 @@ def run_b200(args):
                                               "max_rel_cost_diff": max(abs(a - b) / abs(b) for a, b in zip(first_traj_costs[:m], ref[:m]))}
             except Exception:
                 pass
+        line["dense_path"] = ("in-tree sm_100a kernels: DMMA contraction with scatter epilogue, blocked Cholesky on packed "
+                              "panels, packed triangular solves (ba_dense.cu)") if os.environ.get("B200BA_DENSE", "own") not in ("lib", "0") \
+            else "cuBLAS dsyrk + cuSOLVER potrf / potrs (B200BA_DENSE=lib)"
+    adj.close()
+    adj = None
+    if rank == 0:
+        if world == 1 and os.environ.get("B200BA_DENSE", "own") not in ("lib", "0") and not args.no_library_comparison:
+            # the same steps with the dense phase on cuBLAS / cuSOLVER: the bar the in-tree kernels are measured against
+            os.environ["B200BA_DENSE"] = "lib"
+            try:
+                ladj = api.BundleAdjuster(sp.problem, local)
+                ladj.set_state(state0)
+                ladj.evaluate_device(opt)
+                lam_l, tot, n_l = -1.0, 0.0, 0
+                lph = {"schur": 0.0, "factor": 0.0, "solve": 0.0}
+                for i in range(7):
+                    opt.init_lambda = lam_l
+                    r_l = ladj.optimize(opt)
+                    lam_l = r_l.final_lambda
+                    if i >= 2:
+                        t_l = ladj.timings()
+                        tot += t_l.total_ms
+                        n_l += 1
+                        lph["schur"] += t_l.schur_ms
+                        lph["factor"] += t_l.factor_ms - t_l.solve_ms
+                        lph["solve"] += t_l.solve_ms
+                ladj.close()
+                line["library_path"] = {"ms_per_step": tot / n_l, "steps": n_l,
+                                        "phases_ms_per_step": {k: v / n_l for k, v in lph.items()},
+                                        "what": "cuBLAS dsyrk + cuSOLVER potrf / potrs for the dense phase, everything else identical"}
+            finally:
+                os.environ.pop("B200BA_DENSE", None)
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(sp, budget_s=args.cpu_budget)
         _emit(line)
-    adj.close()
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
@@ -554,6 +585,7 @@ def main():
                     help="--impl reference: stop after the first complete iteration that ends beyond this many seconds")
     ap.add_argument("--cpu-threads", type=int, default=0, help="host threads of the CPU arm (0 = all cores)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-library-comparison", action="store_true")
     args = ap.parse_args()
     # Exactly ONE line goes to stdout (the JSON line): libraries (NCCL prints its version banner)
     # write to fd 1 directly, so fd 1 is pointed at stderr until the result is ready.

@@ -190,3 +190,58 @@ def test_numeric_and_analytic_jacobians_agree(oracle_lib):
             a, b = en[k][both], ea[k][both]
             assert np.abs(a - b).max() < 2e-3 * np.abs(b).max(), (cfg, k)
         assert np.abs(en["residuals"][both] - ea["residuals"][both]).max() < 1e-9
+
+
+def test_fast_dense_schur_solve_agrees_with_plain(oracle_lib):
+    """The blocked, OpenMP-threaded dense kernels used at full size (oracle/ba_dense_fast.h: 4x3
+    register-tile product, blocked LDLT with the pivot sequence replayed up front) compute what the plain
+    loops compute: random block-arrow SPD systems, a diagonal that forces pivoting, 1 and 4 threads."""
+    import ctypes as C
+    rng = np.random.default_rng(5)
+    bs, nb, nd = 3, 60, 333
+    n = bs * nb + nd
+    J = rng.standard_normal((2 * n, n))
+    H = J.T @ J + 0.1 * np.eye(n)
+    for i in range(nb):
+        for j in range(nb):
+            if i != j:
+                H[i * bs:(i + 1) * bs, j * bs:(j + 1) * bs] = 0
+    H[bs * nb:, bs * nb:] += np.diag(rng.uniform(0, 500, nd))  # unsorted diagonal: the pivot order is not the identity
+    H += 40 * np.eye(n)
+    D = np.stack([np.triu(H[i * bs:(i + 1) * bs, i * bs:(i + 1) * bs]) for i in range(nb)])
+    B = np.ascontiguousarray(H[:bs * nb, bs * nb:])
+    Cm = np.ascontiguousarray(np.triu(H[bs * nb:, bs * nb:]))
+    b = rng.standard_normal(n)
+    x0 = oracle_lib.schur_solve(bs, D, B, Cm, b[:bs * nb], b[bs * nb:])
+    p = lambda a: np.ascontiguousarray(a).ctypes.data_as(C.POINTER(C.c_double))
+    for threads in (1, 4):
+        oracle_lib.set_threads(threads)
+        try:
+            x1 = np.zeros(n)
+            b1, b2 = np.ascontiguousarray(b[:bs * nb]), np.ascontiguousarray(b[bs * nb:])
+            Dc = np.ascontiguousarray(D)
+            oracle_lib.lib().oracle_schur_solve_fast(bs, nb, nd, p(Dc), p(B), p(Cm), p(b1), p(b2), p(x1))
+        finally:
+            oracle_lib.set_threads(1)
+        assert np.abs(x1 - x0).max() < 1e-10 * max(1.0, np.abs(x0).max())
+    assert np.abs(H @ x0 - b).max() < 1e-8 * np.abs(b).max() * n
+
+
+def test_threaded_evaluation_is_bitwise_the_sequential_one(oracle_lib):
+    """compute_mt (per-observation work in parallel, accumulation replayed in the reference's order): H, b,
+    cost and the LM trajectory are bitwise those of the single-threaded pass, NUMERIC and ANALYTIC."""
+    from camera_calibration_b200 import cabi, synthetic
+    sp = synthetic.make_problem(2, n_imagesets=6, lattice=(8, 6), image_size=(300, 220))
+    for mode in (cabi.JACOBIAN_NUMERIC, cabi.JACOBIAN_ANALYTIC):
+        opt = cabi.default_options(jacobian_mode=mode, max_iteration_count=2)
+        H0, b0, c0 = oracle_lib.build_system(sp.problem, sp.init_state, opt)
+        s0, r0 = oracle_lib.optimize(sp.problem, sp.init_state, opt)
+        oracle_lib.set_threads(4)
+        try:
+            H1, b1, c1 = oracle_lib.build_system(sp.problem, sp.init_state, opt)
+            s1, r1 = oracle_lib.optimize(sp.problem, sp.init_state, opt)
+        finally:
+            oracle_lib.set_threads(1)
+        assert np.array_equal(H0, H1) and np.array_equal(b0, b1) and c0 == c1
+        assert r0.trace() == r1.trace()
+        assert np.array_equal(s0.points, s1.points)
