@@ -90,6 +90,11 @@ def make_workload(args):
     if args.imagesets:
         kw["n_imagesets"] = args.imagesets
     cache = f"/tmp/b200ba_workload_c{args.config}_i{args.imagesets}_v2.pkl"
+    # a pre-generated copy shipped with the snapshot (workload_cache/, git-ignored: plain seeded synthetic data
+    # that every rank would otherwise regenerate for minutes of GPU-box time) takes precedence
+    shipped = os.path.join(ROOT, "workload_cache", os.path.basename(cache))
+    if os.path.exists(shipped):
+        cache = shipped
     if os.path.exists(cache):
         try:
             d = pickle.load(open(cache, "rb"))
@@ -101,17 +106,21 @@ def make_workload(args):
                     setattr(c, k, v)
                 cams.append(c)
             pb = FlatProblem(cams, d["n_imagesets"], d["n_points"], d["oi"], d["oc"], d["op"], d["oxy"])
-            mk = lambda t: FlatState(t[0], t[1], t[2], t[3], t[4])
+            zlp = lambda a: a if a is not None else np.zeros((len(d["oi"]), 2))  # all-zero caches are not stored
+            mk = lambda t: FlatState(t[0], t[1], t[2], t[3], zlp(t[4]))
             return synthetic.SyntheticProblem(d["name"], pb, mk(d["init"]), mk(d["gt"]), d["seed"], d["info"])
         except Exception:
             pass
     sp = synthetic.make_problem(args.config, **kw)
     try:
         p = sp.problem
-        st = lambda s: (s.points, s.rig_tr_global, s.camera_tr_rig, s.intrinsics, s.last_projection)
+        st = lambda s: (s.points, s.rig_tr_global, s.camera_tr_rig, s.intrinsics,
+                        None if (s.last_projection is None or not np.any(s.last_projection)) else s.last_projection)
         d = dict(cams=[{k: getattr(c, k) for k, _ in c._fields_} for c in p.cameras], n_imagesets=p.n_imagesets,
                  n_points=p.n_points, oi=p.obs_imageset, oc=p.obs_camera, op=p.obs_point, oxy=p.obs_xy,
                  init=st(sp.init_state), gt=st(sp.gt_state), seed=sp.seed, info=sp.info, name=sp.name)
+        if cache.startswith(os.path.join(ROOT, "workload_cache")):
+            cache = f"/tmp/b200ba_workload_c{args.config}_i{args.imagesets}_v2.pkl"
         tmp = cache + f".{os.getpid()}"
         pickle.dump(d, open(tmp, "wb"))
         os.replace(tmp, cache)

@@ -57,35 +57,72 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
       : "d"(a), "d"(b));
 }
 
-// One BK x W operand tile (pitch W + 4): rows k0 .. k0 + BK of the k-strided matrix X (leading dimension
-// ldx), columns i0 .. i0 + W, zero-filled beyond (rows, K). `aligned` = every 16-byte chunk is 16-byte
+// Loader of one operand's BK x W tiles (pitch W + 4): rows k0 .. k0 + BK of the k-strided matrix X (leading
+// dimension ldx), columns i0 .. i0 + W, zero-filled beyond (rows, K). Everything that does not change along k --
+// the source pointer of each of the thread's chunks, its byte count (row in range?), its shared-memory offset --
+// is computed ONCE per tile in init(); issue() only advances the pointers by BK rows and checks k < K. (The first
+// version recomputed the index arithmetic and four predicates per chunk in every k-iteration: with 2-4 warps per
+// scheduler that integer latency was a third of all stall samples.) `aligned` = every 16-byte chunk is 16-byte
 // aligned in global memory (even ldx, even i0, 16-byte aligned base); otherwise 8-byte copies.
 template <int BK, int W, int THREADS>
-__device__ __forceinline__ void load_tile(double* dst, const double* __restrict__ X, int64_t ldx, int rows, int K, int i0,
-                                          int k0, bool aligned) {
-  constexpr int LD = W + 4;
-  if (aligned) {
-    constexpr int CH = W / 2;  // 16-byte chunks per row
-#pragma unroll
-    for (int q = 0; q < BK * CH / THREADS; ++q) {
-      const int c = threadIdx.x + q * THREADS;
-      const int kk = c / CH, ch = c % CH;
-      const int i = i0 + 2 * ch, k = k0 + kk;
-      int bytes = 0;
-      if (k < K) bytes = (i + 1 < rows) ? 16 : ((i < rows) ? 8 : 0);
-      cp_async16(dst + kk * LD + 2 * ch, bytes ? (X + static_cast<int64_t>(k) * ldx + i) : X, bytes);
+struct TileLoader {
+  static constexpr int LD = W + 4;
+  static constexpr int CH = W / 2;               // 16-byte chunks per row
+  static constexpr int KS16 = THREADS / CH;      // rows between two chunks of one thread (aligned path)
+  static constexpr int KS8 = THREADS / W;        // ... (unaligned path)
+  static constexpr int Q16 = BK / KS16, Q8 = BK / KS8;
+  static_assert(THREADS % CH == 0 && THREADS % W == 0 && BK % KS16 == 0 && BK % KS8 == 0, "tile / thread count mismatch");
+  // all chunks of a thread sit in the same column(s) and KS rows apart: one pointer, one byte count
+  const double* src;   // chunk of row k0 + kk0
+  const double* base;
+  int64_t row_step;    // KS * ldx
+  int64_t tile_step;   // BK * ldx
+  int off0, kk0, bytes;
+  bool aligned;
+
+  __device__ __forceinline__ void init(const double* __restrict__ X, int64_t ldx, int rows, int i0, bool al) {
+    aligned = al;
+    base = X;
+    tile_step = static_cast<int64_t>(BK) * ldx;
+    int i;
+    if (al) {
+      kk0 = threadIdx.x / CH;
+      const int ch = threadIdx.x % CH;
+      i = i0 + 2 * ch;
+      off0 = kk0 * LD + 2 * ch;
+      bytes = (i + 1 < rows) ? 16 : ((i < rows) ? 8 : 0);
+      row_step = static_cast<int64_t>(KS16) * ldx;
+    } else {
+      kk0 = threadIdx.x / W;
+      const int ii = threadIdx.x % W;
+      i = i0 + ii;
+      off0 = kk0 * LD + ii;
+      bytes = (i < rows) ? 8 : 0;
+      row_step = static_cast<int64_t>(KS8) * ldx;
     }
-  } else {
-#pragma unroll
-    for (int q = 0; q < BK * W / THREADS; ++q) {
-      const int c = threadIdx.x + q * THREADS;
-      const int kk = c / W, ii = c % W;
-      const int i = i0 + ii, k = k0 + kk;
-      const bool ok = (k < K) && (i < rows);
-      cp_async8(dst + kk * LD + ii, ok ? (X + static_cast<int64_t>(k) * ldx + i) : X, ok ? 8 : 0);
-    }
+    src = X + static_cast<int64_t>(kk0) * ldx + min(i, max(rows - 1, 0));
   }
-}
+  // copies the tile whose first row is k0 into dst and advances to the next tile
+  __device__ __forceinline__ void issue(double* dst, int k0, int K) {
+    const double* p = src;
+    if (aligned) {
+#pragma unroll
+      for (int q = 0; q < Q16; ++q) {
+        const int nb = (k0 + kk0 + q * KS16 < K) ? bytes : 0;
+        cp_async16(dst + off0 + q * KS16 * LD, nb ? p : base, nb);
+        p += row_step;
+      }
+    } else {
+#pragma unroll
+      for (int q = 0; q < Q8; ++q) {
+        const int nb = (k0 + kk0 + q * KS8 < K) ? bytes : 0;
+        cp_async8(dst + off0 + q * KS8 * LD, nb ? p : base, nb);
+        p += row_step;
+      }
+    }
+    src += tile_step;
+  }
+};
 
 }  // namespace
 
@@ -145,11 +182,15 @@ __global__ void __launch_bounds__(gemm_threads(BN_), BN_ == 64 ? 2 : 1) dgemm_nt
       for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
     const int nk = (g.K + BK - 1) / BK;
+    TileLoader<BK, BM, THREADS> la;
+    TileLoader<BK, BN_, THREADS> lb;
+    la.init(g.A, g.lda, g.M, m0, g.a_aligned);
+    if (!same) lb.init(g.B, g.ldb, g.N, n0, g.b_aligned);
 #pragma unroll
     for (int s = 0; s < STAGES - 1; ++s) {
       if (s < nk) {
-        load_tile<BK, BM, THREADS>(As + s * BK * LDT, g.A, g.lda, g.M, g.K, m0, s * BK, g.a_aligned);
-        if (!same) load_tile<BK, BN_, THREADS>(Bs + s * BK * LDB, g.B, g.ldb, g.N, g.K, n0, s * BK, g.b_aligned);
+        la.issue(As + s * BK * LDT, s * BK, g.K);
+        if (!same) lb.issue(Bs + s * BK * LDB, s * BK, g.K);
       }
       cp_async_commit();
     }
@@ -161,8 +202,8 @@ __global__ void __launch_bounds__(gemm_threads(BN_), BN_ == 64 ? 2 : 1) dgemm_nt
         const int nt = kt + STAGES - 1;
         if (nt < nk) {
           const int s = nt % STAGES;
-          load_tile<BK, BM, THREADS>(As + s * BK * LDT, g.A, g.lda, g.M, g.K, m0, nt * BK, g.a_aligned);
-          if (!same) load_tile<BK, BN_, THREADS>(Bs + s * BK * LDB, g.B, g.ldb, g.N, g.K, n0, nt * BK, g.b_aligned);
+          la.issue(As + s * BK * LDT, nt * BK, g.K);
+          if (!same) lb.issue(Bs + s * BK * LDB, nt * BK, g.K);
         }
         cp_async_commit();
       }
@@ -267,7 +308,9 @@ int launch_dgemm_nt(const GemmArgs& g_in, bool lower, bool scatter, cudaStream_t
     configured = true;
   }
   GemmArgs g = g_in;
-  const int bn = (variant == 64) ? 64 : 128;
+  // an in-place product (C aliases A: the panel solve X <- X Linv^T, N = K = 128) must see ONE tile per row block:
+  // with 64-wide tiles the CTA of columns 0..63 would overwrite operand columns the CTA of columns 64..127 still reads
+  const int bn = (variant == 64 && !g.in_place) ? 64 : 128;
   const int q = BM / bn;
   const int64_t tm = (g.M + BM - 1) / BM, tn = (g.N + bn - 1) / bn;
   const bool tri_enum = lower || scatter || g.owned_only;
@@ -282,7 +325,7 @@ int launch_dgemm_nt(const GemmArgs& g_in, bool lower, bool scatter, cudaStream_t
   const int per_sm = (bn == 64) ? 2 : 1;
   const int cap = std::max(1, (sm_count[dev & 63] - (leave_sms ? g_gemm_reserve_sms : 0)) * per_sm);
   const unsigned grid = static_cast<unsigned>(std::min<int64_t>(n_tiles, cap));
-  if (variant == 64)
+  if (variant == 64 && !g.in_place)
     launch_gemm_variant<64, 16, 4>(g, tri_enum, scatter, grid, s);
   else if (variant == 12816)
     launch_gemm_variant<128, 16, 4>(g, tri_enum, scatter, grid, s);
@@ -688,6 +731,7 @@ int dense_factor(DenseCtx* d) {
           g.ldc = hk;
           g.alpha = 1.0;
           g.beta = 0.0;
+          g.in_place = true;
           g.a_aligned = gemm_operand_aligned(g.A, g.lda);
           g.b_aligned = gemm_operand_aligned(g.B, g.ldb);
           if (launch_dgemm_nt(g, false, false, sp)) return 1;

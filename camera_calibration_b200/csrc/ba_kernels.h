@@ -103,6 +103,7 @@ struct GemmArgs {
   // global column col_base + n (rows likewise); tiles of column blocks owned by other ranks are skipped
   bool owned_only;
   int rank, col_base;
+  bool in_place;  // C aliases A (N = K <= 128): forces one 128-wide tile per row block
 };
 inline bool gemm_operand_aligned(const double* p, int64_t ld) {
   return (reinterpret_cast<uintptr_t>(p) % 16 == 0) && (ld % 2 == 0);
