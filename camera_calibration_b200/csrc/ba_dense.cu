@@ -663,7 +663,8 @@ int dense_plan(DenseCtx* d, int n, int nb, int rank, int ranks) {
   for (int k = 0; k < d->nblk; ++k) {
     const int hk = n - k * nb;
     d->panel_h[k] = (hk + 1) / 2 * 2;
-    d->panel_off[k + 1] = d->panel_off[k] + static_cast<int64_t>(d->panel_h[k]) * nb;
+    // a panel region = hk x NB factor columns followed by the inverses of its diagonal tiles: ONE broadcast
+    d->panel_off[k + 1] = d->panel_off[k] + static_cast<int64_t>(d->panel_h[k]) * nb + static_cast<int64_t>(nb / PT) * PT * PT;
   }
   return 0;
 }
@@ -715,7 +716,7 @@ int dense_factor(DenseCtx* d) {
         if (c0 >= kw) break;
         const int live = std::min(PT, kw - c0);
         double* tile = P + static_cast<int64_t>(c0) * hk + c0;
-        double* Li = d->Linv + static_cast<int64_t>(k * sub_n + sub) * PT * PT;
+        double* Li = P + static_cast<int64_t>(hk) * NB + static_cast<int64_t>(sub) * PT * PT;
         if (launch_potrf_tile(tile, hk, live, Li, d->info, sp)) return 1;
         const int below = hlive - c0 - PT;
         if (below > 0) {
@@ -756,13 +757,8 @@ int dense_factor(DenseCtx* d) {
       }
     }
     if (R > 1) {
-      if (d->bcast(P, static_cast<size_t>(hk) * kw, owner(k), sp, d->user)) return 1;
-      if (owner(k) != me && d->bcast_linv) {
-        // the inverse tiles travel too (the triangular solves run on every rank)
-      }
-      if (d->bcast(d->Linv + static_cast<int64_t>(k) * sub_n * PT * PT, static_cast<size_t>(sub_n) * PT * PT, owner(k), sp,
-                   d->user))
-        return 1;
+      // the packed panel and the inverses of its diagonal tiles (stored right behind it) travel together
+      if (d->bcast(P, static_cast<size_t>(hk) * NB + static_cast<size_t>(sub_n) * PT * PT, owner(k), sp, d->user)) return 1;
     }
     cudaEventRecord(d->ev_ready[k & 1], sp);
     // look-ahead: the owner of the next block column updates it FIRST (on the main stream, with the whole
@@ -811,7 +807,7 @@ int dense_solve(DenseCtx* d, double* b) {
   const int sub_n = NB / PT;
   auto linv_of = [&](int t) {
     const int k = (t * PT) / NB, sub = (t * PT - k * NB) / PT;
-    return d->Linv + static_cast<int64_t>(k * sub_n + sub) * PT * PT;
+    return d->Lpack + d->panel_off[k] + static_cast<int64_t>(d->panel_h[k]) * NB + static_cast<int64_t>(sub) * PT * PT;
   };
   // forward: L y = b  (y is collected in d->tmp)
   for (int t = 0; t < d->ntiles; ++t) {
@@ -839,6 +835,67 @@ int dense_solve(DenseCtx* d, double* b) {
     }
   }
   return cudaGetLastError() == cudaSuccess ? 0 : 1;
+}
+
+
+// ------------------------------------------------------------------------------------------
+// matrix-vector products with the off-diagonal block B [rows][ld] row-major (reduced right-hand side and
+// back-substitution of the Schur solve, LV/lm_optimizer.h:1319,1366-1367). Fixed summation order.
+// ------------------------------------------------------------------------------------------
+// y[c] += alpha * sum_r B[r][c] u[r]: stage 1 sums 128-row slabs (coalesced along c), stage 2 the slabs
+constexpr int GV_ROWS = 128;
+__global__ void gemv_t_stage1_kernel(int rows, int cols, int64_t ld, const double* __restrict__ B,
+                                     const double* __restrict__ u, double* __restrict__ partial) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const int r0 = blockIdx.y * GV_ROWS, r1 = min(rows, r0 + GV_ROWS);
+  if (c >= cols) return;
+  double a0 = 0.0, a1 = 0.0;
+  int r = r0;
+  for (; r + 1 < r1; r += 2) {
+    a0 = fma(B[static_cast<int64_t>(r) * ld + c], u[r], a0);
+    a1 = fma(B[static_cast<int64_t>(r + 1) * ld + c], u[r + 1], a1);
+  }
+  if (r < r1) a0 = fma(B[static_cast<int64_t>(r) * ld + c], u[r], a0);
+  partial[static_cast<int64_t>(blockIdx.y) * cols + c] = a0 + a1;
+}
+__global__ void gemv_t_stage2_kernel(int slabs, int cols, const double* __restrict__ partial, double alpha,
+                                     double* __restrict__ y) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= cols) return;
+  double a = 0.0;
+  for (int s = 0; s < slabs; ++s) a += partial[static_cast<int64_t>(s) * cols + c];
+  y[c] = fma(alpha, a, y[c]);
+}
+// t[r] = sum_c B[r][c] x[c]: one warp per row
+__global__ void gemv_n_kernel(int rows, int cols, int64_t ld, const double* __restrict__ B, const double* __restrict__ x,
+                              double* __restrict__ t) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= rows) return;
+  const double* row = B + static_cast<int64_t>(warp) * ld;
+  double a0 = 0.0, a1 = 0.0;
+  int c = lane;
+  for (; c + 32 < cols; c += 64) {
+    a0 = fma(row[c], x[c], a0);
+    a1 = fma(row[c + 32], x[c + 32], a1);
+  }
+  if (c < cols) a0 = fma(row[c], x[c], a0);
+  double a = a0 + a1;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+  if (lane == 0) t[warp] = a;
+}
+int gemv_t_partial_size(int rows, int cols) { return ((rows + GV_ROWS - 1) / GV_ROWS) * std::max(cols, 1); }
+void launch_gemv_t(int rows, int cols, int64_t ld, const double* B, const double* u, double alpha, double* y, double* partial,
+                   cudaStream_t s) {
+  if (rows <= 0 || cols <= 0) return;
+  const int slabs = (rows + GV_ROWS - 1) / GV_ROWS;
+  dim3 grid((cols + 255) / 256, slabs);
+  gemv_t_stage1_kernel<<<grid, 256, 0, s>>>(rows, cols, ld, B, u, partial);
+  gemv_t_stage2_kernel<<<(cols + 255) / 256, 256, 0, s>>>(slabs, cols, partial, alpha, y);
+}
+void launch_gemv_n(int rows, int cols, int64_t ld, const double* B, const double* x, double* t, cudaStream_t s) {
+  if (rows <= 0) return;
+  gemv_n_kernel<<<(rows * 32 + 255) / 256, 256, 0, s>>>(rows, cols, ld, B, x, t);
 }
 
 }  // namespace b200ba

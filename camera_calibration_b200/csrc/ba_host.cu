@@ -177,6 +177,7 @@ struct b200ba_handle {
   int dense_nb = 256;                   // column-block width of the factorisation (B200BA_DENSE_NB, multiple of 128)
   cudaStream_t panel_stream = nullptr;  // panel factorisations + broadcasts (look-ahead)
   int* d_ident_cols = nullptr;          // 0 .. nd - 1 (scatter epilogue of the dense contraction with several ranks)
+  double* d_gemv_partial = nullptr;     // slab sums of the B^T u product
 
   // timings
   b200ba_timings timings{};
@@ -424,7 +425,6 @@ int plan_dense(b200ba_handle* h) {
   if (dev_alloc(h, &h->d_S, static_cast<size_t>(std::max<int64_t>(1, d.chunk * h->n_ranks)))) return 1;
   d.S = h->d_S;
   if (dev_alloc(h, &d.Lpack, static_cast<size_t>(std::max<int64_t>(1, d.panel_off[d.nblk])))) return 1;
-  if (dev_alloc(h, &d.Linv, static_cast<size_t>(std::max(1, d.nblk)) * (d.NB / 128) * 128 * 128)) return 1;
   if (dev_alloc(h, &d.tmp, std::max(1, nd))) return 1;
   if (dev_alloc(h, &d.d_panel_off, d.panel_off.size())) return 1;
   if (dev_alloc(h, &d.d_panel_h, d.panel_h.size())) return 1;
@@ -436,6 +436,7 @@ int plan_dense(b200ba_handle* h) {
     if (dev_alloc(h, &h->d_ident_cols, ident.size())) return 1;
     CUDA_TRY(h, cudaMemcpy(h->d_ident_cols, ident.data(), ident.size() * sizeof(int), cudaMemcpyHostToDevice));
   }
+  if (dev_alloc(h, &h->d_gemv_partial, static_cast<size_t>(gemv_t_partial_size(h->L.nbd, std::max(1, nd))))) return 1;
   // the un-owned chunks of S are never written by the contraction of a single rank but are read by nobody either;
   // zero once so that partial sums start clean
   CUDA_TRY(h, cudaMemset(h->d_S, 0, static_cast<size_t>(std::max<int64_t>(1, d.chunk * h->n_ranks)) * sizeof(double)));
@@ -950,7 +951,6 @@ int solve_system_own(b200ba_handle* h, double lambda, int* spd) {
   const Layout& L = h->L;
   DenseCtx& d = h->dn;
   const int nd = L.nd, R = h->n_ranks;
-  const double one = 1.0, minus_one = -1.0, zero = 0.0;
   {
     ScopedPhase ph(h, PH_SCHUR);
     CUDA_TRY(h, cudaMemsetAsync(h->d_fail, 0, sizeof(int), h->stream));
@@ -1047,9 +1047,8 @@ int solve_system_own(b200ba_handle* h, double lambda, int* spd) {
     if (h->rank == 0) launch_add_diagonal_map(nd, h->d_S, d.map, lambda, h->stream);
     // x_dense <- b_d - B^T u   (B, D, b are global after the per-build all-reduce)
     CUDA_TRY(h, cudaMemcpyAsync(h->d_x + L.nbd, h->sys.bd, nd * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
-    if (L.nbd > 0 && nd > 0)
-      CUBLAS_TRY(h, cublasDgemv(h->cublas, CUBLAS_OP_N, nd, L.nbd, &minus_one, h->sys.B, nd, h->d_u, 1, &one, h->d_x + L.nbd, 1));
-    h->timings.kernel_launches += 2;
+    if (L.nbd > 0 && nd > 0) launch_gemv_t(L.nbd, nd, nd, h->sys.B, h->d_u, -1.0, h->d_x + L.nbd, h->d_gemv_partial, h->stream);
+    h->timings.kernel_launches += 4;
   }
   if (R > 1 && nd > 0) {
     // partial sums -> the block columns each rank owns (in place: rank r keeps chunk r)
@@ -1089,7 +1088,7 @@ int solve_system_own(b200ba_handle* h, double lambda, int* spd) {
     ScopedPhase ph(h, PH_SCHUR);
     // t = B x_d ; x_block = u - D^-1 t   (W is never needed for the back-substitution)
     if (L.nbd > 0 && nd > 0)
-      CUBLAS_TRY(h, cublasDgemv(h->cublas, CUBLAS_OP_T, nd, L.nbd, &one, h->sys.B, nd, h->d_x + L.nbd, 1, &zero, h->d_y, 1));
+      launch_gemv_n(L.nbd, nd, nd, h->sys.B, h->d_x + L.nbd, h->d_y, h->stream);
     else if (L.nbd > 0)
       CUDA_TRY(h, cudaMemsetAsync(h->d_y, 0, L.nbd * sizeof(double), h->stream));
     launch_block_backsub2(L.bs, L.nblocks, h->d_Linv, h->d_u, h->d_y, h->d_x, h->stream);
@@ -1137,7 +1136,7 @@ void free_handle_buffers(b200ba_handle* h) {
   if (h->h_count) cudaFreeHost(h->h_count);
   h->h_count = nullptr;
   F(h->d_partial); F(h->d_scal); F(h->d_rot);
-  F(h->dn.Lpack); F(h->dn.Linv); F(h->dn.tmp); F(h->dn.d_panel_off); F(h->dn.d_panel_h); F(h->d_ident_cols);
+  F(h->dn.Lpack); F(h->dn.tmp); F(h->dn.d_panel_off); F(h->dn.d_panel_h); F(h->d_ident_cols); F(h->d_gemv_partial);
   h->dn.S = nullptr;
   h->dense_planned_n = -1;
   if (h->h_scal) cudaFreeHost(h->h_scal);
@@ -1891,7 +1890,6 @@ int b200ba_dense_cholesky_solve(int device, int32_t n, int32_t nb, const double*
   ok(cudaMalloc(reinterpret_cast<void**>(&dA), static_cast<size_t>(n) * n * sizeof(double)));
   ok(cudaMalloc(reinterpret_cast<void**>(&d.S), static_cast<size_t>(d.chunk) * sizeof(double)));
   ok(cudaMalloc(reinterpret_cast<void**>(&d.Lpack), static_cast<size_t>(d.panel_off[d.nblk]) * sizeof(double)));
-  ok(cudaMalloc(reinterpret_cast<void**>(&d.Linv), static_cast<size_t>(d.nblk) * (nb / 128) * 128 * 128 * sizeof(double)));
   ok(cudaMalloc(reinterpret_cast<void**>(&d.tmp), static_cast<size_t>(n) * sizeof(double)));
   ok(cudaMalloc(reinterpret_cast<void**>(&d.d_panel_off), d.panel_off.size() * sizeof(int64_t)));
   ok(cudaMalloc(reinterpret_cast<void**>(&d.d_panel_h), d.panel_h.size() * sizeof(int)));
@@ -1933,7 +1931,7 @@ int b200ba_dense_cholesky_solve(int device, int32_t n, int32_t nb, const double*
       rc = 4;
     }
   }
-  for (double* p : {dA, d.S, d.Lpack, d.Linv, d.tmp, db})
+  for (double* p : {dA, d.S, d.Lpack, d.tmp, db})
     if (p) cudaFree(p);
   if (d.d_panel_off) cudaFree(d.d_panel_off);
   if (d.d_panel_h) cudaFree(d.d_panel_h);

@@ -116,6 +116,11 @@ void set_gemm_sm_reserve(int n);
 // Cholesky of a 128 x 128 (live size n) column-major diagonal tile in place + Linv [128 x 128, ld 128].
 int launch_potrf_tile(double* A, int64_t lda, int n, double* Linv, int* info, cudaStream_t s);
 
+// y += alpha B^T u (two stages, fixed order; partial: gemv_t_partial_size doubles) and t = B x for row-major B
+int gemv_t_partial_size(int rows, int cols);
+void launch_gemv_t(int rows, int cols, int64_t ld, const double* B, const double* u, double alpha, double* y, double* partial,
+                   cudaStream_t s);
+void launch_gemv_n(int rows, int cols, int64_t ld, const double* B, const double* x, double* t, cudaStream_t s);
 void launch_add_diagonal_map(int n, double* S, const DenseMap& map, double lambda, cudaStream_t s);
 
 // Context of the dense factorisation / solve (ba_dense.cu). The caller owns the buffers.
@@ -127,8 +132,8 @@ struct DenseCtx {
   std::vector<int64_t> panel_off;    // [nblk + 1] offsets of the packed panels in Lpack
   std::vector<int> panel_h;          // [nblk] leading dimension (even) of each packed panel
   double* S = nullptr;               // ranks * chunk doubles
-  double* Lpack = nullptr;           // panel_off[nblk] doubles: the factor
-  double* Linv = nullptr;            // [nblk * NB / 128][128 * 128] inverses of the diagonal tiles
+  double* Lpack = nullptr;           // panel_off[nblk] doubles: the factor; each panel is followed by the explicit
+                                     // inverses of its NB / 128 diagonal tiles ([128 * 128] each)
   double* tmp = nullptr;             // [n] intermediate of the triangular solves
   int64_t* d_panel_off = nullptr;    // device copies for the backward step
   int* d_panel_h = nullptr;
@@ -138,7 +143,6 @@ struct DenseCtx {
   // broadcast of `count` doubles from rank `root` on stream s (multi-GPU only)
   int (*bcast)(double* buf, size_t count, int root, cudaStream_t s, void* user) = nullptr;
   void* user = nullptr;
-  bool bcast_linv = true;
 };
 int dense_plan(DenseCtx* d, int n, int nb, int rank, int ranks);
 int dense_factor(DenseCtx* d);
