@@ -682,10 +682,12 @@ int dense_factor(DenseCtx* d) {
   cudaStreamWaitEvent(sp, d->ev_misc, 0);
 
   // trailing update of the block columns [j_first, j_last] by panel k (single launch when they are contiguous in S)
-  auto update = [&](int k, int j_first, int j_last, cudaStream_t st, bool leave_sms) -> int {
+  // col_lo / col_hi: optional sub-range of columns (relative to the first block) for the split look-ahead
+  auto update = [&](int k, int j_first, int j_last, cudaStream_t st, bool leave_sms, int col_lo = 0, int col_hi = -1) -> int {
     const int k0 = k * NB, kw = std::min(NB, n - k0);
-    const int j0 = j_first * NB;
-    const int jn = std::min(n, (j_last + 1) * NB) - j0;
+    const int j0 = j_first * NB + col_lo;
+    const int jend = (col_hi < 0) ? std::min(n, (j_last + 1) * NB) : std::min(n, j_first * NB + col_hi);
+    const int jn = jend - j0;
     if (jn <= 0) return 0;
     GemmArgs g{};
     g.M = n - j0;
@@ -703,17 +705,25 @@ int dense_factor(DenseCtx* d) {
     return launch_dgemm_nt(g, /*lower=*/true, /*scatter=*/false, st, leave_sms);
   };
 
+  bool need_half2 = false;  // block k's columns 128.. were updated by a second look-ahead launch (event ev_half2)
+  int half2_slot = 0;
   for (int k = 0; k < d->nblk; ++k) {
     const int k0 = k * NB, kw = std::min(NB, n - k0), hk = d->panel_h[k], hlive = n - k0;
     double* P = d->Lpack + d->panel_off[k];
+    if (owner(k) != me) need_half2 = false;
     if (owner(k) == me) {
-      // pack the (fully updated) block column into its panel, then factor it in place
+      // pack the (fully updated) block column into its panel, then factor it in place. With the split
+      // look-ahead the columns beyond the first 128 are packed once their update has landed.
+      const int kw1 = need_half2 ? std::min(kw, PT) : kw;
       cudaMemcpy2DAsync(P, static_cast<size_t>(hk) * sizeof(double), d->S + d->map.col_offset(k0) + k0,
-                        static_cast<size_t>(d->map.ld) * sizeof(double), static_cast<size_t>(hlive) * sizeof(double), kw,
+                        static_cast<size_t>(d->map.ld) * sizeof(double), static_cast<size_t>(hlive) * sizeof(double), kw1,
                         cudaMemcpyDeviceToDevice, sp);
       for (int sub = 0; sub < sub_n; ++sub) {
         const int c0 = sub * PT;
         if (c0 >= kw) break;
+        if (sub == 1 && need_half2) {
+          // (the in-panel update below writes these columns: they must be packed before it; see the wait there)
+        }
         const int live = std::min(PT, kw - c0);
         double* tile = P + static_cast<int64_t>(c0) * hk + c0;
         double* Li = P + static_cast<int64_t>(hk) * NB + static_cast<int64_t>(sub) * PT * PT;
@@ -737,6 +747,12 @@ int dense_factor(DenseCtx* d) {
           g.b_aligned = gemm_operand_aligned(g.B, g.ldb);
           if (launch_dgemm_nt(g, false, false, sp)) return 1;
           const int rest = kw - c0 - PT;  // remaining columns of this panel
+          if (sub == 0 && need_half2 && kw > PT) {
+            cudaStreamWaitEvent(sp, d->ev_half2[half2_slot], 0);
+            cudaMemcpy2DAsync(P + static_cast<int64_t>(PT) * hk, static_cast<size_t>(hk) * sizeof(double),
+                              d->S + d->map.col_offset(k0 + PT) + k0, static_cast<size_t>(d->map.ld) * sizeof(double),
+                              static_cast<size_t>(hlive) * sizeof(double), kw - PT, cudaMemcpyDeviceToDevice, sp);
+          }
           if (rest > 0) {
             GemmArgs u{};
             u.M = below;
@@ -756,6 +772,10 @@ int dense_factor(DenseCtx* d) {
         }
       }
     }
+    if (owner(k) == me) {
+      if (need_half2 && kw <= PT) cudaStreamWaitEvent(sp, d->ev_half2[half2_slot], 0);  // nothing to pack, but order the streams
+      need_half2 = false;
+    }
     if (R > 1) {
       // the packed panel and the inverses of its diagonal tiles (stored right behind it) travel together
       if (d->bcast(P, static_cast<size_t>(hk) * NB + static_cast<size_t>(sub_n) * PT * PT, owner(k), sp, d->user)) return 1;
@@ -767,9 +787,17 @@ int dense_factor(DenseCtx* d) {
     cudaStreamWaitEvent(sm, d->ev_ready[k & 1], 0);
     int first_rest = k + 1;
     if (k + 1 < d->nblk && owner(k + 1) == me) {
-      if (update(k, k + 1, k + 1, sm, false)) return 1;
+      // split in two: the panel stream may start on the first 128 columns of block k + 1 while the others
+      // are still being updated (it waits for ev_half2 before it touches them, see `need_half2` above)
+      if (update(k, k + 1, k + 1, sm, false, 0, PT)) return 1;
       cudaEventRecord(d->ev_main[k & 1], sm);
       cudaStreamWaitEvent(sp, d->ev_main[k & 1], 0);
+      if (NB > PT) {
+        if (update(k, k + 1, k + 1, sm, false, PT, NB)) return 1;
+        cudaEventRecord(d->ev_half2[k & 1], sm);
+        need_half2 = true;
+        half2_slot = k & 1;
+      }
       first_rest = k + 2;
     }
     if (R == 1) {

@@ -446,6 +446,7 @@ int plan_dense(b200ba_handle* h) {
   for (int i = 0; i < 2; ++i) {
     if (!d.ev_ready[i]) CUDA_TRY(h, cudaEventCreateWithFlags(&d.ev_ready[i], cudaEventDisableTiming));
     if (!d.ev_main[i]) CUDA_TRY(h, cudaEventCreateWithFlags(&d.ev_main[i], cudaEventDisableTiming));
+    if (!d.ev_half2[i]) CUDA_TRY(h, cudaEventCreateWithFlags(&d.ev_half2[i], cudaEventDisableTiming));
   }
   if (!d.ev_misc) CUDA_TRY(h, cudaEventCreateWithFlags(&d.ev_misc, cudaEventDisableTiming));
   d.bcast = nccl_bcast_cb;
@@ -1385,6 +1386,7 @@ void b200ba_destroy(b200ba_handle* h) {
   for (int i = 0; i < 2; ++i) {
     if (h->dn.ev_ready[i]) cudaEventDestroy(h->dn.ev_ready[i]);
     if (h->dn.ev_main[i]) cudaEventDestroy(h->dn.ev_main[i]);
+    if (h->dn.ev_half2[i]) cudaEventDestroy(h->dn.ev_half2[i]);
   }
   if (h->dn.ev_misc) cudaEventDestroy(h->dn.ev_misc);
   delete h;
@@ -1882,6 +1884,7 @@ int b200ba_dense_cholesky_solve(int device, int32_t n, int32_t nb, const double*
   for (int i = 0; i < 2; ++i) {
     ok(cudaEventCreateWithFlags(&d.ev_ready[i], cudaEventDisableTiming));
     ok(cudaEventCreateWithFlags(&d.ev_main[i], cudaEventDisableTiming));
+    ok(cudaEventCreateWithFlags(&d.ev_half2[i], cudaEventDisableTiming));
   }
   ok(cudaEventCreateWithFlags(&d.ev_misc, cudaEventDisableTiming));
   ok(cudaEventCreate(&e0));
@@ -1939,6 +1942,7 @@ int b200ba_dense_cholesky_solve(int device, int32_t n, int32_t nb, const double*
   for (int i = 0; i < 2; ++i) {
     if (d.ev_ready[i]) cudaEventDestroy(d.ev_ready[i]);
     if (d.ev_main[i]) cudaEventDestroy(d.ev_main[i]);
+    if (d.ev_half2[i]) cudaEventDestroy(d.ev_half2[i]);
   }
   for (cudaEvent_t e : {d.ev_misc, e0, e1, e2})
     if (e) cudaEventDestroy(e);
