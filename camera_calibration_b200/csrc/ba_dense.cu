@@ -289,7 +289,7 @@ void launch_gemm_variant(const GemmArgs& g, bool lower, bool scatter, unsigned g
 }
 }  // namespace
 
-int launch_dgemm_nt(const GemmArgs& g_in, bool lower, bool scatter, cudaStream_t s, bool leave_sms) {
+int launch_dgemm_nt(const GemmArgs& g_in, bool lower, bool scatter, cudaStream_t s, bool leave_sms, bool one_tile_per_cta) {
   if (g_in.M <= 0 || g_in.N <= 0) return 0;
   static bool configured_dev[64] = {};
   static int sm_count[64] = {};
@@ -324,7 +324,9 @@ int launch_dgemm_nt(const GemmArgs& g_in, bool lower, bool scatter, cudaStream_t
   }
   const int per_sm = (bn == 64) ? 2 : 1;
   const int cap = std::max(1, (sm_count[dev & 63] - (leave_sms ? g_gemm_reserve_sms : 0)) * per_sm);
-  const unsigned grid = static_cast<unsigned>(std::min<int64_t>(n_tiles, cap));
+  // one_tile_per_cta: an ordinary grid (the hardware scheduler can then hand SMs to a higher-priority stream
+  // between tiles) instead of persistent CTAs
+  const unsigned grid = static_cast<unsigned>(one_tile_per_cta ? n_tiles : std::min<int64_t>(n_tiles, cap));
   if (variant == 64 && !g.in_place)
     launch_gemm_variant<64, 16, 4>(g, tri_enum, scatter, grid, s);
   else if (variant == 12816)
@@ -671,6 +673,17 @@ int dense_plan(DenseCtx* d, int n, int nb, int rank, int ranks) {
 
 // Factors the matrix held (lower triangle, storage map d->map) in d->S. On return every rank holds the
 // complete factor in d->Lpack. Work is enqueued on d->s_main / d->s_panel; the caller synchronises.
+//
+// Schedule (right-looking, block columns of NB, owner(k) = k mod R). The whole critical path lives on the
+// high-priority panel stream:
+//     factor(k) -> broadcast(k) -> U(k, k+1) -> [wait rest(k-1)] -> U(k, k+2) -> factor(k+1) -> ...
+// where U(k, j) applies panel k to block column j (each rank only for the blocks it owns). The bulk
+//     rest(k) = U(k, j) for all owned j >= k + 3
+// runs on the main stream as ordinary (non-persistent) grids, so the panel stream's CTAs take over SMs at
+// tile granularity. Block column j thus receives its updates in panel order: rest(k) for k <= j - 3 (main stream,
+// in order), then U(j-2, j) (after the wait for rest(j-3)), then U(j-1, j), then it is factored. rest(k) has a
+// whole iteration of the chain to finish before anything waits for it: per iteration the cost is
+// max(chain, rest) instead of chain + rest.
 int dense_factor(DenseCtx* d) {
   const int n = d->n, NB = d->NB, R = d->ranks, me = d->rank;
   if (n == 0) return 0;
@@ -681,13 +694,12 @@ int dense_factor(DenseCtx* d) {
   cudaEventRecord(d->ev_misc, sm);
   cudaStreamWaitEvent(sp, d->ev_misc, 0);
 
-  // trailing update of the block columns [j_first, j_last] by panel k (single launch when they are contiguous in S)
-  // col_lo / col_hi: optional sub-range of columns (relative to the first block) for the split look-ahead
-  auto update = [&](int k, int j_first, int j_last, cudaStream_t st, bool leave_sms, int col_lo = 0, int col_hi = -1) -> int {
+  // U(k, j_first .. j_last): one launch; owned_only = skip the tiles of column blocks other ranks own
+  auto update = [&](int k, int j_first, int j_last, cudaStream_t st, bool owned_only) -> int {
+    if (j_first >= d->nblk || j_first > j_last) return 0;
     const int k0 = k * NB, kw = std::min(NB, n - k0);
-    const int j0 = j_first * NB + col_lo;
-    const int jend = (col_hi < 0) ? std::min(n, (j_last + 1) * NB) : std::min(n, j_first * NB + col_hi);
-    const int jn = jend - j0;
+    const int j0 = j_first * NB;
+    const int jn = std::min(n, (std::min(j_last, d->nblk - 1) + 1) * NB) - j0;
     if (jn <= 0) return 0;
     GemmArgs g{};
     g.M = n - j0;
@@ -697,33 +709,33 @@ int dense_factor(DenseCtx* d) {
     g.lda = d->panel_h[k];
     g.B = g.A;
     g.ldb = g.lda;
-    g.C = d->S + d->map.col_offset(j0) + j0;
-    g.ldc = d->map.ld;
     g.alpha = -1.0;
     g.beta = 1.0;
     g.a_aligned = g.b_aligned = gemm_operand_aligned(g.A, g.lda);
-    return launch_dgemm_nt(g, /*lower=*/true, /*scatter=*/false, st, leave_sms);
+    if (owned_only) {
+      g.C = d->S;
+      g.map = d->map;
+      g.owned_only = true;
+      g.rank = me;
+      g.col_base = j0;
+    } else {
+      g.C = d->S + d->map.col_offset(j0) + j0;
+      g.ldc = d->map.ld;
+    }
+    return launch_dgemm_nt(g, /*lower=*/true, /*scatter=*/false, st, /*leave_sms=*/false, /*one_tile_per_cta=*/true);
   };
 
-  bool need_half2 = false;  // block k's columns 128.. were updated by a second look-ahead launch (event ev_half2)
-  int half2_slot = 0;
   for (int k = 0; k < d->nblk; ++k) {
     const int k0 = k * NB, kw = std::min(NB, n - k0), hk = d->panel_h[k], hlive = n - k0;
     double* P = d->Lpack + d->panel_off[k];
-    if (owner(k) != me) need_half2 = false;
     if (owner(k) == me) {
-      // pack the (fully updated) block column into its panel, then factor it in place. With the split
-      // look-ahead the columns beyond the first 128 are packed once their update has landed.
-      const int kw1 = need_half2 ? std::min(kw, PT) : kw;
+      // pack the (fully updated) block column into its panel, then factor it in place
       cudaMemcpy2DAsync(P, static_cast<size_t>(hk) * sizeof(double), d->S + d->map.col_offset(k0) + k0,
-                        static_cast<size_t>(d->map.ld) * sizeof(double), static_cast<size_t>(hlive) * sizeof(double), kw1,
+                        static_cast<size_t>(d->map.ld) * sizeof(double), static_cast<size_t>(hlive) * sizeof(double), kw,
                         cudaMemcpyDeviceToDevice, sp);
       for (int sub = 0; sub < sub_n; ++sub) {
         const int c0 = sub * PT;
         if (c0 >= kw) break;
-        if (sub == 1 && need_half2) {
-          // (the in-panel update below writes these columns: they must be packed before it; see the wait there)
-        }
         const int live = std::min(PT, kw - c0);
         double* tile = P + static_cast<int64_t>(c0) * hk + c0;
         double* Li = P + static_cast<int64_t>(hk) * NB + static_cast<int64_t>(sub) * PT * PT;
@@ -747,12 +759,6 @@ int dense_factor(DenseCtx* d) {
           g.b_aligned = gemm_operand_aligned(g.B, g.ldb);
           if (launch_dgemm_nt(g, false, false, sp)) return 1;
           const int rest = kw - c0 - PT;  // remaining columns of this panel
-          if (sub == 0 && need_half2 && kw > PT) {
-            cudaStreamWaitEvent(sp, d->ev_half2[half2_slot], 0);
-            cudaMemcpy2DAsync(P + static_cast<int64_t>(PT) * hk, static_cast<size_t>(hk) * sizeof(double),
-                              d->S + d->map.col_offset(k0 + PT) + k0, static_cast<size_t>(d->map.ld) * sizeof(double),
-                              static_cast<size_t>(hlive) * sizeof(double), kw - PT, cudaMemcpyDeviceToDevice, sp);
-          }
           if (rest > 0) {
             GemmArgs u{};
             u.M = below;
@@ -772,56 +778,23 @@ int dense_factor(DenseCtx* d) {
         }
       }
     }
-    if (owner(k) == me) {
-      if (need_half2 && kw <= PT) cudaStreamWaitEvent(sp, d->ev_half2[half2_slot], 0);  // nothing to pack, but order the streams
-      need_half2 = false;
-    }
     if (R > 1) {
       // the packed panel and the inverses of its diagonal tiles (stored right behind it) travel together
       if (d->bcast(P, static_cast<size_t>(hk) * NB + static_cast<size_t>(sub_n) * PT * PT, owner(k), sp, d->user)) return 1;
     }
     cudaEventRecord(d->ev_ready[k & 1], sp);
-    // look-ahead: the owner of the next block column updates it FIRST (on the main stream, with the whole
-    // GPU), hands it to the panel stream, and only then applies panel k to the rest of its columns. The
-    // panel stream factors block k + 1 on the SMs the persistent rest-update leaves free.
+    // bulk of the trailing update on the main stream: owned blocks >= k + 3
     cudaStreamWaitEvent(sm, d->ev_ready[k & 1], 0);
-    int first_rest = k + 1;
-    if (k + 1 < d->nblk && owner(k + 1) == me) {
-      // split in two: the panel stream may start on the first 128 columns of block k + 1 while the others
-      // are still being updated (it waits for ev_half2 before it touches them, see `need_half2` above)
-      if (update(k, k + 1, k + 1, sm, false, 0, PT)) return 1;
-      cudaEventRecord(d->ev_main[k & 1], sm);
-      cudaStreamWaitEvent(sp, d->ev_main[k & 1], 0);
-      if (NB > PT) {
-        if (update(k, k + 1, k + 1, sm, false, PT, NB)) return 1;
-        cudaEventRecord(d->ev_half2[k & 1], sm);
-        need_half2 = true;
-        half2_slot = k & 1;
-      }
-      first_rest = k + 2;
-    }
-    if (R == 1) {
-      if (first_rest < d->nblk && update(k, first_rest, d->nblk - 1, sm, true)) return 1;
-    } else if (first_rest < d->nblk) {
-      // one launch over the whole trailing matrix; the kernel skips the tiles of column blocks other ranks own
-      const int k0u = k * NB, kwu = std::min(NB, n - k0u), j0 = first_rest * NB;
-      GemmArgs g{};
-      g.M = g.N = n - j0;
-      g.K = kwu;
-      g.A = g.B = d->Lpack + d->panel_off[k] + (j0 - k0u);
-      g.lda = g.ldb = d->panel_h[k];
-      g.C = d->S;
-      g.alpha = -1.0;
-      g.beta = 1.0;
-      g.a_aligned = g.b_aligned = gemm_operand_aligned(g.A, g.lda);
-      g.map = d->map;
-      g.owned_only = true;
-      g.rank = me;
-      g.col_base = j0;
-      if (launch_dgemm_nt(g, true, false, sm, true)) return 1;
+    if (k + 3 < d->nblk && update(k, k + 3, d->nblk - 1, sm, R > 1)) return 1;
+    cudaEventRecord(d->ev_main[k & 1], sm);  // rest(k) done
+    // the two next block columns on the panel stream (critical path)
+    if (k + 1 < d->nblk && owner(k + 1) == me && update(k, k + 1, k + 1, sp, false)) return 1;
+    if (k + 2 < d->nblk && owner(k + 2) == me) {
+      if (k > 0) cudaStreamWaitEvent(sp, d->ev_main[(k - 1) & 1], 0);  // rest(k - 1) has applied panel k - 1 to block k + 2
+      if (update(k, k + 2, k + 2, sp, false)) return 1;
     }
   }
-  // the last panel was factored on the panel stream: join
+  // the tail ran on the panel stream: join
   cudaEventRecord(d->ev_misc, sp);
   cudaStreamWaitEvent(sm, d->ev_misc, 0);
   return cudaGetLastError() == cudaSuccess ? 0 : 1;

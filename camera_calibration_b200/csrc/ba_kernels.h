@@ -111,7 +111,8 @@ inline bool gemm_operand_aligned(const double* p, int64_t ld) {
 // lower: only tiles / entries with i >= j (M == N); scatter: the scatter-subtract epilogue (implies lower).
 // leave_sms: cap the persistent grid at (SM count - reserve) so that concurrently running panel kernels find
 // a free SM at once (set_gemm_sm_reserve; used for the trailing updates of the factorisation).
-int launch_dgemm_nt(const GemmArgs& g, bool lower, bool scatter, cudaStream_t s, bool leave_sms = false);
+int launch_dgemm_nt(const GemmArgs& g, bool lower, bool scatter, cudaStream_t s, bool leave_sms = false,
+                    bool one_tile_per_cta = false);
 void set_gemm_sm_reserve(int n);
 // Cholesky of a 128 x 128 (live size n) column-major diagonal tile in place + Linv [128 x 128, ld 128].
 int launch_potrf_tile(double* A, int64_t lda, int n, double* Linv, int* info, cudaStream_t s);
