@@ -16,6 +16,7 @@
 #include <stdexcept>
 #include <string>
 #include <unordered_map>
+#include <utility>
 #include <vector>
 
 #include "b200ba.h"
@@ -33,6 +34,28 @@ struct SE3d {
   double tx = 0, ty = 0, tz = 0;
 };
 
+// R(q) p + t and the group product (a * b)(p) = a(b(p)), as Sophus::SE3d::operator* does them
+inline Vec3d apply(const SE3d& T, const Vec3d& p) {
+  const double w = T.qw, x = T.qx, y = T.qy, z = T.qz;
+  return Vec3d{(1 - 2 * (y * y + z * z)) * p.x + 2 * (x * y - w * z) * p.y + 2 * (x * z + w * y) * p.z + T.tx,
+               2 * (x * y + w * z) * p.x + (1 - 2 * (x * x + z * z)) * p.y + 2 * (y * z - w * x) * p.z + T.ty,
+               2 * (x * z - w * y) * p.x + 2 * (y * z + w * x) * p.y + (1 - 2 * (x * x + y * y)) * p.z + T.tz};
+}
+inline SE3d compose(const SE3d& a, const SE3d& b) {
+  SE3d r;
+  r.qw = a.qw * b.qw - a.qx * b.qx - a.qy * b.qy - a.qz * b.qz;
+  r.qx = a.qw * b.qx + a.qx * b.qw + a.qy * b.qz - a.qz * b.qy;
+  r.qy = a.qw * b.qy - a.qx * b.qz + a.qy * b.qw + a.qz * b.qx;
+  r.qz = a.qw * b.qz + a.qx * b.qy - a.qy * b.qx + a.qz * b.qw;
+  const double n = std::sqrt(r.qw * r.qw + r.qx * r.qx + r.qy * r.qy + r.qz * r.qz);
+  r.qw /= n; r.qx /= n; r.qy /= n; r.qz /= n;
+  SE3d rot = a;
+  rot.tx = rot.ty = rot.tz = 0;
+  const Vec3d t = apply(rot, Vec3d{b.tx, b.ty, b.tz});
+  r.tx = a.tx + t.x; r.ty = a.ty + t.y; r.tz = a.tz + t.z;
+  return r;
+}
+
 // models/camera_model.h:42-204 (only what the BA path touches)
 class CameraModel {
  public:
@@ -47,6 +70,12 @@ class CameraModel {
   virtual bool GetGridResolution(int* rx, int* ry) const { (void)rx; (void)ry; return false; }
   // flat intrinsics in the layout include/b200ba.h documents
   virtual std::vector<double>& flat_intrinsics() = 0;
+  // camera_model.h:127-129: only non-central models carry metric quantities
+  virtual void Scale(double factor) { (void)factor; }
+  // camera_model.h:182-185
+  Vec2d CenterOfCalibratedArea() const {
+    return Vec2d{0.5 * (m_calibration_min_x + m_calibration_max_x + 1), 0.5 * (m_calibration_min_y + m_calibration_max_y + 1)};
+  }
   int width() const { return m_width; }
   int height() const { return m_height; }
   int calibration_min_x() const { return m_calibration_min_x; }
@@ -112,6 +141,10 @@ class NoncentralGenericModel : public CameraModel {
   int update_parameter_count() const override { return 5 * gw * gh; }
   bool GetGridResolution(int* rx, int* ry) const override { *rx = gw; *ry = gh; return true; }
   std::vector<double>& flat_intrinsics() override { return grids; }
+  // noncentral_generic.cc:148-154: the line origins (second half of `grids`) are metric
+  void Scale(double factor) override {
+    for (size_t i = grids.size() / 2; i < grids.size(); ++i) grids[i] *= factor;
+  }
   static constexpr int IntrinsicsJacobianSize = 5 * 16;
   int gw, gh;
   std::vector<double> grids;
@@ -143,23 +176,40 @@ class Imageset {
   explicit Imageset(int num_cameras) : m_features(num_cameras) {}
   std::vector<PointFeature>& FeaturesOfCamera(int c) { return m_features[c]; }
   const std::vector<PointFeature>& FeaturesOfCamera(int c) const { return m_features[c]; }
+  void SetFilename(const std::string& filename) { m_filename = filename; }
+  const std::string& GetFilename() const { return m_filename; }
  private:
+  std::string m_filename;
   std::vector<std::vector<PointFeature>> m_features;
+};
+
+// dataset.h:45-55: the known layout of one calibration pattern
+struct KnownGeometry {
+  float cell_length_in_meters = 0;
+  // insertion-ordered (feature id, pattern x, pattern y); the reference keeps an unordered_map
+  std::vector<std::pair<int, std::pair<int, int>>> feature_id_to_position;
 };
 
 // dataset.h:131-212
 class Dataset {
  public:
-  explicit Dataset(int num_cameras) : m_num_cameras(num_cameras) {}
+  explicit Dataset(int num_cameras) : m_num_cameras(num_cameras), m_image_sizes(num_cameras, std::make_pair(0, 0)) {}
+  void SetImageSize(int camera_index, int width, int height) { m_image_sizes[camera_index] = std::make_pair(width, height); }
+  std::pair<int, int> GetImageSize(int camera_index) const { return m_image_sizes[camera_index]; }
+  std::vector<KnownGeometry>& known_geometries() { return m_known_geometries; }
+  const std::vector<KnownGeometry>& known_geometries() const { return m_known_geometries; }
   std::shared_ptr<Imageset> NewImageset() {
     m_imagesets.emplace_back(new Imageset(m_num_cameras));
     return m_imagesets.back();
   }
   std::shared_ptr<Imageset> GetImageset(int i) { return m_imagesets[i]; }
+  std::shared_ptr<const Imageset> GetImageset(int i) const { return m_imagesets[i]; }
   int ImagesetCount() const { return static_cast<int>(m_imagesets.size()); }
   int num_cameras() const { return m_num_cameras; }
  private:
   int m_num_cameras;
+  std::vector<std::pair<int, int>> m_image_sizes;
+  std::vector<KnownGeometry> m_known_geometries;
   std::vector<std::shared_ptr<Imageset>> m_imagesets;
 };
 
@@ -172,6 +222,17 @@ struct BAState {
   std::vector<std::shared_ptr<CameraModel>> intrinsics;
   std::vector<Vec3d> points;
   int num_cameras() const { return static_cast<int>(intrinsics.size()); }
+  // ba_state.h:65-67: camera_tr_rig[camera] * rig_tr_global[imageset]
+  SE3d image_tr_global(int camera_index, int imageset_index) const {
+    return compose(camera_tr_rig[camera_index], rig_tr_global[imageset_index]);
+  }
+  // ba_state.cc:60-76: every translation, the points and the models' metric parts
+  void ScaleState(double scaling_factor) {
+    for (SE3d& T : camera_tr_rig) { T.tx *= scaling_factor; T.ty *= scaling_factor; T.tz *= scaling_factor; }
+    for (SE3d& T : rig_tr_global) { T.tx *= scaling_factor; T.ty *= scaling_factor; T.tz *= scaling_factor; }
+    for (Vec3d& p : points) { p.x *= scaling_factor; p.y *= scaling_factor; p.z *= scaling_factor; }
+    for (auto& m : intrinsics) m->Scale(scaling_factor);
+  }
   // ba_state.cc:78-91
   void ComputeFeatureIdToPointsIndex(Dataset* dataset) {
     for (int i = 0; i < dataset->ImagesetCount(); ++i)
