@@ -26,6 +26,7 @@
 #include <cstdlib>
 
 #include "ba_kernels.h"
+#include "ba_tile.cuh"
 
 namespace b200ba {
 
@@ -474,6 +475,41 @@ __global__ void __launch_bounds__(POTRF_THREADS, 1)
   for (int q = 0; q < 4; ++q) out[lane + 32 * q] = x[q];
 }
 
+// The blocked tile step (ba_tile.cuh): factor + inverse in one launch of 8 CTAs.
+struct TileDeviceExec {
+  tile::Thread t;
+  template <class F>
+  __host__ __device__ __forceinline__ void run(F f) {
+#if defined(__CUDA_ARCH__)
+    f(t, static_cast<int>(threadIdx.x));
+    __syncthreads();
+#else
+    (void)f;
+#endif
+  }
+};
+__global__ void __launch_bounds__(tile::THREADS, 1)
+    potrf_trinv_tile_kernel(const double* __restrict__ Ain, int64_t lda_in, int n, double* __restrict__ Lout, int64_t lda_out,
+                            double* __restrict__ Linv, int* __restrict__ info) {
+  extern __shared__ __align__(16) unsigned char tile_smem[];
+  tile::Shared& sh = *reinterpret_cast<tile::Shared*>(tile_smem);
+  TileDeviceExec ex;
+  tile::potrf_trinv_program(ex, sh, Ain, lda_in, n, Lout, lda_out, Linv, static_cast<int>(blockIdx.x), info);
+}
+// Ain and Lout must not overlap (see ba_tile.cuh).
+int launch_potrf_trinv_tile(const double* Ain, int64_t lda_in, int n, double* Lout, int64_t lda_out, double* Linv, int* info,
+                            cudaStream_t s) {
+  static bool configured_dev[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (!configured_dev[dev & 63]) {
+    cudaFuncSetAttribute(potrf_trinv_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(tile::Shared)));
+    configured_dev[dev & 63] = true;
+  }
+  potrf_trinv_tile_kernel<<<tile::CTAS, tile::THREADS, sizeof(tile::Shared), s>>>(Ain, lda_in, n, Lout, lda_out, Linv, info);
+  return cudaGetLastError() == cudaSuccess ? 0 : 1;
+}
+
 int launch_potrf_tile(double* A, int64_t lda, int n, double* Linv, int* info, cudaStream_t s) {
   static bool configured_dev[64] = {};
   int dev = 0;
@@ -648,6 +684,14 @@ __global__ void __launch_bounds__(TS_THREADS)
 // ------------------------------------------------------------------------------------------
 // host side: blocked right-looking Cholesky with look-ahead, block-cyclic over the ranks
 // ------------------------------------------------------------------------------------------
+// B200BA_PANEL=2 (default): blocked tile kernel + out-of-place panel solves straight out of S; =1: the first
+// version (pack, register-window tile Cholesky, separate inverse launch, in-place solves)
+static int panel_version() {
+  static int v = -1;
+  if (v < 0) v = getenv("B200BA_PANEL") ? atoi(getenv("B200BA_PANEL")) : 1;
+  return v;
+}
+
 int dense_plan(DenseCtx* d, int n, int nb, int rank, int ranks) {
   d->n = n;
   d->rank = rank;
@@ -728,8 +772,59 @@ int dense_factor(DenseCtx* d) {
   for (int k = 0; k < d->nblk; ++k) {
     const int k0 = k * NB, kw = std::min(NB, n - k0), hk = d->panel_h[k], hlive = n - k0;
     double* P = d->Lpack + d->panel_off[k];
-    if (owner(k) == me) {
-      // pack the (fully updated) block column into its panel, then factor it in place
+    if (owner(k) == me && panel_version() == 2) {
+      // Panel factorisation straight out of S: every diagonal tile goes through the blocked factor + inverse launch
+      // (S -> P), the rows below it are solved OUT of place (S -> P, so the product may use the 128 x 64 tiles: a
+      // panel has fewer than 148 row blocks and whole 128 x 128 x 128 tiles per SM made this step throughput-bound
+      // on a third of the machine), and the panel-internal update is applied to the remaining columns in S.
+      const double* Sk = d->S + d->map.col_offset(k0) + k0;  // (i, c) of the block column at Sk[c * ld + i]
+      double* Sk_w = d->S + d->map.col_offset(k0) + k0;
+      const int64_t ld = d->map.ld;
+      for (int sub = 0; sub < sub_n; ++sub) {
+        const int c0 = sub * PT;
+        if (c0 >= kw) break;
+        const int live = std::min(PT, kw - c0);
+        double* tile_out = P + static_cast<int64_t>(c0) * hk + c0;
+        double* Li = P + static_cast<int64_t>(hk) * NB + static_cast<int64_t>(sub) * PT * PT;
+        if (launch_potrf_trinv_tile(Sk + static_cast<int64_t>(c0) * ld + c0, ld, live, tile_out, hk, Li, d->info, sp)) return 1;
+        const int below = hlive - c0 - PT;
+        if (below > 0) {
+          GemmArgs g{};  // rows below: X = A Linv^T
+          g.M = below;
+          g.N = PT;
+          g.K = PT;
+          g.A = Sk + static_cast<int64_t>(c0) * ld + c0 + PT;
+          g.lda = ld;
+          g.B = Li;
+          g.ldb = PT;
+          g.C = tile_out + PT;
+          g.ldc = hk;
+          g.alpha = 1.0;
+          g.beta = 0.0;
+          g.a_aligned = gemm_operand_aligned(g.A, g.lda);
+          g.b_aligned = gemm_operand_aligned(g.B, g.ldb);
+          if (launch_dgemm_nt(g, false, false, sp, false, true)) return 1;
+          const int rest = kw - c0 - PT;  // remaining columns of this panel
+          if (rest > 0) {
+            GemmArgs u{};
+            u.M = below;
+            u.N = rest;
+            u.K = PT;
+            u.A = tile_out + PT;
+            u.lda = hk;
+            u.B = u.A;
+            u.ldb = hk;
+            u.C = Sk_w + static_cast<int64_t>(c0 + PT) * ld + (c0 + PT);
+            u.ldc = ld;
+            u.alpha = -1.0;
+            u.beta = 1.0;
+            u.a_aligned = u.b_aligned = gemm_operand_aligned(u.A, u.lda);
+            if (launch_dgemm_nt(u, true, false, sp, false, true)) return 1;
+          }
+        }
+      }
+    } else if (owner(k) == me) {
+      // first version: pack the (fully updated) block column into its panel, then factor it in place
       cudaMemcpy2DAsync(P, static_cast<size_t>(hk) * sizeof(double), d->S + d->map.col_offset(k0) + k0,
                         static_cast<size_t>(d->map.ld) * sizeof(double), static_cast<size_t>(hlive) * sizeof(double), kw,
                         cudaMemcpyDeviceToDevice, sp);
