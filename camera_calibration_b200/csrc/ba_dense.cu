@@ -688,7 +688,7 @@ __global__ void __launch_bounds__(TS_THREADS)
 // version (pack, register-window tile Cholesky, separate inverse launch, in-place solves)
 static int panel_version() {
   static int v = -1;
-  if (v < 0) v = getenv("B200BA_PANEL") ? atoi(getenv("B200BA_PANEL")) : 1;
+  if (v < 0) v = getenv("B200BA_PANEL") ? atoi(getenv("B200BA_PANEL")) : 2;
   return v;
 }
 
@@ -734,6 +734,9 @@ int dense_factor(DenseCtx* d) {
   const int sub_n = NB / PT;
   cudaStream_t sm = d->s_main, sp = d->s_panel;
   auto owner = [&](int k) { return k % R; };
+  // B200BA_AUX=0 keeps the second look-ahead update on the panel stream
+  static const bool aux_enabled = !(getenv("B200BA_AUX") && atoi(getenv("B200BA_AUX")) == 0);
+  const bool use_aux = aux_enabled && R == 1 && d->s_aux != nullptr;
   // S is ready when everything queued on s_main so far has run
   cudaEventRecord(d->ev_misc, sm);
   cudaStreamWaitEvent(sp, d->ev_misc, 0);
@@ -882,6 +885,20 @@ int dense_factor(DenseCtx* d) {
     cudaStreamWaitEvent(sm, d->ev_ready[k & 1], 0);
     if (k + 3 < d->nblk && update(k, k + 3, d->nblk - 1, sm, R > 1)) return 1;
     cudaEventRecord(d->ev_main[k & 1], sm);  // rest(k) done
+    if (use_aux) {
+      // one GPU: U(k, k + 2) is not needed before factor(k + 1) -- it only sat on the panel stream because the stream
+      // serialises. It runs beside the next panel factorisation on a third (high-priority) stream; the panel stream
+      // picks it up again before U(k + 1, k + 2).
+      if (k >= 1) cudaStreamWaitEvent(sp, d->ev_half2[(k - 1) & 1], 0);  // U(k - 1, k + 1) before U(k, k + 1)
+      if (k + 1 < d->nblk && update(k, k + 1, k + 1, sp, false)) return 1;
+      if (k + 2 < d->nblk) {
+        cudaStreamWaitEvent(d->s_aux, d->ev_ready[k & 1], 0);
+        if (k > 0) cudaStreamWaitEvent(d->s_aux, d->ev_main[(k - 1) & 1], 0);  // rest(k - 1) has applied panel k - 1 to block k + 2
+        if (update(k, k + 2, k + 2, d->s_aux, false)) return 1;
+      }
+      cudaEventRecord(d->ev_half2[k & 1], d->s_aux);
+      continue;
+    }
     // the two next block columns on the panel stream (critical path)
     if (k + 1 < d->nblk && owner(k + 1) == me && update(k, k + 1, k + 1, sp, false)) return 1;
     if (k + 2 < d->nblk && owner(k + 2) == me) {
@@ -889,6 +906,7 @@ int dense_factor(DenseCtx* d) {
       if (update(k, k + 2, k + 2, sp, false)) return 1;
     }
   }
+  if (use_aux && d->nblk >= 1) cudaStreamWaitEvent(sp, d->ev_half2[(d->nblk - 1) & 1], 0);
   // the tail ran on the panel stream: join
   cudaEventRecord(d->ev_misc, sp);
   cudaStreamWaitEvent(sm, d->ev_misc, 0);

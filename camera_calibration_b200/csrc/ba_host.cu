@@ -176,6 +176,7 @@ struct b200ba_handle {
   int dense_planned_ranks = 0, dense_planned_n = -1;
   int dense_nb = 256;                   // column-block width of the factorisation (B200BA_DENSE_NB, multiple of 128)
   cudaStream_t panel_stream = nullptr;  // panel factorisations + broadcasts (look-ahead)
+  cudaStream_t aux_stream = nullptr;    // second look-ahead update of the single-GPU factorisation
   int* d_ident_cols = nullptr;          // 0 .. nd - 1 (scatter epilogue of the dense contraction with several ranks)
   double* d_gemv_partial = nullptr;     // slab sums of the B^T u product
 
@@ -443,6 +444,7 @@ int plan_dense(b200ba_handle* h) {
   d.info = h->d_info;
   d.s_main = h->stream;
   d.s_panel = h->panel_stream;
+  d.s_aux = h->aux_stream;
   for (int i = 0; i < 2; ++i) {
     if (!d.ev_ready[i]) CUDA_TRY(h, cudaEventCreateWithFlags(&d.ev_ready[i], cudaEventDisableTiming));
     if (!d.ev_main[i]) CUDA_TRY(h, cudaEventCreateWithFlags(&d.ev_main[i], cudaEventDisableTiming));
@@ -1332,6 +1334,7 @@ int b200ba_create(const b200ba_problem* p, int device, b200ba_handle** out) {
     int lo = 0, hi = 0;
     cudaDeviceGetStreamPriorityRange(&lo, &hi);
     TRYC(cuda_ok(cudaStreamCreateWithPriority(&h->panel_stream, cudaStreamNonBlocking, hi), "cudaStreamCreate"));
+    TRYC(cuda_ok(cudaStreamCreateWithPriority(&h->aux_stream, cudaStreamNonBlocking, hi), "cudaStreamCreate"));
   }
   if (const char* e = getenv("B200BA_GROUPED")) h->force_grouped = atoi(e);
   if (const char* e = getenv("B200BA_COMPACT_J")) h->compact_j = atoi(e) != 0;
@@ -1383,6 +1386,7 @@ void b200ba_destroy(b200ba_handle* h) {
   if (h->stream) cudaStreamDestroy(h->stream);
   if (h->side_stream) cudaStreamDestroy(h->side_stream);
   if (h->panel_stream) cudaStreamDestroy(h->panel_stream);
+  if (h->aux_stream) cudaStreamDestroy(h->aux_stream);
   for (int i = 0; i < 2; ++i) {
     if (h->dn.ev_ready[i]) cudaEventDestroy(h->dn.ev_ready[i]);
     if (h->dn.ev_main[i]) cudaEventDestroy(h->dn.ev_main[i]);
@@ -1881,6 +1885,7 @@ int b200ba_dense_cholesky_solve(int device, int32_t n, int32_t nb, const double*
   cudaDeviceGetStreamPriorityRange(&lo, &hi);
   ok(cudaStreamCreateWithFlags(&d.s_main, cudaStreamNonBlocking));
   ok(cudaStreamCreateWithPriority(&d.s_panel, cudaStreamNonBlocking, hi));
+  ok(cudaStreamCreateWithPriority(&d.s_aux, cudaStreamNonBlocking, hi));
   for (int i = 0; i < 2; ++i) {
     ok(cudaEventCreateWithFlags(&d.ev_ready[i], cudaEventDisableTiming));
     ok(cudaEventCreateWithFlags(&d.ev_main[i], cudaEventDisableTiming));
@@ -1948,6 +1953,7 @@ int b200ba_dense_cholesky_solve(int device, int32_t n, int32_t nb, const double*
     if (e) cudaEventDestroy(e);
   if (d.s_main) cudaStreamDestroy(d.s_main);
   if (d.s_panel) cudaStreamDestroy(d.s_panel);
+  if (d.s_aux) cudaStreamDestroy(d.s_aux);
   return rc;
 }
 

@@ -139,7 +139,7 @@ struct DenseCtx {
   int64_t* d_panel_off = nullptr;    // device copies for the backward step
   int* d_panel_h = nullptr;
   int* info = nullptr;               // device flag: non-positive pivot
-  cudaStream_t s_main = nullptr, s_panel = nullptr;
+  cudaStream_t s_main = nullptr, s_panel = nullptr, s_aux = nullptr;
   cudaEvent_t ev_ready[2] = {nullptr, nullptr}, ev_main[2] = {nullptr, nullptr}, ev_half2[2] = {nullptr, nullptr}, ev_misc = nullptr;
   // broadcast of `count` doubles from rank `root` on stream s (multi-GPU only)
   int (*bcast)(double* buf, size_t count, int root, cudaStream_t s, void* user) = nullptr;
