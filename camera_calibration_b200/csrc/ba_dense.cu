@@ -682,6 +682,141 @@ __global__ void __launch_bounds__(TS_THREADS)
 }
 
 // ------------------------------------------------------------------------------------------
+// triangular solves, second version: the tile product leaves the critical path of the other CTAs
+// ------------------------------------------------------------------------------------------
+// In the step kernels above EVERY CTA first repeats the 128 x 128 product with the inverted diagonal tile (out of
+// L2: 100-200 CTAs x 64-128 KB per launch) before it touches its rows, and every thread keeps only 8 loads in
+// flight. Here the tile's solution arrives through global memory: step t applies y_t to all rows below in 128-row
+// CTAs (32 independent loads per thread and batch), and CTA 0 -- which owns exactly the rows of tile t + 1 --
+// goes on to y_{t+1} = Linv_{t+1} b_{t+1} with the inverse prefetched into shared memory by cp.async while the
+// row update runs. One wave of at most 102 CTAs; nothing is computed twice.
+constexpr int TS2_THREADS = 256;
+constexpr int TS2_LD = PT + 2;  // pitch of the staged inverse (16-byte aligned columns)
+constexpr size_t kTs2Smem = static_cast<size_t>(PT) * TS2_LD * sizeof(double);
+
+__device__ __forceinline__ void stage_tile_async(double* dst, const double* __restrict__ src) {
+  // 128 x 128 doubles, column c -> dst[c * TS2_LD ..]: 8192 chunks of 16 bytes
+  for (int ch = threadIdx.x; ch < PT * PT / 2; ch += TS2_THREADS) {
+    const int c = ch >> 6, i2 = (ch & 63) * 2;
+    cp_async16(dst + c * TS2_LD + i2, src + c * PT + i2, 16);
+  }
+  cp_async_commit();
+}
+
+// forward: b_below -= L(below, tile t) y_t ; CTA 0: y_{t+1} = Linv_{t+1} b_{t+1}
+__global__ void __launch_bounds__(TS2_THREADS, 1)
+    trsv_forward2_kernel(const double* __restrict__ Lp /* L(row 0 below the tile, column 0 of the tile) */, int64_t hk,
+                         int rows_below, const double* __restrict__ y_t, double* __restrict__ b_below,
+                         const double* __restrict__ Linv_next, double* __restrict__ y_next) {
+  extern __shared__ __align__(16) double ts2_smem[];
+  __shared__ double ys[PT], part[2][PT], bs[PT];
+  const int tid = threadIdx.x;
+  const bool chain = blockIdx.x == 0;
+  if (chain) stage_tile_async(ts2_smem, Linv_next);
+  if (tid < PT) ys[tid] = y_t[tid];
+  const int row = tid & (PT - 1), half = tid >> 7;
+  const int r = blockIdx.x * PT + row;
+  const bool live_row = r < rows_below;
+  const double* lp = Lp + static_cast<int64_t>(half * 64) * hk + (live_row ? r : 0);
+  __syncthreads();
+  double acc0 = 0.0, acc1 = 0.0;
+#pragma unroll
+  for (int batch = 0; batch < 2; ++batch) {
+    double l[32];
+#pragma unroll
+    for (int q = 0; q < 32; ++q) l[q] = live_row ? lp[static_cast<int64_t>(batch * 32 + q) * hk] : 0.0;
+    const double* yc = ys + half * 64 + batch * 32;
+#pragma unroll
+    for (int q = 0; q < 32; q += 2) {
+      acc0 = fma(l[q], yc[q], acc0);
+      acc1 = fma(l[q + 1], yc[q + 1], acc1);
+    }
+  }
+  part[half][row] = acc0 + acc1;
+  __syncthreads();
+  if (half == 0) {
+    const double v = live_row ? b_below[r] - (part[0][row] + part[1][row]) : 0.0;
+    if (chain)
+      bs[row] = v;
+    else if (live_row)
+      b_below[r] = v;
+  }
+  if (!chain) return;
+  cp_async_wait<0>();
+  __syncthreads();
+  // y_next(i) = sum_{c <= i} Linv(i, c) b(c): even / odd c per half
+  double s0 = 0.0, s1 = 0.0;
+  for (int c = half; c <= row; c += 4) {
+    s0 = fma(ts2_smem[c * TS2_LD + row], bs[c], s0);
+    if (c + 2 <= row) s1 = fma(ts2_smem[(c + 2) * TS2_LD + row], bs[c + 2], s1);
+  }
+  part[half][row] = s0 + s1;
+  __syncthreads();
+  if (half == 0 && live_row) y_next[row] = part[0][row] + part[1][row];
+}
+
+// backward: y_c -= sum_{i in tile t} L(i, c) x_i for the columns c left of the tile; CTA 0 (the columns of tile
+// t - 1): x_{t-1} = Linv_{t-1}^T y_{t-1}. One warp per column (the rows of a column are contiguous), 16 columns
+// per warp in two batches of 8 (32 loads in flight per lane).
+__global__ void __launch_bounds__(TS2_THREADS, 1)
+    trsv_backward2_kernel(const double* __restrict__ Lpack, const int64_t* __restrict__ panel_off,
+                          const int* __restrict__ panel_h, int NB, int r0, int live, const double* __restrict__ x_t,
+                          double* __restrict__ y /* full vector */, const double* __restrict__ Linv_prev,
+                          double* __restrict__ x_prev /* at row r0 - 128 */) {
+  extern __shared__ __align__(16) double ts2_smem[];
+  __shared__ double xs[PT], ysm[PT], part[2][PT];
+  const int tid = threadIdx.x;
+  const bool chain = blockIdx.x == 0;
+  if (chain) stage_tile_async(ts2_smem, Linv_prev);
+  if (tid < PT) xs[tid] = (tid < live) ? x_t[tid] : 0.0;
+  __syncthreads();
+  const int warp = tid >> 5, lane = tid & 31;
+  const int cbase = r0 - PT * (static_cast<int>(blockIdx.x) + 1);  // this CTA's 128 columns: cbase .. cbase + 127
+#pragma unroll
+  for (int batch = 0; batch < 2; ++batch) {
+    double l[8][4];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const int c = cbase + warp * 16 + batch * 8 + q;
+      const int k = c / NB;
+      const double* col = Lpack + panel_off[k] + static_cast<int64_t>(c - k * NB) * panel_h[k] + (r0 - k * NB);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) l[q][u] = (lane + 32 * u < live) ? col[lane + 32 * u] : 0.0;
+    }
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      double acc = 0.0;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) acc = fma(l[q][u], xs[lane + 32 * u], acc);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+      if (lane == 0) {
+        const int c = cbase + warp * 16 + batch * 8 + q;
+        const double v = y[c] - acc;
+        if (chain)
+          ysm[c - cbase] = v;
+        else
+          y[c] = v;
+      }
+    }
+  }
+  if (!chain) return;
+  cp_async_wait<0>();
+  __syncthreads();
+  // x_prev(j) = sum_{i >= j} Linv(i, j) y(i): column j of the staged inverse, even / odd i per half
+  const int j = tid & (PT - 1), half = tid >> 7;
+  double s0 = 0.0, s1 = 0.0;
+  const double* colj = ts2_smem + j * TS2_LD;
+  for (int i = j + half; i < PT; i += 4) {
+    s0 = fma(colj[i], ysm[i], s0);
+    if (i + 2 < PT) s1 = fma(colj[i + 2], ysm[i + 2], s1);
+  }
+  part[half][j] = s0 + s1;
+  __syncthreads();
+  if (half == 0) x_prev[j] = part[0][j] + part[1][j];
+}
+
+// ------------------------------------------------------------------------------------------
 // host side: blocked right-looking Cholesky with look-ahead, block-cyclic over the ranks
 // ------------------------------------------------------------------------------------------
 // B200BA_PANEL=2 (default): blocked tile kernel + out-of-place panel solves straight out of S; =1: the first
@@ -923,6 +1058,39 @@ int dense_solve(DenseCtx* d, double* b) {
     const int k = (t * PT) / NB, sub = (t * PT - k * NB) / PT;
     return d->Lpack + d->panel_off[k] + static_cast<int64_t>(d->panel_h[k]) * NB + static_cast<int64_t>(sub) * PT * PT;
   };
+  static int version = -1;  // B200BA_TRSV=1: the first version (one launch per tile, every CTA repeats the tile product)
+  if (version < 0) version = getenv("B200BA_TRSV") ? atoi(getenv("B200BA_TRSV")) : 1;
+  if (version == 2) {
+    static bool configured_dev[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!configured_dev[dev & 63]) {
+      cudaFuncSetAttribute(trsv_forward2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kTs2Smem));
+      cudaFuncSetAttribute(trsv_backward2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kTs2Smem));
+      configured_dev[dev & 63] = true;
+    }
+    const int T = d->ntiles;
+    // forward: y_0 = Linv_0 b_0, then one launch per tile that has rows below it
+    trsv_store_tile_kernel<<<1, PT, 0, sm>>>(linv_of(0), b, std::min(PT, n), d->tmp, false);
+    for (int t = 0; t + 1 < T; ++t) {
+      const int c0 = t * PT, k = c0 / NB, off = c0 - k * NB;
+      const int rows_below = n - c0 - PT;
+      const double* Lp = d->Lpack + d->panel_off[k] + static_cast<int64_t>(off) * d->panel_h[k] + off + PT;
+      trsv_forward2_kernel<<<(rows_below + PT - 1) / PT, TS2_THREADS, kTs2Smem, sm>>>(Lp, d->panel_h[k], rows_below, d->tmp + c0,
+                                                                                      b + c0 + PT, linv_of(t + 1), d->tmp + c0 + PT);
+    }
+    // backward: x_{T-1} = Linv^T y_{T-1}, then one launch per tile that has columns to its left
+    {
+      const int r0 = (T - 1) * PT;
+      trsv_store_tile_kernel<<<1, PT, 0, sm>>>(linv_of(T - 1), d->tmp + r0, std::min(PT, n - r0), b + r0, true);
+    }
+    for (int t = T - 1; t >= 1; --t) {
+      const int r0 = t * PT, live = std::min(PT, n - r0);
+      trsv_backward2_kernel<<<r0 / PT, TS2_THREADS, kTs2Smem, sm>>>(d->Lpack, d->d_panel_off, d->d_panel_h, NB, r0, live, b + r0,
+                                                                    d->tmp, linv_of(t - 1), b + r0 - PT);
+    }
+    return cudaGetLastError() == cudaSuccess ? 0 : 1;
+  }
   // forward: L y = b  (y is collected in d->tmp)
   for (int t = 0; t < d->ntiles; ++t) {
     const int c0 = t * PT, live = std::min(PT, n - c0), k = c0 / NB;
