@@ -1059,7 +1059,7 @@ int dense_solve(DenseCtx* d, double* b) {
     return d->Lpack + d->panel_off[k] + static_cast<int64_t>(d->panel_h[k]) * NB + static_cast<int64_t>(sub) * PT * PT;
   };
   static int version = -1;  // B200BA_TRSV=1: the first version (one launch per tile, every CTA repeats the tile product)
-  if (version < 0) version = getenv("B200BA_TRSV") ? atoi(getenv("B200BA_TRSV")) : 1;
+  if (version < 0) version = getenv("B200BA_TRSV") ? atoi(getenv("B200BA_TRSV")) : 2;
   if (version == 2) {
     static bool configured_dev[64] = {};
     int dev = 0;
