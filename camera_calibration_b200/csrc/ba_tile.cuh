@@ -6,18 +6,21 @@
 // ba_dense.cu, still selectable) keeps a 32-column register window per thread and issues 32 shared-memory loads
 // per thread and column step: 100 k cycles per tile, LSU-bound, and a second launch of 45 k cycles for the inverse.
 // Here both are blocked by 16 columns:
-//   * Cholesky: per 16-column panel, 16 column steps on a 128 x 16 register panel (4 entries per thread, one
-//     barrier per step through a double-buffered published column; only a reciprocal, a multiply and one FMA sit
-//     between two barriers), then ONE rank-16 update of the trailing lower triangle with a register block of
-//     2 rows x 8 columns per thread (at most 420 blocks: a single pass).
+//   * Cholesky: per 16-column panel, 16 software-pipelined column steps on a 128 x 16 register panel (4 entries per
+//     thread, one barrier per step through a double-buffered published column; only the pivot load, a reciprocal
+//     seed with one cubic correction and the update of the ONE entry published next sit between two barriers, see
+//     panel_step), then ONE rank-16 update of the trailing lower triangle with a register block of 2 rows x 8
+//     columns per thread (at most 420 blocks: a single pass). Measured: 47 us per tile for factor + inverse
+//     (first version 50 + 22 us in two launches); the chain is bound by the dependent FP64 latency.
 //   * inverse: the launch has 8 CTAs; each repeats the (deterministic) factorisation and then solves L X = E_J
 //     for its own 16 columns J by block forward substitution with the explicitly inverted 16 x 16 diagonal
 //     blocks. CTA 0 stores the factor. One launch instead of two, no reload of the tile.
 //
 // The program is a template over an executor: on the device `run(f)` calls f for this thread and then
 // __syncthreads(); the host executor of tests/tile_emulation.cc calls f for all 512 threads of the CTA in a
-// forward or reversed order -- every phase must give the same result in both (no thread may read what another
-// thread writes in the same phase), which pins the barrier placement and all index arithmetic without a GPU.
+// forward, reversed or shuffled order -- every phase must give the same result in all of them (no thread may read
+// what another thread writes in the same phase), which pins the barrier placement and all index arithmetic
+// without a GPU.
 #pragma once
 
 #include <cmath>
