@@ -542,7 +542,7 @@ def run_b200(args):
             except Exception:
                 pass
         line["dense_path"] = ("in-tree sm_100a kernels: DMMA contraction with scatter epilogue, blocked Cholesky on packed "
-                              "panels, packed triangular solves (ba_dense.cu)") if os.environ.get("B200BA_DENSE", "own") not in ("lib", "0") \
+                              "panels (fused tile factor + inverse launch), packed triangular solves (ba_dense.cu, ba_tile.cuh)") if os.environ.get("B200BA_DENSE", "own") not in ("lib", "0") \
             else "cuBLAS dsyrk + cuSOLVER potrf / potrs (B200BA_DENSE=lib)"
     adj.close()
     adj = None
