@@ -25,6 +25,26 @@ static void pinhole(CameraModel&, const std::vector<double>& lp, std::vector<dou
   }
 }
 
+// stand-ins for the device calls of ResampleModel (same formulas in the Python test): un-projection of a pinhole with
+// f = 400, c = (320, 240), undefined in a strip on the left and in a small square; the fit leaves the grid as initialised
+static void pinhole_unproject(CameraModel&, const std::vector<double>& px, std::vector<double>* dirs, std::vector<int32_t>* ok) {
+  const size_t n = px.size() / 2;
+  dirs->assign(3 * n, 0.0);
+  ok->assign(n, 0);
+  for (size_t i = 0; i < n; ++i) {
+    const double x = px[2 * i], y = px[2 * i + 1];
+    const double dx = (x - 320.0) / 400.0, dy = (y - 240.0) / 400.0;
+    const double norm = std::sqrt(dx * dx + dy * dy + 1.0);
+    (*dirs)[3 * i] = dx / norm;
+    (*dirs)[3 * i + 1] = dy / norm;
+    (*dirs)[3 * i + 2] = 1.0 / norm;
+    (*ok)[i] = (x < 7.0 || (x > 200 && x < 204 && y > 100 && y < 104)) ? 0 : 1;
+  }
+}
+static void no_fit(CentralGenericModel&, const std::vector<double>& gp, const std::vector<double>& d, int) {
+  std::printf("samples %zu %zu\n", gp.size() / 2, d.size() / 3);
+}
+
 int main(int argc, char** argv) {
   if (argc < 2) return 2;
   const std::string mode = argv[1];
@@ -67,6 +87,34 @@ int main(int argc, char** argv) {
       for (bool u : st.image_used) std::printf(" %d", u ? 1 : 0);
       std::printf("\n");
       return SaveDataset(argv[6], *ds) ? 0 : 1;
+    }
+    if (mode == "gridres" && argc == 7) {
+      int rx, ry, lx, ly;
+      ComputeGridResolution(std::atoi(argv[2]), std::atoi(argv[3]), std::atoi(argv[4]), std::atoi(argv[5]), &rx, &ry);
+      CalcGridResolutionForLevel(std::atoi(argv[6]), rx, ry, &lx, &ly);
+      std::printf("%d %d %d %d\n", rx, ry, lx, ly);
+      return 0;
+    }
+    if (mode == "bounds" && argc == 4) {
+      std::shared_ptr<Dataset> ds;
+      if (!LoadDataset(argv[2], &ds)) { std::printf("load failed\n"); return 1; }
+      int a, b, c, d;
+      std::vector<bool> used(ds->ImagesetCount(), true);
+      used[1] = false;
+      ComputeIntegerBoundingRectForFeatures(*ds, std::atoi(argv[3]), used, &a, &b, &c, &d);
+      std::printf("%d %d %d %d\n", a, b, c, d);
+      return 0;
+    }
+    if (mode == "resample" && argc == 8) {
+      // resample <model.yaml> <target type: 0 central, 1 non-central> <res x> <res y> <out.yaml> <unused>
+      std::shared_ptr<CameraModel> model = LoadCameraModel(argv[2]);
+      if (!model) { std::printf("load failed\n"); return 1; }
+      const CameraModel::Type target = std::atoi(argv[3]) == 0 ? CameraModel::Type::CentralGeneric : CameraModel::Type::NoncentralGeneric;
+      std::shared_ptr<CameraModel> fresh = ResampleModel(*model, model->calibration_min_x(), model->calibration_min_y(), model->calibration_max_x(),
+                                                         model->calibration_max_y(), target, std::atoi(argv[4]), std::atoi(argv[5]),
+                                                         pinhole_unproject, no_fit);
+      if (!fresh) { std::printf("not resampled\n"); return 0; }
+      return SaveCameraModel(*fresh, argv[6]) ? 0 : 1;
     }
     if (mode == "malformed" && argc == 3) {
       // every loader must answer false (not crash, not throw) on this file

@@ -155,3 +155,64 @@ def test_cpp_delete_outlier_features_matches_python(exe, tmp_path):
     for i in range(ref_ds.ImagesetCount()):
         a, b = ref_ds.GetImageset(i).FeaturesOfCamera(0), got.GetImageset(i).FeaturesOfCamera(0)
         assert np.array_equal(a["id"], b["id"]) and np.array_equal(a["xy"], b["xy"])
+
+
+def test_cpp_pyramid_helpers_match_python(exe, tmp_path):
+    from camera_calibration_b200 import io, pipeline
+    for w, h, ext, approx, level in ((640, 480, 1, 50, 0), (1207, 933, 1, 37, 2), (1999, 1499, 0, 30, 4), (410, 290, 1, 20, 1)):
+        rx, ry = pipeline.ComputeGridResolution(w, h, ext, approx)
+        lx, ly = pipeline.CalcGridResolutionForLevel(level, rx, ry)
+        assert _run(exe, "gridres", str(w), str(h), str(ext), str(approx), str(level)).split() == [str(v) for v in (rx, ry, lx, ly)]
+    ds, st = _problem(4, n_imagesets=5, lattice=(8, 7), image_size=(410, 290))
+    io.SaveDataset(str(tmp_path / "dataset.bin"), ds)
+    used = [True] * ds.ImagesetCount()
+    used[1] = False
+    for cam in (0, 1):
+        rect = pipeline.ComputeIntegerBoundingRectForFeatures(ds, cam, used)
+        assert _run(exe, "bounds", str(tmp_path / "dataset.bin"), str(cam)).split() == [str(int(v)) for v in rect]
+
+
+def _pinhole_unproject(model, px):
+    """The stand-in of tests/io_example.cc for the device un-projection."""
+    x, y = px[:, 0], px[:, 1]
+    d = np.stack([(x - 320.0) / 400.0, (y - 240.0) / 400.0, np.ones_like(x)], -1)
+    d = d / np.sqrt(d[:, 0] ** 2 + d[:, 1] ** 2 + 1.0)[:, None]
+    ok = ~((x < 7.0) | ((x > 200) & (x < 204) & (y > 100) & (y < 104)))
+    return d, None, ok
+
+
+@pytest.mark.parametrize("source,target", [("central", 0), ("central", 1), ("noncentral", 1), ("noncentral", 0)])
+def test_cpp_resample_model_matches_python(exe, tmp_path, source, target):
+    """ResampleModel (calibration.cc:373-522): the host logic -- grid initialisation from the dense direction image
+    incl. the closest-valid-pixel search and the linear extrapolation, the sample selection, the bilinear re-sampling of
+    a non-central model -- with the two device calls replaced by the same stand-ins on both sides."""
+    from camera_calibration_b200 import api, io, pipeline
+    ds, st = _problem(2 if source == "central" else 3, n_imagesets=4, lattice=(8, 7), image_size=(410, 290))
+    model = st.intrinsics[0]
+    io.SaveCameraModel(model, str(tmp_path / "model.yaml"))
+    model = io.LoadCameraModel(str(tmp_path / "model.yaml"))  # what the C++ side reads (14 digits, re-normalised)
+    T = api.CameraModel.Type
+    samples = []
+
+    def no_fit(gw, gh, grid, gp, d, iterations):
+        samples.append((len(gp), len(d)))
+        return grid, None
+
+    ok, new = pipeline.ResampleModel(model, np.array([1.0, 0, 0, 0, 0, 0, 0]), model.calibration_min_x(), model.calibration_min_y(),
+                                     model.calibration_max_x(), model.calibration_max_y(), T.CentralGeneric if target == 0 else T.NoncentralGeneric,
+                                     13, 11, fit_fn=no_fit, unproject_many=_pinhole_unproject)
+    out = _run(exe, "resample", str(tmp_path / "model.yaml"), str(target), "13", "11", str(tmp_path / "new.yaml"), "-")
+    if not ok:
+        assert "not resampled" in out
+        return
+    if samples:
+        assert f"samples {samples[0][0]} {samples[0][1]}" in out
+    # un-normalised comparison of what was written: read the flow lists directly (LoadCameraModel re-normalises directions)
+    import yaml
+    got = yaml.safe_load(open(tmp_path / "new.yaml"))
+    assert got["type"] == type(new).__name__ and (got["grid_width"], got["grid_height"]) == (13, 11)
+    if isinstance(new, api.CentralGenericModel):
+        assert np.allclose(np.array(got["grid"]), new.grid().reshape(-1), rtol=0, atol=2e-14)
+    else:
+        assert np.allclose(np.array(got["direction_grid"]), new.direction_grid().reshape(-1), rtol=0, atol=2e-14)
+        assert np.allclose(np.array(got["point_grid"]), new.point_grid().reshape(-1), rtol=0, atol=2e-14)
