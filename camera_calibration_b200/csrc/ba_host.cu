@@ -174,7 +174,7 @@ struct b200ba_handle {
   bool own_dense = true;
   DenseCtx dn;
   int dense_planned_ranks = 0, dense_planned_n = -1;
-  int dense_nb = 256;                   // column-block width of the factorisation (B200BA_DENSE_NB, multiple of 128)
+  int dense_nb = 0;                     // column-block width of the factorisation (B200BA_DENSE_NB, multiple of 128); 0 = by rank count
   cudaStream_t panel_stream = nullptr;  // panel factorisations + broadcasts (look-ahead)
   cudaStream_t aux_stream = nullptr;    // second look-ahead update of the single-GPU factorisation
   int* d_ident_cols = nullptr;          // 0 .. nd - 1 (scatter epilogue of the dense contraction with several ranks)
@@ -422,7 +422,10 @@ int plan_dense(b200ba_handle* h) {
   const int nd = h->L.nd;
   if (h->dense_planned_n == nd && h->dense_planned_ranks == h->n_ranks) return 0;
   DenseCtx& d = h->dn;
-  dense_plan(&d, nd, h->dense_nb, h->rank, h->n_ranks);
+  // one GPU: 512-wide block columns (fewer, longer panels: 28.6 vs 29.5 ms at n_d = 13 080, profiles/r02zc_dense_timing.log);
+  // several ranks: 256, so that the block-cyclic distribution has enough blocks per rank and the broadcasts stay short
+  const int nb = h->dense_nb > 0 ? h->dense_nb : (h->n_ranks == 1 ? 512 : 256);
+  dense_plan(&d, nd, nb, h->rank, h->n_ranks);
   if (dev_alloc(h, &h->d_S, static_cast<size_t>(std::max<int64_t>(1, d.chunk * h->n_ranks)))) return 1;
   d.S = h->d_S;
   if (dev_alloc(h, &d.Lpack, static_cast<size_t>(std::max<int64_t>(1, d.panel_off[d.nblk])))) return 1;
